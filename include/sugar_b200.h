@@ -1,0 +1,173 @@
+/*
+ * sugar_b200.h -- C ABI of libsugar_b200.so: a Blackwell (sm_100a) differentiable
+ * Gaussian-splat rasterizer + SuGaR density/SDF field evaluator.
+ *
+ * Drop-in boundary.  These entry points are what a binding of the reference's rasterizer
+ * path would call instead of `CudaRasterizer::Rasterizer::{forward,backward,markVisible}`
+ * (gaussian_splatting/submodules/diff-gaussian-rasterization/cuda_rasterizer/rasterizer.h:20-85),
+ * and instead of the PyTorch ops behind `SuGaR.get_field_values` / `SuGaR.compute_density`
+ * (sugar_scene/sugar_model.py:1247-1316, 1345-1368).  Plain pointers and sizes only: every
+ * pointer is a DEVICE pointer unless stated otherwise; the library allocates nothing that
+ * outlives a call except one pinned 4 KiB page + one event per device (the num_rendered
+ * read-back).  All work is enqueued on the caller's `stream` (a cudaStream_t passed as void*).
+ *
+ * Every function returns 0 on success or a negative SGR_E* code; sgr_last_error() gives the
+ * thread-local message.  CUDA launch errors surface synchronously only when `debug` is set
+ * (reference: CHECK_CUDA, cuda_rasterizer/auxiliary.h:166-173).
+ */
+#ifndef SUGAR_B200_H_
+#define SUGAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SGR_API __attribute__((visibility("default")))
+#else
+#define SGR_API
+#endif
+
+#define SGR_OK 0
+#define SGR_EINVAL (-1)   /* bad argument (shape, null pointer, ambiguous optionals) */
+#define SGR_ECUDA (-2)    /* CUDA runtime error */
+#define SGR_ENOMEM (-3)   /* an allocator callback returned NULL */
+
+/* Per-view constants: field-for-field `GaussianRasterizationSettings`
+ * (diff_gaussian_rasterization/__init__.py:157-169). */
+typedef struct SgrView {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    const float *bg;         /* f32[3] */
+    float scale_modifier;
+    const float *viewmatrix; /* f32[16], world->view transposed (read column-major) */
+    const float *projmatrix; /* f32[16], full projection transposed */
+    int32_t sh_degree;       /* active degree D, 0..3 */
+    const float *campos;     /* f32[3] */
+    int32_t prefiltered;
+    int32_t debug;
+} SgrView;
+
+/* Per-Gaussian inputs of `_C.rasterize_gaussians` (rasterize_points.h:19-38).  Optional
+ * arrays are NULL when absent, exactly as the reference tests `ptr == nullptr`
+ * (forward.cu:205,241): exactly one of {shs, colors_precomp} and exactly one of
+ * {scales+rotations, cov3D_precomp} must be non-NULL. */
+typedef struct SgrGaussians {
+    int32_t P;                   /* number of Gaussians */
+    int32_t M;                   /* SH coefficients stored per Gaussian (0 if shs == NULL) */
+    const float *means3D;        /* f32[P,3] */
+    const float *opacities;      /* f32[P]   */
+    const float *shs;            /* f32[P,M,3] or NULL */
+    const float *colors_precomp; /* f32[P,3]   or NULL */
+    const float *scales;         /* f32[P,3]   or NULL */
+    const float *rotations;      /* f32[P,4] (w,x,y,z; pre-normalised by the caller) or NULL */
+    const float *cov3D_precomp;  /* f32[P,6]   or NULL */
+} SgrGaussians;
+
+/* Scratch allocator: replaces `std::function<char*(size_t)>` (rasterizer.h:31-34,
+ * rasterize_points.cu:27-33).  Must return device memory aligned to >= 256 bytes that stays
+ * valid until the matching backward has run.  The three buffers are opaque round-trip state. */
+typedef void *(*SgrAlloc)(void *ctx, size_t bytes);
+
+/* Forward: replaces Rasterizer::forward (rasterizer_impl.cu:198-336).
+ *   out_color  f32[3,H,W]  (fully written)
+ *   radii      i32[P]      (fully written; >0 == visible)
+ *   capacity_hint: 0 -> wait for the instance count before sizing the binning buffer (what the
+ *     reference does, rasterizer_impl.cu:281); >0 -> allocate that many instances up front and
+ *     enqueue everything without a host wait, re-running binning+blend only on overflow.
+ *   *num_rendered receives R (number of (Gaussian, tile) instances). */
+SGR_API int sgr_rasterize_forward(const SgrView *view, const SgrGaussians *g,
+                          SgrAlloc geom_alloc, void *geom_ctx,
+                          SgrAlloc binning_alloc, void *binning_ctx,
+                          SgrAlloc image_alloc, void *image_ctx,
+                          float *out_color, int32_t *radii,
+                          int64_t capacity_hint, int64_t *num_rendered, void *stream);
+
+/* Backward: replaces Rasterizer::backward (rasterizer_impl.cu:340-434) together with the
+ * zero-initialised outputs of RasterizeGaussiansBackwardCUDA (rasterize_points.cu:151-159):
+ * every output row is written by the kernels (zeros for culled Gaussians), so the caller may
+ * pass uninitialised memory.  `grad_scratch` must hold sgr_backward_scratch_bytes(P).
+ *   dL_dmeans2D f32[P,3], dL_dcolors f32[P,3], dL_dopacity f32[P,1], dL_dmeans3D f32[P,3],
+ *   dL_dcov3D f32[P,6], dL_dsh f32[P,M,3] (may be NULL when M==0), dL_dscales f32[P,3],
+ *   dL_drotations f32[P,4]. */
+SGR_API int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii,
+                           const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
+                           int64_t num_rendered, const float *dL_dout_color,
+                           float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
+                           float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
+                           float *dL_dscales, float *dL_drotations,
+                           void *grad_scratch, void *stream);
+
+/* markVisible (rasterizer_impl.cu:141-153): present[i] = view-space z > 0.2. */
+SGR_API int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,
+                     const float *projmatrix, uint8_t *present, void *stream);
+
+/* Sizes of the opaque buffers (what `required<T>(P)` is in rasterizer_impl.h:66-72). */
+SGR_API size_t sgr_geometry_bytes(int32_t P);
+SGR_API size_t sgr_binning_bytes(int64_t capacity);
+SGR_API size_t sgr_image_bytes(int32_t width, int32_t height);
+SGR_API size_t sgr_backward_scratch_bytes(int32_t P);
+
+/* Decode the opaque buffers into the reference's named arrays, for parity tests
+ * (GeometryState / BinningState / ImageState, rasterizer_impl.h:30-63).  Any output may be NULL.
+ *   depths f32[P], means2D f32[P,2], conic_opacity f32[P,4], rgb f32[P,3], clamped u8[P,3],
+ *   tiles_touched u32[P]; keys u64[R] = (tile<<32 | depth bits) in sorted order,
+ *   point_list u32[R]; ranges u32[T,2]; final_T f32[H,W]; n_contrib u32[H,W]. */
+SGR_API int sgr_inspect_state(int32_t P, int32_t width, int32_t height, int64_t num_rendered,
+                      const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
+                      float *depths, float *means2D, float *conic_opacity, float *rgb, uint8_t *clamped,
+                      uint32_t *tiles_touched, uint64_t *keys, uint32_t *point_list, uint32_t *ranges,
+                      float *final_T, uint32_t *n_contrib, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SuGaR surface-regularisation field: fused K-neighbour gather + anisotropic density / SDF.
+ * Replaces the PyTorch ops of SuGaR.get_field_values (sugar_model.py:1247-1316, beta_mode
+ * 'average' sugar_model.py:1192-1195) and SuGaR.compute_density (:1345-1368).
+ *   x          f32[N,3]   sample points
+ *   nbr_idx    i64[N,K]   neighbour Gaussian indices per sample (knn_idx[gaussian_idx])
+ *   points f32[P,3], scaling f32[P,3] (activated), quaternions f32[P,4] (normalised, w first),
+ *   strengths f32[P] (sigmoid(densities))
+ * Outputs (any may be NULL): density f32[N] (before the straight-through clamp),
+ *   nbr_opacity f32[N,K], beta f32[N], sdf f32[N].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct SgrFieldParams {
+    int32_t N, K, P;
+    float density_factor;
+    float density_threshold;
+    float opacity_min_clamp; /* 1e-16 in the reference */
+} SgrFieldParams;
+
+/* `scratch` must hold sgr_field_scratch_bytes(P) (packed per-Gaussian records; device memory). */
+SGR_API size_t sgr_field_scratch_bytes(int32_t P);
+
+SGR_API int sgr_field_forward(const SgrFieldParams *p, const float *x, const int64_t *nbr_idx,
+                      const float *points, const float *scaling, const float *quaternions,
+                      const float *strengths,
+                      float *density, float *nbr_opacity, float *beta, float *sdf,
+                      void *scratch, void *stream);
+
+/* Backward of the above.  Upstream grads (any may be NULL = zero): g_density f32[N],
+ * g_nbr_opacity f32[N,K], g_beta f32[N], g_sdf f32[N].  Downstream grads are fully WRITTEN
+ * (any may be NULL): g_x f32[N,3], g_points f32[P,3], g_scaling f32[P,3],
+ * g_quaternions f32[P,4] (w.r.t. the quaternion passed in, through two_s = 2/|q|^2 exactly as
+ * pytorch3d's quaternion_to_matrix differentiates), g_strengths f32[P]. */
+SGR_API int sgr_field_backward(const SgrFieldParams *p, const float *x, const int64_t *nbr_idx,
+                       const float *points, const float *scaling, const float *quaternions,
+                       const float *strengths,
+                       const float *g_density, const float *g_nbr_opacity, const float *g_beta,
+                       const float *g_sdf,
+                       float *g_x, float *g_points, float *g_scaling, float *g_quaternions,
+                       float *g_strengths, void *scratch, void *stream);
+
+SGR_API const char *sgr_last_error(void);
+SGR_API const char *sgr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUGAR_B200_H_ */

@@ -1,0 +1,83 @@
+"""ctypes binding of libsugar_b200.so (the C ABI declared in include/sugar_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at import, and every
+call raises on a non-zero status with the library's own message.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsugar_b200.so")
+
+
+class SgrError(RuntimeError):
+    pass
+
+
+class SgrView(C.Structure):
+    _fields_ = [
+        ("image_height", C.c_int32), ("image_width", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float),
+        ("bg", C.c_void_p), ("scale_modifier", C.c_float),
+        ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+        ("sh_degree", C.c_int32), ("campos", C.c_void_p),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+    ]
+
+
+class SgrGaussians(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("M", C.c_int32),
+        ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("shs", C.c_void_p),
+        ("colors_precomp", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("cov3D_precomp", C.c_void_p),
+    ]
+
+
+class SgrFieldParams(C.Structure):
+    _fields_ = [("N", C.c_int32), ("K", C.c_int32), ("P", C.c_int32), ("density_factor", C.c_float),
+                ("density_threshold", C.c_float), ("opacity_min_clamp", C.c_float)]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+PROTOTYPES = {
+    "sgr_rasterize_forward": (C.c_int, [C.POINTER(SgrView), C.POINTER(SgrGaussians), ALLOC_FN, C.c_void_p, ALLOC_FN,
+                                        C.c_void_p, ALLOC_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.POINTER(C.c_int64), C.c_void_p]),
+    "sgr_rasterize_backward": (C.c_int, [C.POINTER(SgrView), C.POINTER(SgrGaussians)] + [C.c_void_p] * 4 +
+                               [C.c_int64] + [C.c_void_p] * 11),
+    "sgr_mark_visible": (C.c_int, [C.c_int32] + [C.c_void_p] * 5),
+    "sgr_geometry_bytes": (C.c_size_t, [C.c_int32]),
+    "sgr_binning_bytes": (C.c_size_t, [C.c_int64]),
+    "sgr_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "sgr_backward_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "sgr_inspect_state": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 15),
+    "sgr_field_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "sgr_field_forward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 12),
+    "sgr_field_backward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 17),
+    "sgr_last_error": (C.c_char_p, []),
+    "sgr_version": (C.c_char_p, []),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise SgrError(
+            f"{LIB_PATH} not found: build it with `python sugar_b200/build.py` (needs nvcc). "
+            "sugar_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise SgrError(lib.sgr_last_error().decode(errors="replace") or f"libsugar_b200 error {status}")

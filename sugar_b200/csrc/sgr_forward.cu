@@ -1,0 +1,739 @@
+// sgr_forward.cu -- forward path of the B200 rasterizer.
+//
+// Replaces (reference: gaussian_splatting/submodules/diff-gaussian-rasterization/cuda_rasterizer/)
+//   preprocessCUDA            forward.cu:155-256      -> preprocess_kernel   (+ per-tile counting)
+//   InclusiveSum + D2H sync   rasterizer_impl.cu:277-281 -> tile_scan_kernel (over TILES, not Gaussians)
+//   duplicateWithKeys         rasterizer_impl.cu:70-111  -> scatter_kernel   (atomic cursor per tile)
+//   cub SortPairs (6 passes)  rasterizer_impl.cu:303-308 -> tile_sort_kernel (per-tile LSD radix in smem)
+//   identifyTileRanges        rasterizer_impl.cu:116-138 -> (ranges fall out of the tile scan)
+//   renderCUDA                forward.cu:261-374      -> blend_forward_kernel
+//
+// Binning design: the 64-bit key (tile<<32 | depth) is sorted MSD-first.  The tile digit is a
+// counting sort (per-tile counts by L2 atomics in preprocess, exclusive scan over tiles, atomic
+// cursor scatter), the remaining (depth, gaussian-id) order is an 8-bit LSD radix sort done
+// entirely in one CTA's shared memory per tile.  Instances move through HBM once (8 B write,
+// 8 B read, 4 B write) instead of ~150 B for six global radix passes, and the sorted order is
+// exactly the reference's: by tile, then depth bits, then Gaussian index (the reference's
+// stable sort keeps emission order = index order among equal keys).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "sgr_internal.cuh"
+
+namespace sgr {
+
+// ------------------------------------------------------------------------------------------------
+// preprocess
+// ------------------------------------------------------------------------------------------------
+constexpr int PRE_T = 256;
+
+struct PreArgs {
+    int P;
+    const float *means, *scales, *rots, *opac, *shs, *colors, *cov_pre;
+    ViewConsts v;
+    int bulk_ok;      // all staged arrays 16B-aligned
+    int sh_stride;    // padded smem row stride in floats (0 = no SH)
+    int sh_vec;       // 1: rows copied as 16-byte cp.async, 0: 4-byte
+    GeomState geom;
+    int32_t *radii;
+    uint32_t *tile_count;
+};
+
+__constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                 0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                 -0.5900435899266435f};
+#define SH_C0 0.28209479177387814f
+#define SH_C1 0.4886025119029199f
+
+// SH -> RGB for one channel (forward.cu:20-71), operation order as compiled for the reference.
+__device__ __forceinline__ float sh_channel(int deg, const float *sh /* stride 3 */, float x, float y, float z)
+{
+#define SHK(k) sh[(k) * 3]
+    float res = __fmul_rn(SH_C0, SHK(0));
+    if (deg > 0) {
+        res = __fmaf_rn(-__fmul_rn(y, SH_C1), SHK(1), res);
+        res = __fmaf_rn(__fmul_rn(z, SH_C1), SHK(2), res);
+        res = __fmaf_rn(-__fmul_rn(x, SH_C1), SHK(3), res);
+        if (deg > 1) {
+            const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+            const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+            const float zz2 = __fadd_rn(zz, zz);
+            const float xx_yy = __fsub_rn(xx, yy);
+            res = __fmaf_rn(__fmul_rn(xy, c_SH_C2[0]), SHK(4), res);
+            res = __fmaf_rn(__fmul_rn(yz, c_SH_C2[1]), SHK(5), res);
+            res = __fmaf_rn(__fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), c_SH_C2[2]), SHK(6), res);
+            res = __fmaf_rn(__fmul_rn(xz, c_SH_C2[3]), SHK(7), res);
+            res = __fmaf_rn(__fmul_rn(xx_yy, c_SH_C2[4]), SHK(8), res);
+            if (deg > 2) {
+                const float zz4_xx_yy = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);
+                res = __fmaf_rn(__fmul_rn(__fmul_rn(y, c_SH_C3[0]), __fmaf_rn(xx, 3.0f, -yy)), SHK(9), res);
+                res = __fmaf_rn(__fmul_rn(__fmul_rn(xy, c_SH_C3[1]), z), SHK(10), res);
+                res = __fmaf_rn(__fmul_rn(__fmul_rn(y, c_SH_C3[2]), zz4_xx_yy), SHK(11), res);
+                res = __fmaf_rn(__fmul_rn(__fmul_rn(z, c_SH_C3[3]), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2))),
+                                SHK(12), res);
+                res = __fmaf_rn(__fmul_rn(__fmul_rn(x, c_SH_C3[4]), zz4_xx_yy), SHK(13), res);
+                res = __fmaf_rn(__fmul_rn(__fmul_rn(z, c_SH_C3[5]), xx_yy), SHK(14), res);
+                res = __fmaf_rn(__fmul_rn(__fmul_rn(x, c_SH_C3[6]), __fmaf_rn(yy, -3.0f, xx)), SHK(15), res);
+            }
+        }
+    }
+#undef SHK
+    return res;
+}
+
+// Cooperative, coalesced copy of n floats into shared memory (fallback when bulk copy is not legal).
+__device__ __forceinline__ void stage_plain(float *dst, const float *__restrict__ src, int n)
+{
+    for (int i = threadIdx.x; i < n; i += PRE_T) dst[i] = __ldg(src + i);
+}
+
+__global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
+{
+    extern __shared__ __align__(16) float s_sh[];  // PRE_T rows x sh_stride floats (only with SH)
+    __shared__ __align__(16) float s_means[PRE_T * 3];
+    __shared__ __align__(16) float s_scales[PRE_T * 3];   // or colors_precomp when scales absent? no: separate below
+    __shared__ __align__(16) float4 s_rots[PRE_T];
+    __shared__ __align__(16) float s_opac[PRE_T];
+    __shared__ __align__(16) float s_col[PRE_T * 3];
+    __shared__ __align__(16) float s_cov[PRE_T * 6];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * PRE_T;
+    const int n = min(PRE_T, a.P - base);
+    const int idx = base + tid;
+    const bool full = (n == PRE_T);
+
+    // ---- stage inputs: one elected thread drives the TMA engine with 1-D bulk copies -----------
+    if (a.bulk_ok && full) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            uint32_t bytes = PRE_T * 12 + PRE_T * 4;
+            if (a.scales) bytes += PRE_T * 12 + PRE_T * 16;
+            if (a.cov_pre) bytes += PRE_T * 24;
+            if (a.colors) bytes += PRE_T * 12;
+            mbar_expect_tx(&s_bar, bytes);
+            bulk_g2s(s_means, a.means + (size_t)base * 3, PRE_T * 12, &s_bar);
+            bulk_g2s(s_opac, a.opac + base, PRE_T * 4, &s_bar);
+            if (a.scales) {
+                bulk_g2s(s_scales, a.scales + (size_t)base * 3, PRE_T * 12, &s_bar);
+                bulk_g2s(s_rots, a.rots + (size_t)base * 4, PRE_T * 16, &s_bar);
+            }
+            if (a.cov_pre) bulk_g2s(s_cov, a.cov_pre + (size_t)base * 6, PRE_T * 24, &s_bar);
+            if (a.colors) bulk_g2s(s_col, a.colors + (size_t)base * 3, PRE_T * 12, &s_bar);
+        }
+    } else {
+        stage_plain(s_means, a.means + (size_t)base * 3, n * 3);
+        stage_plain(s_opac, a.opac + base, n);
+        if (a.scales) {
+            stage_plain(s_scales, a.scales + (size_t)base * 3, n * 3);
+            stage_plain((float *)s_rots, a.rots + (size_t)base * 4, n * 4);
+        }
+        if (a.cov_pre) stage_plain(s_cov, a.cov_pre + (size_t)base * 6, n * 6);
+        if (a.colors) stage_plain(s_col, a.colors + (size_t)base * 3, n * 3);
+    }
+    // ---- SH rows: coalesced cp.async into bank-conflict-free padded rows -----------------------
+    if (a.shs) {
+        const int row_f = a.v.M * 3;
+        const float *src = a.shs + (size_t)base * row_f;
+        if (a.sh_vec) {
+            const int row_v = row_f >> 2, total = n * row_v;
+            for (int i = tid; i < total; i += PRE_T) {
+                const int r = i / row_v, c = i - r * row_v;
+                cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)i * 4);
+            }
+        } else {
+            const int total = n * row_f;
+            for (int i = tid; i < total; i += PRE_T) {
+                const int r = i / row_f, c = i - r * row_f;
+                cp_async4(s_sh + r * a.sh_stride + c, src + i);
+            }
+        }
+        cp_async_commit();
+    }
+    __syncthreads();  // barrier init visible / plain staging complete
+    if (a.bulk_ok && full) mbar_wait(&s_bar, 0);
+
+    // ---- per-Gaussian projection, cull, covariance, radius, tile rect (bit-exact chain) --------
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0, radius = 0;
+    bool visible = false;
+    float depth = 0.f, px = 0.f, py = 0.f, con_a = 0.f, con_b = 0.f, con_c = 0.f, opacity = 0.f;
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (tid < n) {
+        mx = s_means[tid * 3], my = s_means[tid * 3 + 1], mz = s_means[tid * 3 + 2];
+        const float *vm = a.v.viewmatrix, *pm = a.v.projmatrix;
+        depth = xf_row(vm, 2, mx, my, mz);
+        if (depth <= 0.2f) {
+            if (a.v.prefiltered) {  // auxiliary.h:156-160
+                printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+                __trap();
+            }
+        } else {
+            const float hx = xf_row(pm, 0, mx, my, mz), hy = xf_row(pm, 1, mx, my, mz), hw = xf_row(pm, 3, mx, my, mz);
+            const float p_w = __frcp_rn(__fadd_rn(hw, 0.0000001f));
+            const float projx = __fmul_rn(hx, p_w), projy = __fmul_rn(hy, p_w);
+            float c3[6];
+            if (a.cov_pre) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c3[k] = s_cov[tid * 6 + k];
+            } else {
+                cov3d_from_scale_rot(s_scales[tid * 3], s_scales[tid * 3 + 1], s_scales[tid * 3 + 2], a.v.scale_modifier,
+                                     s_rots[tid], c3);
+            }
+            const float tx0 = xf_row(vm, 0, mx, my, mz), ty0 = xf_row(vm, 1, mx, my, mz);
+            const Cov2D cv = cov2d_project(tx0, ty0, depth, a.v.focal_x, a.v.focal_y, a.v.tanfovx, a.v.tanfovy, c3, vm);
+            const float det = __fmaf_rn(cv.a, cv.c, -__fmul_rn(cv.b, cv.b));
+            if (det != 0.0f) {
+                const float det_inv = __frcp_rn(det);
+                con_a = __fmul_rn(cv.c, det_inv);
+                con_b = __fmul_rn(cv.b, -det_inv);
+                con_c = __fmul_rn(cv.a, det_inv);
+                const float mid = __fmul_rn(__fadd_rn(cv.a, cv.c), 0.5f);
+                const float s = __fsqrt_rn(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
+                const float lmax = fmaxf(__fadd_rn(mid, s), __fsub_rn(mid, s));
+                radius = (int)ceilf(__fmul_rn(3.0f, __fsqrt_rn(lmax)));
+                px = ndc2pix(projx, a.v.W);
+                py = ndc2pix(projy, a.v.H);
+                tile_rect(px, py, radius, a.v.gx, a.v.gy, x0, y0, x1, y1);
+                visible = (x1 - x0) * (y1 - y0) != 0;
+                opacity = s_opac[tid];
+            }
+        }
+    }
+    if (a.shs) {
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+    if (tid < n) {
+        if (visible) {
+            float r, g, b;
+            uint32_t clamp_bits = 0;
+            if (a.colors) {
+                r = s_col[tid * 3], g = s_col[tid * 3 + 1], b = s_col[tid * 3 + 2];
+            } else {
+                const float *cp = a.v.campos;
+                const float dx = __fsub_rn(mx, cp[0]), dy = __fsub_rn(my, cp[1]), dz = __fsub_rn(mz, cp[2]);
+                const float len = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
+                const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
+                const float *row = s_sh + tid * a.sh_stride;
+                r = sh_channel(a.v.D, row + 0, x, y, z);
+                g = sh_channel(a.v.D, row + 1, x, y, z);
+                b = sh_channel(a.v.D, row + 2, x, y, z);
+                // clamped <=> result + 0.5 < 0 (forward.cu:63-70)
+                clamp_bits = (r < -0.5f ? 1u : 0u) | (g < -0.5f ? 2u : 0u) | (b < -0.5f ? 4u : 0u);
+                r = (clamp_bits & 1u) ? 0.0f : __fadd_rn(r, 0.5f);
+                g = (clamp_bits & 2u) ? 0.0f : __fadd_rn(g, 0.5f);
+                b = (clamp_bits & 4u) ? 0.0f : __fadd_rn(b, 0.5f);
+            }
+            // Conservative cull threshold: alpha = min(.99, o*exp(power)) < 1/255 is certain when
+            // power < tau = ln(1/(255 o)) - 1e-4 (margin >> ulp error of expf/logf).
+            float tau;
+            if (opacity * 255.0f > 1.0f) tau = -logf(opacity * 255.0f) - 1e-4f;
+            else if (opacity == opacity) tau = __int_as_float(0x7f800000);  // never reaches 1/255: always skipped
+            else tau = -__int_as_float(0x7f800000);                          // NaN opacity: take the exact path
+            float4 *rec = a.geom.rec + (size_t)idx * 3;
+            rec[0] = make_float4(px, py, con_a, con_b);
+            rec[1] = make_float4(con_c, tau, opacity, r);
+            rec[2] = make_float4(g, b, 0.f, 0.f);
+            a.geom.depth[idx] = depth;
+            a.geom.aux[idx] = clamp_bits;
+            a.geom.rect[idx] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+            a.radii[idx] = radius;
+        } else {
+            a.geom.rect[idx] = make_ushort4(0, 0, 0, 0);
+            a.radii[idx] = 0;
+        }
+    }
+
+    // ---- per-tile instance counts: the warp walks its members' rects cooperatively -------------
+    const unsigned lane = tid & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, visible);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int rx0 = __shfl_sync(0xffffffffu, x0, src), ry0 = __shfl_sync(0xffffffffu, y0, src);
+        const int rx1 = __shfl_sync(0xffffffffu, x1, src), ry1 = __shfl_sync(0xffffffffu, y1, src);
+        const int w = rx1 - rx0, cnt = w * (ry1 - ry0);
+        for (int k = lane; k < cnt; k += 32) {
+            const int ty = k / w, tx = k - ty * w;
+            atomicAdd(a.tile_count + (ry0 + ty) * a.v.gx + rx0 + tx, 1u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan over tile counts -> tile_start[0..T], cursor copy, R
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t *__restrict__ count, uint32_t *__restrict__ start,
+                                                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ counters, int T,
+                                                         uint32_t *host_mirror)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024 * 4) {
+        const int i0 = base + tid * 4;
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            v[k] = (i0 + k < T) ? count[i0 + k] : 0u;
+            sum += v[k];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - w;  // exclusive
+        }
+        __syncthreads();
+        uint32_t excl = s_carry + s_warp[wid] + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < T) {
+                start[i0 + k] = excl;
+                cursor[i0 + k] = excl;
+            }
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = excl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        start[T] = s_carry;
+        counters[0] = s_carry;
+        if (host_mirror) *host_mirror = s_carry;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter: one (depth|id) word per (Gaussian, tile) instance into its tile's segment
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, const ushort4 *__restrict__ rect,
+                                                      const float *__restrict__ depth, uint32_t *__restrict__ cursor,
+                                                      const uint32_t *__restrict__ counters, uint64_t capacity,
+                                                      uint64_t *__restrict__ inst)
+{
+    if ((uint64_t)counters[0] > capacity) return;  // overflow: host re-runs with a bigger buffer
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    ushort4 rc = make_ushort4(0, 0, 0, 0);
+    uint32_t dbits = 0;
+    if (idx < P) {
+        rc = rect[idx];
+        if (rc.z > rc.x) dbits = __float_as_uint(depth[idx]);
+    }
+    const bool has = (rc.z > rc.x) && (rc.w > rc.y);
+    unsigned todo = __ballot_sync(0xffffffffu, has);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int rx0 = __shfl_sync(0xffffffffu, (int)rc.x, src), ry0 = __shfl_sync(0xffffffffu, (int)rc.y, src);
+        const int rx1 = __shfl_sync(0xffffffffu, (int)rc.z, src), ry1 = __shfl_sync(0xffffffffu, (int)rc.w, src);
+        const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
+        const int gid = (idx - (int)lane) + src;
+        const uint64_t word = ((uint64_t)db << 32) | (uint32_t)gid;
+        const int w = rx1 - rx0, cnt = w * (ry1 - ry0);
+        for (int k = lane; k < cnt; k += 32) {
+            const int ty = k / w, tx = k - ty * w;
+            const uint32_t slot = atomicAdd(cursor + (ry0 + ty) * gx + rx0 + tx, 1u);
+            inst[slot] = word;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-tile sort of (depth|id) words: LSD radix, 8-bit digits, warp-private histograms,
+// match_any ranking (stable), constant bytes skipped.  SMEM variant keeps both ping-pong buffers
+// in shared memory; the GLOBAL variant (tiles with more than SORT_CAP instances) ping-pongs
+// between inst_a and inst_b in L2/HBM with the same code.
+// ------------------------------------------------------------------------------------------------
+constexpr int SORT_CAP = 4096;
+
+template <int THREADS, bool GLOBAL>
+__global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t *__restrict__ tile_start,
+                                                            const uint32_t *__restrict__ counters, uint64_t capacity,
+                                                            uint64_t *__restrict__ inst_a, uint64_t *__restrict__ inst_b,
+                                                            uint32_t *__restrict__ plist)
+{
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) uint64_t s_keys[];  // SMEM variant: 2 * SORT_CAP
+    __shared__ uint32_t s_hist[NW][256];
+    __shared__ uint32_t s_diff[2];
+    __shared__ uint32_t s_wsum[32];
+
+    if ((uint64_t)counters[0] > capacity) return;
+    const int tile = blockIdx.x;
+    const uint32_t lo = tile_start[tile];
+    const int n = (int)(tile_start[tile + 1] - lo);
+    if (GLOBAL ? (n <= SORT_CAP) : (n > SORT_CAP || n == 0)) return;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint64_t *src, *dst;
+    if (GLOBAL) {
+        src = inst_a + lo;
+        dst = inst_b + lo;
+    } else {
+        src = s_keys;
+        dst = s_keys + SORT_CAP;
+    }
+
+    // load (SMEM) + find which key bytes vary inside this tile
+    if (tid < 2) s_diff[tid] = 0;
+    __syncthreads();
+    {
+        const uint64_t k0 = inst_a[lo];
+        uint32_t dlo = 0, dhi = 0;
+        for (int i = tid; i < n; i += THREADS) {
+            const uint64_t k = inst_a[lo + i];
+            if (!GLOBAL) src[i] = k;
+            const uint64_t x = k ^ k0;
+            dlo |= (uint32_t)x;
+            dhi |= (uint32_t)(x >> 32);
+        }
+        dlo = __reduce_or_sync(0xffffffffu, dlo);
+        dhi = __reduce_or_sync(0xffffffffu, dhi);
+        if (lane == 0) {
+            if (dlo) atomicOr(&s_diff[0], dlo);
+            if (dhi) atomicOr(&s_diff[1], dhi);
+        }
+    }
+    __syncthreads();
+    const uint64_t diff = ((uint64_t)s_diff[1] << 32) | s_diff[0];
+
+    // contiguous chunk per warp (multiple of 32 so that lanes map to consecutive elements)
+    const int chunk = ((n + NW - 1) / NW + 31) & ~31;
+    const int w_lo = min(n, wid * chunk), w_hi = min(n, w_lo + chunk);
+
+    for (int shift = 0; shift < 64; shift += 8) {
+        if (((diff >> shift) & 0xffull) == 0) continue;
+        for (int i = tid; i < NW * 256; i += THREADS) (&s_hist[0][0])[i] = 0;
+        __syncthreads();
+        // pass 1: warp-private digit histogram
+        for (int i = w_lo + lane; i - lane < w_hi; i += 32) {
+            const bool ok = i < w_hi;
+            const unsigned act = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const uint32_t d = (uint32_t)(src[i] >> shift) & 0xffu;
+                const unsigned peers = __match_any_sync(act, d);
+                if ((int)(__ffs(peers) - 1) == lane) s_hist[wid][d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // digit-major exclusive scan over (digit, warp)
+        {
+            uint32_t tot = 0;
+            if (tid < 256) {
+#pragma unroll 4
+                for (int w = 0; w < NW; w++) tot += s_hist[w][tid];
+            }
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (tid < 256 && lane == 31) s_wsum[wid] = inc;
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t basev = inc - tot;
+                for (int w = 0; w < wid; w++) basev += s_wsum[w];
+                for (int w = 0; w < NW; w++) {
+                    const uint32_t c = s_hist[w][tid];
+                    s_hist[w][tid] = basev;
+                    basev += c;
+                }
+            }
+            __syncthreads();
+        }
+        // pass 2: stable scatter
+        for (int i = w_lo + lane; i - lane < w_hi; i += 32) {
+            const bool ok = i < w_hi;
+            const unsigned act = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const uint64_t k = src[i];
+                const uint32_t d = (uint32_t)(k >> shift) & 0xffu;
+                const unsigned peers = __match_any_sync(act, d);
+                const uint32_t pos = s_hist[wid][d] + __popc(peers & ((1u << lane) - 1u));
+                dst[pos] = k;
+                __syncwarp(act);
+                if ((int)(__ffs(peers) - 1) == lane) s_hist[wid][d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        uint64_t *t = src;
+        src = dst;
+        dst = t;
+    }
+    for (int i = tid; i < n; i += THREADS) plist[lo + i] = (uint32_t)src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward blend: one CTA per 16x16 tile, one thread per pixel, splat records gathered
+// once per tile into shared memory.  power / alpha / T / C follow the reference's rounding exactly
+// (forward.cu:261-374), so final_T, n_contrib and the image are bit-identical to the reference;
+// the conservative `power < tau` test only skips pairs the exact alpha test would reject.
+// ------------------------------------------------------------------------------------------------
+constexpr int BLEND_T = 256;
+
+__global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *__restrict__ tile_start,
+                                                                const uint32_t *__restrict__ plist,
+                                                                const float4 *__restrict__ rec,
+                                                                const uint32_t *__restrict__ counters, uint64_t capacity,
+                                                                int W, int H, int gx, const float *__restrict__ bg,
+                                                                float *__restrict__ final_T,
+                                                                uint32_t *__restrict__ n_contrib,
+                                                                float *__restrict__ out_color)
+{
+    __shared__ float4 s_a[BLEND_T];  // x, y, conic a, conic b
+    __shared__ float4 s_b[BLEND_T];  // conic c, tau, opacity, r
+    __shared__ float2 s_c[BLEND_T];  // g, b
+    if ((uint64_t)counters[0] > capacity) return;
+    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int tid = threadIdx.y * SGR_TILE + threadIdx.x;
+    const uint32_t pxi = blockIdx.x * SGR_TILE + threadIdx.x, pyi = blockIdx.y * SGR_TILE + threadIdx.y;
+    const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
+    const float pxf = (float)pxi, pyf = (float)pyi;
+    const uint32_t lo = tile_start[tile], hi = tile_start[tile + 1];
+    int todo = (int)(hi - lo);
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t contributor = 0, last = 0;
+    for (uint32_t b0 = lo; b0 < hi; b0 += BLEND_T, todo -= BLEND_T) {
+        if (__syncthreads_count(done) == BLEND_T) break;
+        if (b0 + tid < hi) {
+            const uint32_t id = plist[b0 + tid];
+            const float4 *r = rec + (size_t)id * 3;
+            const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+            s_a[tid] = r0;
+            s_b[tid] = r1;
+            s_c[tid] = make_float2(r2.x, r2.y);
+        }
+        __syncthreads();
+        const int m = min(BLEND_T, todo);
+        for (int j = 0; !done && j < m; j++) {
+            contributor++;
+            const float4 A = s_a[j];
+            const float4 B = s_b[j];
+            const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
+            const float power = splat_power(dx, dy, A.z, A.w, B.x);
+            if (power > 0.0f || power < B.y) continue;
+            const float alpha = fminf(0.99f, __fmul_rn(B.z, expf(power)));
+            if (alpha < 1.0f / 255.0f) continue;
+            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+            if (test_T < 0.0001f) {
+                done = true;
+                continue;
+            }
+            const float2 Cc = s_c[j];
+            C0 = __fmaf_rn(T, __fmul_rn(alpha, B.w), C0);
+            C1 = __fmaf_rn(T, __fmul_rn(alpha, Cc.x), C1);
+            C2 = __fmaf_rn(T, __fmul_rn(alpha, Cc.y), C2);
+            T = test_T;
+            last = contributor;
+        }
+    }
+    if (inside) {
+        const size_t pix = (size_t)pyi * W + pxi, plane = (size_t)H * W;
+        final_T[pix] = T;
+        n_contrib[pix] = last;
+        out_color[pix] = __fmaf_rn(T, bg[0], C0);
+        out_color[plane + pix] = __fmaf_rn(T, bg[1], C1);
+        out_color[2 * plane + pix] = __fmaf_rn(T, bg[2], C2);
+    }
+}
+
+__global__ void mark_visible_kernel(int P, const float *__restrict__ means, const float *__restrict__ vm,
+                                    uint8_t *__restrict__ present)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float d = xf_row(vm, 2, means[3 * i], means[3 * i + 1], means[3 * i + 2]);
+    present[i] = !(d <= 0.2f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+struct DeviceSlot {
+    uint32_t *pinned = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool attrs_set = false;
+};
+static DeviceSlot g_slots[64];
+
+static int get_slot(DeviceSlot **out)
+{
+    int dev = 0;
+    SGR_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        set_error("device ordinal %d out of range", dev);
+        return SGR_EINVAL;
+    }
+    DeviceSlot &s = g_slots[dev];
+    if (!s.pinned) {
+        SGR_CUDA(cudaHostAlloc((void **)&s.pinned, 4096, cudaHostAllocDefault));
+        SGR_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    }
+    if (!s.attrs_set) {
+        SGR_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SGR_CUDA(cudaFuncSetAttribute(tile_sort_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      2 * SORT_CAP * 8));
+        s.attrs_set = true;
+    }
+    *out = &s;
+    return SGR_OK;
+}
+
+static inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+static int launch_binning_and_blend(const ViewConsts &v, int P, const GeomState &geom, const ImageState &img,
+                                    const BinState &bin, uint64_t capacity, float *out_color, cudaStream_t st)
+{
+    const int T = v.gx * v.gy;
+    scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, v.gx, geom.rect, geom.depth, img.tile_cursor, img.counters,
+                                                    capacity, bin.inst_a);
+    tile_sort_kernel<256, false><<<T, 256, 2 * SORT_CAP * 8, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
+                                                                  bin.inst_b, bin.plist);
+    tile_sort_kernel<1024, true><<<T, 1024, 0, st>>>(img.tile_start, img.counters, capacity, bin.inst_a, bin.inst_b,
+                                                    bin.plist);
+    blend_forward_kernel<<<dim3(v.gx, v.gy), dim3(SGR_TILE, SGR_TILE), 0, st>>>(
+        img.tile_start, bin.plist, geom.rec, img.counters, capacity, v.W, v.H, v.gx, v.bg, img.final_T, img.n_contrib,
+        out_color);
+    SGR_CUDA(cudaGetLastError());
+    return SGR_OK;
+}
+
+int launch_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc geom_alloc, void *geom_ctx,
+                   SgrAlloc binning_alloc, void *binning_ctx, SgrAlloc image_alloc, void *image_ctx, float *out_color,
+                   int32_t *radii, int64_t capacity_hint, int64_t *num_rendered, cudaStream_t st)
+{
+    const int P = g->P, W = view->image_width, H = view->image_height;
+    DeviceSlot *slot;
+    int rc = get_slot(&slot);
+    if (rc) return rc;
+
+    ViewConsts v;
+    v.viewmatrix = view->viewmatrix;
+    v.projmatrix = view->projmatrix;
+    v.campos = view->campos;
+    v.bg = view->bg;
+    v.W = W;
+    v.H = H;
+    v.gx = (W + SGR_TILE - 1) / SGR_TILE;
+    v.gy = (H + SGR_TILE - 1) / SGR_TILE;
+    v.tanfovx = view->tanfovx;
+    v.tanfovy = view->tanfovy;
+    v.focal_y = H / (2.0f * view->tanfovy);  // rasterizer_impl.cu:222-223
+    v.focal_x = W / (2.0f * view->tanfovx);
+    v.scale_modifier = view->scale_modifier;
+    v.D = view->sh_degree;
+    v.M = g->M;
+    v.prefiltered = view->prefiltered;
+    const int T = v.gx * v.gy;
+
+    void *geom_mem = geom_alloc(geom_ctx, GeomState::bytes(P));
+    void *img_mem = image_alloc(image_ctx, ImageState::bytes(W, H));
+    if (!geom_mem || !img_mem) {
+        set_error("scratch allocator returned NULL");
+        return SGR_ENOMEM;
+    }
+    GeomState geom = GeomState::carve(geom_mem, P);
+    ImageState img = ImageState::carve(img_mem, W, H);
+
+    SGR_CUDA(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * T, st));
+
+    PreArgs a;
+    a.P = P;
+    a.means = g->means3D;
+    a.scales = g->scales;
+    a.rots = g->rotations;
+    a.opac = g->opacities;
+    a.shs = g->shs;
+    a.colors = g->colors_precomp;
+    a.cov_pre = g->cov3D_precomp;
+    a.v = v;
+    a.bulk_ok = aligned16(g->means3D) && aligned16(g->opacities) && (!g->scales || aligned16(g->scales)) &&
+                (!g->rotations || aligned16(g->rotations)) && (!g->cov3D_precomp || aligned16(g->cov3D_precomp)) &&
+                (!g->colors_precomp || aligned16(g->colors_precomp));
+    a.sh_stride = 0;
+    a.sh_vec = 0;
+    size_t dyn = 0;
+    if (g->shs) {
+        const int row_f = g->M * 3;
+        if ((row_f % 4) == 0 && aligned16(g->shs)) {
+            int s4 = row_f / 4;
+            if ((s4 & 1) == 0) s4 += 1;  // odd number of 16-byte units per row: conflict-free LDS
+            a.sh_stride = s4 * 4;
+            a.sh_vec = 1;
+        } else {
+            a.sh_stride = (row_f & 1) ? row_f : row_f + 1;
+        }
+        dyn = (size_t)PRE_T * a.sh_stride * sizeof(float);
+    }
+    a.geom = geom;
+    a.radii = radii;
+    a.tile_count = img.tile_count;
+    preprocess_kernel<<<(P + PRE_T - 1) / PRE_T, PRE_T, dyn, st>>>(a);
+    tile_scan_kernel<<<1, 1024, 0, st>>>(img.tile_count, img.tile_start, img.tile_cursor, img.counters, T, nullptr);
+    SGR_CUDA(cudaGetLastError());
+    SGR_CUDA(cudaMemcpyAsync(slot->pinned, img.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SGR_CUDA(cudaEventRecord(slot->ev, st));
+
+    // Optimistic path: size the binning buffer from the caller's hint and enqueue everything
+    // before looking at R; the device-side guard makes an overflowing attempt a no-op.
+    bool launched = false;
+    uint64_t capacity = 0;
+    BinState bin;
+    if (capacity_hint > 0) {
+        capacity = (uint64_t)capacity_hint;
+        void *bin_mem = binning_alloc(binning_ctx, BinState::bytes(capacity));
+        if (!bin_mem) {
+            set_error("binning allocator returned NULL");
+            return SGR_ENOMEM;
+        }
+        bin = BinState::carve(bin_mem, capacity);
+        rc = launch_binning_and_blend(v, P, geom, img, bin, capacity, out_color, st);
+        if (rc) return rc;
+        launched = true;
+    }
+    SGR_CUDA(cudaEventSynchronize(slot->ev));
+    const uint64_t R = *slot->pinned;
+    if (!launched || R > capacity) {
+        capacity = R;
+        void *bin_mem = binning_alloc(binning_ctx, BinState::bytes(capacity));
+        if (!bin_mem) {
+            set_error("binning allocator returned NULL");
+            return SGR_ENOMEM;
+        }
+        bin = BinState::carve(bin_mem, capacity);
+        if (launched) {  // cursors were not advanced by the guarded attempt, but be explicit
+            SGR_CUDA(cudaMemcpyAsync(img.tile_cursor, img.tile_start, sizeof(uint32_t) * T, cudaMemcpyDeviceToDevice, st));
+        }
+        rc = launch_binning_and_blend(v, P, geom, img, bin, capacity, out_color, st);
+        if (rc) return rc;
+    }
+    *num_rendered = (int64_t)R;
+    if (view->debug) SGR_CUDA(cudaStreamSynchronize(st));
+    return SGR_OK;
+}
+
+}  // namespace sgr
