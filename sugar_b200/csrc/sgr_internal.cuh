@@ -6,7 +6,7 @@
 //   geometry (per Gaussian)            image (per pixel / per tile)          binning (per instance)
 //   rec    float4[3P]  48 B splat rec  final_T  f32[HW]                      inst_a  u64[C] depth|idx
 //   rect   ushort4[P]   8 B tile rect  n_contrib u32[HW]                     inst_b  u64[C] sort pong
-//   depth  f32[P]       4 B            tile_count u32[T]  tile_start u32[T+1] plist  u32[C] sorted ids
+//   depth  f32[P]       4 B            tile_count u32[T]  tile_start u32[T+1] (plist is laid out FIRST)
 //   aux    u32[P]       4 B clamp bits tile_cursor u32[T] counters u32[16]
 //
 // Splat record (what the blend kernels gather, 48 B = 1.5 sectors instead of the reference's
@@ -75,9 +75,11 @@ struct ImageState {
 };
 
 struct BinState {
+    // plist comes first so that its address does not depend on the capacity the forward chose
+    // (backward and inspection only know num_rendered, not the optimistic capacity).
+    uint32_t *plist;
     uint64_t *inst_a;
     uint64_t *inst_b;
-    uint32_t *plist;
     static size_t bytes(size_t C)
     {
         if (C == 0) C = 1;
@@ -88,9 +90,9 @@ struct BinState {
         if (C == 0) C = 1;
         char *p = (char *)align_up((size_t)base);
         BinState s;
+        s.plist = (uint32_t *)p; p += align_up(C * 4);
         s.inst_a = (uint64_t *)p; p += align_up(C * 8);
-        s.inst_b = (uint64_t *)p; p += align_up(C * 8);
-        s.plist = (uint32_t *)p;
+        s.inst_b = (uint64_t *)p;
         return s;
     }
 };
