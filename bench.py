@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward views/sec of the Gaussian-splat rasterizer hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): forward+backward views/sec @ 3M Gaussians, 1920x1080, SH degree 3,
+plus achieved HBM GB/s of the dominant kernel vs the measured peak.  One "step" = one view
+rendered forward and backward on each GPU (weak scaling: every rank renders its own view of the
+replicated cloud; for N>1 the per-Gaussian gradients are then summed with one NCCL all-reduce).
+
+Prints ONE JSON line (rank 0).  Keys are documented in DESIGN.md section "Measurement".
+  value        views/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          views/s through the public drop-in API with per-step host->device copies of the
+               view's camera + upstream image gradient (pinned) and a device->host loss read
+  roofline     dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (scalar C port of the reference) on a bounded sample
+--impl reference runs the UNMODIFIED reference CUDA build (oracle/_ref) through its own
+GaussianRasterizer on the same tensors and protocol (the reference has no CPU rasterizer; its
+CUDA build is the baseline BASELINE.md section 2 names), falling back to the CPU oracle port
+when oracle/_ref is absent.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "forward+backward views/sec @3M Gaussians 1920x1080"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=3_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic bytes per kernel launch (DESIGN.md "Algorithmic bytes")
+# P Gaussians, V visible, R instances, T tiles, M stored / D active SH, W x H pixels
+# ---------------------------------------------------------------------------------------------
+def algorithmic_bytes(P, V, R, W, H, M, D):
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    sh = 12 * (D + 1) ** 2
+    return {
+        "preprocess": P * (44 + sh) + P * 12 + V * 56 + R * 4,
+        "tile_scan": T * 12,
+        "scatter": P * 8 + V * 4 + R * 12,
+        "tile_sort_smem": R * 12,
+        "tile_sort_global": R * 12,
+        "blend_forward": R * 40 + W * H * 20,
+        "blend_backward": R * 40 + W * H * 20 + V * 36 * 2,
+        "preprocess_backward": V * (36 + 44 + sh) + P * (92 + 12 * M),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(args):
+    """Scalar C oracle (port of the reference algorithm) on a bounded sample: a 1/64-area scene of
+    the same splat density (P/64 Gaussians at W/8 x H/8), forward+backward, timed on one host core."""
+    from oracle import raster_oracle as ro
+    from sugar_b200 import scenes
+    import helpers as h
+    f = 8
+    P, W, H = args.gaussians // (f * f), args.width // f, args.height // f
+    sc = scenes.make_scene(P, W, H, seed=0)
+    dL = scenes.upstream_grad(W, H)
+    t0 = time.perf_counter()
+    fw, bw = h.run_oracle(sc, np.zeros(3, np.float32), dL, use_sh=True, sh_degree=args.sh_degree)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / (dt * f * f), "unit": "views/s", "cores": 1, "kind": "port",
+            "sample": f"1/{f*f}-area sample of the workload ({P} Gaussians @ {W}x{H}, same splat density), "
+                      f"fwd+bwd {dt:.2f} s on 1 core, scaled x{f*f}", "host_cores": os.cpu_count()}
+
+
+def main():
+    args = parse()
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        if args.impl == "reference" and rank != 0:
+            return 0  # the reference is single-GPU: rank 0 alone runs it
+        if args.impl != "reference":
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    P, W, H, D = args.gaussians, args.width, args.height, args.sh_degree
+
+    from sugar_b200 import scenes
+    use_ref = False
+    if args.impl == "reference":
+        import helpers as h
+        if h.have_ref():
+            mod = h.load_ref_module()
+            use_ref = True
+        else:
+            # no reference CUDA build on this box: the CPU oracle port is the reference arm
+            cb = cpu_baseline(args)
+            print(json.dumps({"metric": METRIC, "value": cb["value"], "unit": "views/s", "n_gpus": 1,
+                              "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "impl": "reference", "config": {"workload": f"{P} Gaussians {W}x{H} SH{D}"},
+                              "cpu_baseline": cb, "gpu_launches": 0,
+                              "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0,
+                                      "d2h_bytes_per_step": 0}}))
+            return 0
+    else:
+        from sugar_b200 import diff_gaussian_rasterization as mod
+        from sugar_b200 import _lib
+
+    # ---- workload: the same cloud on every rank, one camera per rank (seeded) ----------------
+    sc = scenes.make_scene(P, W, H, seed=0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    params = {k: t(getattr(sc, k)).requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    means2D = torch.zeros_like(params["means3D"], requires_grad=True)
+    # each rank looks at the cloud from a slightly different (seeded) pose: rotate about the view axis
+    ang = 0.05 * rank
+    Rz = np.eye(4, dtype=np.float64)
+    Rz[0, 0] = Rz[1, 1] = math.cos(ang); Rz[0, 1] = -math.sin(ang); Rz[1, 0] = math.sin(ang)
+    V = Rz  # world->view
+    viewmatrix_h = torch.from_numpy(V.T.astype(np.float32)).pin_memory()
+    Pm = scenes.projection_matrix(0.01, 100.0, sc.tanfovx, sc.tanfovy)
+    projmatrix_h = torch.from_numpy((V.T @ Pm.T).astype(np.float32)).pin_memory()
+    campos_h = torch.zeros(3).pin_memory()
+    bg_h = torch.zeros(3).pin_memory()
+    dL_h = torch.from_numpy(scenes.upstream_grad(W, H, seed=1 + rank)).pin_memory()
+    viewmatrix, projmatrix, campos, bg, dL = (x.to(dev) for x in (viewmatrix_h, projmatrix_h, campos_h, bg_h, dL_h))
+
+    def settings(vm, pm, cp, b):
+        return mod.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy,
+                                                 bg=b, scale_modifier=1.0, viewmatrix=vm, projmatrix=pm, sh_degree=D,
+                                                 campos=cp, prefiltered=False, debug=False)
+
+    arena = None
+    if dist is not None:
+        from sugar_b200 import parallel
+        arena = parallel.GradArena(P, 16, dev)
+
+    def zero_grads():
+        for p in params.values():
+            p.grad = None
+        means2D.grad = None
+
+    def step_device():
+        rast = mod.GaussianRasterizer(settings(viewmatrix, projmatrix, campos, bg))
+        color, radii = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
+                            shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+        torch.autograd.backward(color, dL)
+        if arena is not None:
+            arena.all_reduce_from(params, 1.0 / world)
+        zero_grads()
+        return radii
+
+    def step_e2e():
+        vm = viewmatrix_h.to(dev, non_blocking=True); pm = projmatrix_h.to(dev, non_blocking=True)
+        cp = campos_h.to(dev, non_blocking=True); b = bg_h.to(dev, non_blocking=True)
+        g = dL_h.to(dev, non_blocking=True)
+        rast = mod.GaussianRasterizer(settings(vm, pm, cp, b))
+        color, radii = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
+                            shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+        loss = (color * g).sum()
+        loss.backward()
+        if arena is not None:
+            arena.all_reduce_from(params, 1.0 / world)
+        val = loss.item()  # device -> host read of the step's result
+        zero_grads()
+        return val
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if dist is not None:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        radii = step_device()
+    torch.cuda.synchronize()
+    V_vis = int((radii > 0).sum())
+
+    launches0 = 0 if use_ref else _lib.lib.sgr_launch_count()
+    clocks = ClockSampler(local)
+    if not use_ref:
+        _lib.profile(True)
+    ms = timed(step_device, args.steps)
+    prof = {}
+    if not use_ref:
+        prof = _lib.profile_read()
+        _lib.profile(False)
+    launches = 0 if use_ref else int(_lib.lib.sgr_launch_count() - launches0)
+    clk = clocks.stop()
+
+    for _ in range(3):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    out = {"metric": METRIC, "value": world / (ms * 1e-3) if not use_ref else 1.0 / (ms * 1e-3), "unit": "views/s",
+           "n_gpus": 1 if use_ref else world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{P} Gaussians (SH deg {D}, M=16) {W}x{H}, 1 view per GPU per step, fwd+bwd",
+                      "visible": V_vis, "l2_policy": "inputs (708 MB of Gaussian parameters) larger than L2; no flush",
+                      "parallelism": f"view-dp{world}" if world > 1 else "single"},
+           "clocks": clk}
+    n_e2e = 1 if use_ref else world
+    out["e2e"] = {"value": n_e2e / (ms_e2e * 1e-3), "unit": "views/s",
+                  "h2d_bytes_per_step": int(dL_h.numel() * 4 + (16 + 16 + 3 + 3) * 4), "d2h_bytes_per_step": 4,
+                  "ms_per_step": ms_e2e}
+    out["gpu_launches"] = launches
+    if use_ref:
+        out["impl"] = "reference"
+        out["config"]["reference"] = "unmodified diff-gaussian-rasterization CUDA sources compiled for sm_100a (oracle/_ref)"
+        out["gpu_launches"] = 0
+    if rank == 0 and not use_ref:
+        # R of this view for the byte model
+        rast = mod.GaussianRasterizer(settings(viewmatrix, projmatrix, campos, bg))
+        with torch.no_grad():
+            from sugar_b200 import _C
+            R = _C.rasterize_gaussians(bg, params["means3D"], torch.Tensor([]), params["opacities"], params["scales"],
+                                       params["rotations"], 1.0, torch.Tensor([]), viewmatrix, projmatrix, sc.tanfovx,
+                                       sc.tanfovy, H, W, params["shs"], D, campos, False, False)[0]
+        alg = algorithmic_bytes(P, V_vis, R, W, H, 16, D)
+        peak, peak_src = load_peaks()
+        stages = {}
+        for name, (tot, cnt) in prof.items():
+            avg_ms = tot / cnt
+            b = alg.get(name)
+            stages[name] = {"ms": round(avg_ms, 4), "launches_per_step": cnt / args.steps,
+                            "gbs": round(b / (avg_ms * 1e-3) / 1e9, 1) if b else None}
+        dom = max(stages, key=lambda k: stages[k]["ms"] * stages[k]["launches_per_step"]) if stages else None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            pass
+        if dom:
+            out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                               "frac": round(stages[dom]["gbs"] / peak, 4) if stages[dom]["gbs"] else None,
+                               "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg.get(dom)}
+        out["stages"] = stages
+        out["config"]["num_rendered"] = R
+        total_alg = sum(alg[k] for k in alg if k in stages)
+        out["hbm_gbs_whole_step"] = round(total_alg / (ms * 1e-3) / 1e9, 1)
+        if not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(args)
+            except Exception as ex:  # the oracle is a checker; never let it break the bench line
+                out["cpu_baseline"] = {"error": repr(ex)}
+    if use_ref:
+        out["cpu_baseline"] = {"value": out["value"], "unit": "views/s", "cores": 0, "kind": "reference",
+                               "sample": "full workload on the GPU: the reference path has no CPU implementation"}
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -164,6 +164,15 @@ SGR_API int sgr_field_backward(const SgrFieldParams *p, const float *x, const in
                        float *g_x, float *g_points, float *g_scaling, float *g_quaternions,
                        float *g_strengths, void *scratch, void *stream);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched in this process;
+ * optional CUDA-event bracketing of every launch on its own stream.  sgr_profile_read fills
+ * total_ms[kind] / counts[kind] for kind < sgr_num_kernel_kinds() and resets the log. */
+SGR_API unsigned long long sgr_launch_count(void);
+SGR_API int sgr_num_kernel_kinds(void);
+SGR_API const char *sgr_kernel_name(int kind);
+SGR_API int sgr_profile_enable(int on);
+SGR_API int sgr_profile_read(float *total_ms, int *counts);
+
 SGR_API const char *sgr_last_error(void);
 SGR_API const char *sgr_version(void);
 

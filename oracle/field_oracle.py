@@ -1,0 +1,89 @@
+"""CPU restatement of SuGaR's density / SDF field -- TEST INFRASTRUCTURE ONLY (see raster_oracle.c).
+
+Follows, op for op in PyTorch on the CPU:
+    get_covariance(return_full_matrix, return_sqrt, inverse_scales)   sugar_scene/sugar_model.py:730-750
+    get_beta, beta_mode == 'average'                                 sugar_scene/sugar_model.py:1192-1195
+    get_field_values                                                 sugar_scene/sugar_model.py:1247-1316
+    compute_density                                                  sugar_scene/sugar_model.py:1345-1368
+    sample_points_in_gaussians                                       sugar_scene/sugar_model.py:885-928
+Third-party arithmetic that is NOT under /root/reference (pytorch3d 0.7.4, environment.yml:161) is
+restated from its published algorithm: quaternion_to_matrix / quaternion_apply (real-first) and
+knn_points (exact K-NN on squared distances; restated with cdist + topk).
+
+Parity pinning: tests/golden/field_*.npz were produced by running the reference's OWN
+SuGaR.get_field_values code (imported from /root/reference with the missing third-party modules
+stubbed, tests/golden/make_field_golden.py); tests/test_field_oracle.py checks this file against them.
+"""
+import numpy as np
+import torch
+
+
+def quaternion_to_matrix(q: torch.Tensor) -> torch.Tensor:
+    """pytorch3d.transforms.quaternion_to_matrix (0.7.4): real part first, two_s = 2/|q|^2."""
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(q.shape[:-1] + (3, 3))
+
+
+def quaternion_apply(q: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """pytorch3d.transforms.quaternion_apply: rotate points by (unit) quaternions."""
+    return (quaternion_to_matrix(q) @ p[..., None])[..., 0]
+
+
+def knn_idx(points: torch.Tensor, K: int, queries: torch.Tensor = None) -> torch.Tensor:
+    """pytorch3d.ops.knn_points(...).idx for one cloud: exact K nearest by squared distance."""
+    q = points if queries is None else queries
+    d = torch.cdist(q.double(), points.double())
+    return d.topk(K, dim=1, largest=False).indices
+
+
+def field_values_torch(x, nbr_idx, points, scaling, quaternions, strengths, density_factor=1.0,
+                       density_threshold=1.0, opacity_min_clamp=1e-16):
+    """get_field_values with closest_gaussians_idx given; tensors may require grad."""
+    s = 1.0 / scaling.clamp(min=1e-8)
+    inv_scaled_rot = quaternion_to_matrix(quaternions) * s[:, None]          # :730-735
+    c_centers = points[nbr_idx]
+    c_isr = inv_scaled_rot[nbr_idx]
+    c_str = strengths.view(-1, 1)[nbr_idx]
+    shift = x[:, None] - c_centers
+    warped = c_isr.transpose(-1, -2) @ shift[..., None]
+    nb = (warped[..., 0] * warped[..., 0]).sum(dim=-1).clamp(min=0.0, max=1e8)
+    nb = density_factor * c_str[..., 0] * torch.exp(-1.0 / 2 * nb)
+    densities = nb.sum(dim=-1)
+    out = {"density": densities.clone(), "closest_gaussian_opacities": nb}
+    mask = densities >= 1.0
+    densities = torch.where(mask, densities / (densities.detach() + 1e-12), densities)   # :1280-1281
+    beta = scaling.min(dim=-1)[0][nbr_idx].mean(dim=1)                                   # :1195
+    clamped = densities.clamp(min=opacity_min_clamp)
+    out["beta"] = beta
+    out["sdf"] = beta * (torch.sqrt(-2.0 * torch.log(clamped)) - np.sqrt(-2.0 * np.log(min(density_threshold, 1.0))))
+    return out
+
+
+def field_values(x, nbr_idx, points, scaling, quaternions, strengths, density_factor=1.0, density_threshold=1.0,
+                 opacity_min_clamp=1e-16, **_):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    with torch.no_grad():
+        o = field_values_torch(t(x), t(nbr_idx), t(points), t(scaling), t(quaternions), t(strengths), density_factor,
+                               density_threshold, opacity_min_clamp)
+    return {k: v.numpy() for k, v in o.items()}
+
+
+def make_case(P=1000, N=2000, K=16, seed=0, density_factor=1.0 / 16.0, density_threshold=1.0):
+    """Seeded cloud + samples drawn like sample_points_in_gaussians(:885-928): multinomial over
+    volumes, x = mu + R(q) (1.5 * s * N(0,1)); neighbours = knn_idx[gaussian_idx]."""
+    g = torch.Generator().manual_seed(seed)
+    points = torch.randn(P, 3, generator=g)
+    scaling = torch.exp(torch.randn(P, 3, generator=g) * 0.5 - 2.3)
+    q = torch.nn.functional.normalize(torch.randn(P, 4, generator=g), dim=-1)
+    strengths = torch.sigmoid(torch.randn(P, generator=g) * 2.0)
+    nn_idx = knn_idx(points, K)
+    areas = (scaling[:, 0] * scaling[:, 1] * scaling[:, 2]).abs()
+    gi = torch.multinomial(areas / areas.sum(), N, replacement=True, generator=g)
+    x = points[gi] + quaternion_apply(q[gi], 1.5 * scaling[gi] * torch.randn(N, 3, generator=g))
+    f = lambda a: np.ascontiguousarray(a.numpy())
+    return dict(x=f(x.float()), nbr_idx=f(nn_idx[gi]), points=f(points), scaling=f(scaling), quaternions=f(q),
+                strengths=f(strengths), density_factor=density_factor, density_threshold=density_threshold)

@@ -57,6 +57,11 @@ PROTOTYPES = {
     "sgr_field_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_field_forward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 12),
     "sgr_field_backward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 17),
+    "sgr_launch_count": (C.c_ulonglong, []),
+    "sgr_num_kernel_kinds": (C.c_int, []),
+    "sgr_kernel_name": (C.c_char_p, [C.c_int]),
+    "sgr_profile_enable": (C.c_int, [C.c_int]),
+    "sgr_profile_read": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgr_last_error": (C.c_char_p, []),
     "sgr_version": (C.c_char_p, []),
 }
@@ -81,3 +86,16 @@ lib = _load()
 def check(status: int) -> None:
     if status != 0:
         raise SgrError(lib.sgr_last_error().decode(errors="replace") or f"libsugar_b200 error {status}")
+
+
+def profile(on: bool) -> None:
+    check(lib.sgr_profile_enable(int(on)))
+
+
+def profile_read():
+    """-> {kernel name: (total_ms, launches)} since profiling was enabled / last read."""
+    n = lib.sgr_num_kernel_kinds()
+    ms = (C.c_float * n)()
+    cnt = (C.c_int * n)()
+    check(lib.sgr_profile_read(ms, cnt))
+    return {lib.sgr_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}

@@ -4,6 +4,7 @@
 // are rejected up front, P == 0 returns without launching anything.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sgr_internal.cuh"
@@ -24,6 +25,45 @@ int cuda_fail(cudaError_t e, const char *what)
 {
     set_error("[CUDA ERROR] %s: %s", what, cudaGetErrorString(e));
     return SGR_ECUDA;
+}
+
+// ---- launch counter + optional event profiling (not thread-safe: one profiling client at a time)
+static const char *const g_kind_names[K_NUM_KINDS] = {
+    "preprocess", "tile_scan", "scatter", "tile_sort_smem", "tile_sort_global", "blend_forward", "blend_backward",
+    "preprocess_backward", "field_pack", "field_forward", "field_backward", "field_unpack", "misc"};
+struct ProfRec {
+    cudaEvent_t a, b;
+    int kind;
+};
+static unsigned long long g_launches = 0;
+static bool g_prof_on = false;
+static ProfRec *g_prof = nullptr;
+static int g_prof_n = 0, g_prof_cap = 0;
+
+void prof_begin(int kind, cudaStream_t st)
+{
+    g_launches++;
+    if (!g_prof_on) return;
+    if (g_prof_n == g_prof_cap) {
+        const int ncap = g_prof_cap ? g_prof_cap * 2 : 1024;
+        ProfRec *np = (ProfRec *)realloc(g_prof, sizeof(ProfRec) * ncap);
+        if (!np) return;
+        for (int i = g_prof_cap; i < ncap; i++) {
+            cudaEventCreate(&np[i].a);
+            cudaEventCreate(&np[i].b);
+        }
+        g_prof = np;
+        g_prof_cap = ncap;
+    }
+    g_prof[g_prof_n].kind = kind;
+    cudaEventRecord(g_prof[g_prof_n].a, st);
+}
+
+void prof_end(cudaStream_t st)
+{
+    if (!g_prof_on || g_prof_n >= g_prof_cap) return;
+    cudaEventRecord(g_prof[g_prof_n].b, st);
+    g_prof_n++;
 }
 
 static int validate(const SgrView *view, const SgrGaussians *g, bool forward)
@@ -142,6 +182,34 @@ using namespace sgr;
 extern "C" {
 
 const char *sgr_last_error(void) { return g_err; }
+
+unsigned long long sgr_launch_count(void) { return g_launches; }
+int sgr_num_kernel_kinds(void) { return K_NUM_KINDS; }
+const char *sgr_kernel_name(int kind) { return (kind >= 0 && kind < K_NUM_KINDS) ? g_kind_names[kind] : "?"; }
+
+int sgr_profile_enable(int on)
+{
+    g_prof_on = on != 0;
+    if (on) g_prof_n = 0;
+    return SGR_OK;
+}
+
+int sgr_profile_read(float *total_ms, int *counts)
+{
+    for (int k = 0; k < K_NUM_KINDS; k++) {
+        total_ms[k] = 0.f;
+        counts[k] = 0;
+    }
+    for (int i = 0; i < g_prof_n; i++) {
+        SGR_CUDA(cudaEventSynchronize(g_prof[i].b));
+        float ms = 0.f;
+        SGR_CUDA(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
+        total_ms[g_prof[i].kind] += ms;
+        counts[g_prof[i].kind]++;
+    }
+    g_prof_n = 0;
+    return SGR_OK;
+}
 const char *sgr_version(void) { return "sugar_b200 0.1 (sm_100a)"; }
 
 size_t sgr_geometry_bytes(int32_t P) { return GeomState::bytes((size_t)(P < 0 ? 0 : P)); }
@@ -202,7 +270,8 @@ int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, c
         return SGR_EINVAL;
     }
     if (P == 0) return SGR_OK;
-    sgr::mark_visible_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, means3D, viewmatrix, present);
+    SGR_LAUNCH(K_MISC, (cudaStream_t)stream,
+               sgr::mark_visible_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, means3D, viewmatrix, present));
     SGR_CUDA(cudaGetLastError());
     return SGR_OK;
 }

@@ -478,8 +478,10 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     float *gacc = (float *)align_up((size_t)grad_scratch);
     SGR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 48, st));
     if (num_rendered > 0) {
-        blend_backward_kernel<<<dim3(gx, gy), dim3(SGR_TILE, SGR_TILE), 0, st>>>(
-            img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T, img.n_contrib, dL_dout_color, gacc);
+        SGR_LAUNCH(K_BLEND_BWD, st,
+                   blend_backward_kernel<<<dim3(gx, gy), dim3(SGR_TILE, SGR_TILE), 0, st>>>(
+                       img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T, img.n_contrib,
+                       dL_dout_color, gacc));
     }
     PreBwdArgs a;
     a.P = P;
@@ -515,7 +517,7 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     a.dsh = dL_dsh;
     a.dscales = dL_dscales;
     a.drots = dL_drotations;
-    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, st>>>(a);
+    SGR_LAUNCH(K_PRE_BWD, st, preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, st>>>(a));
     SGR_CUDA(cudaGetLastError());
     if (view->debug) SGR_CUDA(cudaStreamSynchronize(st));
     return SGR_OK;

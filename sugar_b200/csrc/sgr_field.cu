@@ -318,10 +318,12 @@ int sgr_field_forward(const SgrFieldParams *p, const float *x, const int64_t *nb
     if (p->N == 0) return SGR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     float4 *rec = (float4 *)align_up((size_t)scratch);
-    field_pack_kernel<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, points, scaling, quaternions, strengths, rec);
+    SGR_LAUNCH(K_FIELD_PACK, st,
+               field_pack_kernel<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, points, scaling, quaternions, strengths, rec));
     const FieldArgs a = make_args(p, x, nbr_idx, rec);
     const int G = group_width(p->K);
     const int blocks = (p->N + 256 / G - 1) / (256 / G);
+    sgr::prof_begin(K_FIELD_FWD, st);
     switch (G) {
         case 1: field_forward_kernel<1><<<blocks, 256, 0, st>>>(a, density, nbr_opacity, beta, sdf); break;
         case 2: field_forward_kernel<2><<<blocks, 256, 0, st>>>(a, density, nbr_opacity, beta, sdf); break;
@@ -330,6 +332,7 @@ int sgr_field_forward(const SgrFieldParams *p, const float *x, const int64_t *nb
         case 16: field_forward_kernel<16><<<blocks, 256, 0, st>>>(a, density, nbr_opacity, beta, sdf); break;
         default: field_forward_kernel<32><<<blocks, 256, 0, st>>>(a, density, nbr_opacity, beta, sdf); break;
     }
+    sgr::prof_end(st);
     SGR_CUDA(cudaGetLastError());
     return SGR_OK;
 }
@@ -347,12 +350,14 @@ int sgr_field_backward(const SgrFieldParams *p, const float *x, const int64_t *n
     float *grec = (float *)((char *)rec + align_up((size_t)p->P * 48));
     SGR_CUDA(cudaMemsetAsync(grec, 0, (size_t)p->P * 48, st));
     if (p->N > 0) {
-        field_pack_kernel<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, points, scaling, quaternions, strengths, rec);
+        SGR_LAUNCH(K_FIELD_PACK, st,
+                   field_pack_kernel<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, points, scaling, quaternions, strengths, rec));
         const FieldArgs a = make_args(p, x, nbr_idx, rec);
         const int G = group_width(p->K);
         const int blocks = (p->N + 256 / G - 1) / (256 / G);
 #define SGR_FB(GW)                                                                                                   \
     field_backward_kernel<GW><<<blocks, 256, 0, st>>>(a, scaling, g_density, g_nbr_opacity, g_beta, g_sdf, g_x, grec)
+        sgr::prof_begin(K_FIELD_BWD, st);
         switch (G) {
             case 1: SGR_FB(1); break;
             case 2: SGR_FB(2); break;
@@ -361,10 +366,12 @@ int sgr_field_backward(const SgrFieldParams *p, const float *x, const int64_t *n
             case 16: SGR_FB(16); break;
             default: SGR_FB(32); break;
         }
+        sgr::prof_end(st);
 #undef SGR_FB
     }
-    field_unpack_kernel<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, (const float4 *)grec, g_points, g_scaling,
-                                                            g_quaternions, g_strengths);
+    SGR_LAUNCH(K_FIELD_UNPACK, st,
+               field_unpack_kernel<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, (const float4 *)grec, g_points, g_scaling,
+                                                                       g_quaternions, g_strengths));
     SGR_CUDA(cudaGetLastError());
     return SGR_OK;
 }

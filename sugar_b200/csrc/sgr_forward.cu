@@ -609,15 +609,19 @@ static int launch_binning_and_blend(const ViewConsts &v, int P, const GeomState 
                                     const BinState &bin, uint64_t capacity, float *out_color, cudaStream_t st)
 {
     const int T = v.gx * v.gy;
-    scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, v.gx, geom.rect, geom.depth, img.tile_cursor, img.counters,
-                                                    capacity, bin.inst_a);
-    tile_sort_kernel<256, false><<<T, 256, 2 * SORT_CAP * 8, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
-                                                                  bin.inst_b, bin.plist);
-    tile_sort_kernel<1024, true><<<T, 1024, 0, st>>>(img.tile_start, img.counters, capacity, bin.inst_a, bin.inst_b,
-                                                    bin.plist);
-    blend_forward_kernel<<<dim3(v.gx, v.gy), dim3(SGR_TILE, SGR_TILE), 0, st>>>(
-        img.tile_start, bin.plist, geom.rec, img.counters, capacity, v.W, v.H, v.gx, v.bg, img.final_T, img.n_contrib,
-        out_color);
+    SGR_LAUNCH(K_SCATTER, st,
+               scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, v.gx, geom.rect, geom.depth, img.tile_cursor,
+                                                               img.counters, capacity, bin.inst_a));
+    SGR_LAUNCH(K_SORT_SMEM, st,
+               tile_sort_kernel<256, false><<<T, 256, 2 * SORT_CAP * 8, st>>>(img.tile_start, img.counters, capacity,
+                                                                             bin.inst_a, bin.inst_b, bin.plist));
+    SGR_LAUNCH(K_SORT_GLOBAL, st,
+               tile_sort_kernel<1024, true><<<T, 1024, 0, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
+                                                               bin.inst_b, bin.plist));
+    SGR_LAUNCH(K_BLEND_FWD, st,
+               blend_forward_kernel<<<dim3(v.gx, v.gy), dim3(SGR_TILE, SGR_TILE), 0, st>>>(
+                   img.tile_start, bin.plist, geom.rec, img.counters, capacity, v.W, v.H, v.gx, v.bg, img.final_T,
+                   img.n_contrib, out_color));
     SGR_CUDA(cudaGetLastError());
     return SGR_OK;
 }
@@ -692,8 +696,10 @@ int launch_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc geom_all
     a.geom = geom;
     a.radii = radii;
     a.tile_count = img.tile_count;
-    preprocess_kernel<<<(P + PRE_T - 1) / PRE_T, PRE_T, dyn, st>>>(a);
-    tile_scan_kernel<<<1, 1024, 0, st>>>(img.tile_count, img.tile_start, img.tile_cursor, img.counters, T, nullptr);
+    SGR_LAUNCH(K_PREPROCESS, st, preprocess_kernel<<<(P + PRE_T - 1) / PRE_T, PRE_T, dyn, st>>>(a));
+    SGR_LAUNCH(K_TILE_SCAN, st,
+               tile_scan_kernel<<<1, 1024, 0, st>>>(img.tile_count, img.tile_start, img.tile_cursor, img.counters, T,
+                                                    nullptr));
     SGR_CUDA(cudaGetLastError());
     SGR_CUDA(cudaMemcpyAsync(slot->pinned, img.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SGR_CUDA(cudaEventRecord(slot->ev, st));

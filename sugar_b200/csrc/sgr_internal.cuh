@@ -114,6 +114,22 @@ struct ViewConsts {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 
+// Kernel bookkeeping: every launch of one of OUR kernels goes through SGR_LAUNCH so that
+// sgr_launch_count() is a measured number and, when profiling is switched on, each launch is
+// bracketed by CUDA events on the launching stream (bench.py reads the per-kernel durations).
+enum KernelKind {
+    K_PREPROCESS = 0, K_TILE_SCAN, K_SCATTER, K_SORT_SMEM, K_SORT_GLOBAL, K_BLEND_FWD, K_BLEND_BWD, K_PRE_BWD,
+    K_FIELD_PACK, K_FIELD_FWD, K_FIELD_BWD, K_FIELD_UNPACK, K_MISC, K_NUM_KINDS
+};
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(cudaStream_t st);
+#define SGR_LAUNCH(kind, st, ...)     \
+    do {                              \
+        sgr::prof_begin((kind), (st)); \
+        __VA_ARGS__;                  \
+        sgr::prof_end((st));          \
+    } while (0)
+
 #define SGR_CUDA(call)                                            \
     do {                                                          \
         cudaError_t e__ = (call);                                 \

@@ -1,0 +1,107 @@
+"""Fused SuGaR density / SDF field (the surface-regularisation inner loop).
+
+Mirrors the semantics of `SuGaR.get_field_values` and `SuGaR.compute_density`
+(sugar_scene/sugar_model.py:1247-1316, 1345-1368; beta_mode 'average', :1192-1195) for given
+neighbour indices: the K-neighbour gather, L^-1 = R(q) diag(1/s) (get_covariance, :730-750),
+the Gaussian opacities, their sum, the straight-through clamp, beta and the SDF run in ONE CUDA
+kernel (sgr_field_forward), and the backward (sgr_field_backward) scatters gradients to points,
+scaling, quaternions, strengths and the samples.
+
+    fields = field_values(x, closest_gaussians_idx, points, scaling, quaternions, strengths,
+                          density_factor=1/16, density_threshold=1., return_sdf=True, ...)
+    fields['density'], fields['sdf'], fields['beta'], fields['closest_gaussian_opacities']
+
+`quaternions` are the normalised (w,x,y,z) quaternions SuGaR.quaternions returns; gradients are
+taken through pytorch3d's quaternion_to_matrix (two_s = 2/|q|^2) exactly like the reference.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import SgrFieldParams, check, lib
+
+
+def _params(N, K, P, density_factor, density_threshold, opacity_min_clamp):
+    p = SgrFieldParams()
+    p.N, p.K, p.P = int(N), int(K), int(P)
+    p.density_factor = float(density_factor)
+    p.density_threshold = float(density_threshold)
+    p.opacity_min_clamp = float(opacity_min_clamp)
+    return p
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class _Field(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, nbr_idx, points, scaling, quaternions, strengths, density_factor, density_threshold,
+                opacity_min_clamp):
+        if not x.is_cuda:
+            raise RuntimeError("sugar_b200.field needs CUDA tensors: there is no CPU fallback")
+        x, points, scaling, quaternions = (t.contiguous().float() for t in (x, points, scaling, quaternions))
+        strengths = strengths.contiguous().float()
+        nbr_idx = nbr_idx.contiguous().long()
+        N, K, P = x.shape[0], nbr_idx.shape[1], points.shape[0]
+        dev = x.device
+        with torch.cuda.device(dev):
+            density = torch.empty(N, device=dev)
+            nbr = torch.empty((N, K), device=dev)
+            beta = torch.empty(N, device=dev)
+            sdf = torch.empty(N, device=dev)
+            scratch = torch.empty(lib.sgr_field_scratch_bytes(P), dtype=torch.uint8, device=dev)
+            p = _params(N, K, P, density_factor, density_threshold, opacity_min_clamp)
+            check(lib.sgr_field_forward(C.byref(p), _ptr(x), _ptr(nbr_idx), _ptr(points), _ptr(scaling),
+                                        _ptr(quaternions), _ptr(strengths), _ptr(density), _ptr(nbr), _ptr(beta),
+                                        _ptr(sdf), _ptr(scratch), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(x, nbr_idx, points, scaling, quaternions, strengths)
+        ctx.cfg = (density_factor, density_threshold, opacity_min_clamp, strengths.shape)
+        ctx.mark_non_differentiable(nbr_idx)
+        return density, nbr, beta, sdf
+
+    @staticmethod
+    def backward(ctx, g_density, g_nbr, g_beta, g_sdf):
+        x, nbr_idx, points, scaling, quaternions, strengths = ctx.saved_tensors
+        density_factor, density_threshold, opacity_min_clamp, s_shape = ctx.cfg
+        N, K, P = x.shape[0], nbr_idx.shape[1], points.shape[0]
+        dev = x.device
+        c = lambda g: None if g is None else g.contiguous().float()
+        g_density, g_nbr, g_beta, g_sdf = map(c, (g_density, g_nbr, g_beta, g_sdf))
+        with torch.cuda.device(dev):
+            g_x = torch.empty_like(x)
+            g_points = torch.empty_like(points)
+            g_scaling = torch.empty_like(scaling)
+            g_quat = torch.empty_like(quaternions)
+            g_str = torch.empty(P, device=dev)
+            scratch = torch.empty(lib.sgr_field_scratch_bytes(P), dtype=torch.uint8, device=dev)
+            p = _params(N, K, P, density_factor, density_threshold, opacity_min_clamp)
+            check(lib.sgr_field_backward(C.byref(p), _ptr(x), _ptr(nbr_idx), _ptr(points), _ptr(scaling),
+                                         _ptr(quaternions), _ptr(strengths), _ptr(g_density), _ptr(g_nbr), _ptr(g_beta),
+                                         _ptr(g_sdf), _ptr(g_x), _ptr(g_points), _ptr(g_scaling), _ptr(g_quat),
+                                         _ptr(g_str), _ptr(scratch), torch.cuda.current_stream(dev).cuda_stream))
+        return g_x, None, g_points, g_scaling, g_quat, g_str.view(s_shape), None, None, None
+
+
+def field_values(x, closest_gaussians_idx, points, scaling, quaternions, strengths, density_factor=1.,
+                 density_threshold=1., opacity_min_clamp=1e-16, return_sdf=True,
+                 return_closest_gaussian_opacities=False, return_beta=False):
+    """SuGaR.get_field_values for explicit neighbour indices (closest_gaussians_idx = knn_idx[gaussian_idx])."""
+    density, nbr, beta, sdf = _Field.apply(x, closest_gaussians_idx, points, scaling, quaternions, strengths,
+                                           density_factor, density_threshold, opacity_min_clamp)
+    fields = {"density": density}
+    if return_closest_gaussian_opacities:
+        fields["closest_gaussian_opacities"] = nbr
+    if return_beta:
+        fields["beta"] = beta
+    if return_sdf:
+        fields["sdf"] = sdf
+    return fields
+
+
+def compute_density(x, closest_gaussians_idx, points, scaling, quaternions, strengths, density_factor=1.,
+                    return_closest_gaussian_opacities=False):
+    """SuGaR.compute_density (sugar_model.py:1345-1368) for given neighbour indices."""
+    density, nbr, _, _ = _Field.apply(x, closest_gaussians_idx, points, scaling, quaternions, strengths,
+                                      density_factor, 1.0, 1e-16)
+    return (density, nbr) if return_closest_gaussian_opacities else density

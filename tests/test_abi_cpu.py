@@ -1,0 +1,55 @@
+"""CPU checks of the C ABI: libsugar_b200.so loads without a GPU and exports every function
+include/sugar_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "sugar_b200.h")).read()
+    return sorted(set(re.findall(r"SGR_API[^;(]*?\b(sgr_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sugar_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 15
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sugar_b200.h but not exported"
+    assert set(_lib.PROTOTYPES) == set(names), (set(names) ^ set(_lib.PROTOTYPES))
+
+
+def test_sizes_and_errors_without_gpu():
+    from sugar_b200 import _lib
+    L = _lib.lib
+    assert b"sm_100a" in L.sgr_version()
+    assert L.sgr_geometry_bytes(1000) >= 1000 * 64
+    assert L.sgr_binning_bytes(0) > 0
+    assert L.sgr_image_bytes(1920, 1080) >= 1920 * 1080 * 8
+    assert L.sgr_backward_scratch_bytes(10) >= 480
+    # argument validation happens before any CUDA call
+    v = _lib.SgrView(); g = _lib.SgrGaussians()
+    v.image_width, v.image_height, g.P = 0, 0, 5
+    n = ctypes.c_int64(0)
+    cb = _lib.ALLOC_FN(lambda ctx, n: 0)
+    rc = L.sgr_rasterize_forward(ctypes.byref(v), ctypes.byref(g), cb, None, cb, None, cb, None, None, None, 0,
+                                 ctypes.byref(n), None)
+    assert rc == -1 and b"bad sizes" in L.sgr_last_error()
+
+
+def test_dropin_module_surface():
+    from sugar_b200 import diff_gaussian_rasterization as m
+    assert m.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+    import inspect
+    sig = inspect.signature(m.GaussianRasterizer.forward)
+    assert list(sig.parameters) == ["self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                    "rotations", "cov3D_precomp"]
+    assert list(inspect.signature(m.rasterize_gaussians).parameters) == [
+        "means3D", "means2D", "sh", "colors_precomp", "opacities", "scales", "rotations", "cov3Ds_precomp",
+        "raster_settings"]
+    assert hasattr(m.GaussianRasterizer, "markVisible")

@@ -1,0 +1,76 @@
+"""GPU: fused density / SDF field kernels vs the CPU oracle (values and gradients) and vs the
+golden vectors of the reference's own code.  fp32 tolerance: 2e-5 relative per tensor for values,
+1e-4 for gradients (sums of N*K atomically accumulated terms)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as h
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def _run_ours(case, weights, dev="cuda"):
+    from sugar_b200 import field
+    leaf = {k: torch.from_numpy(case[k]).to(dev).requires_grad_(True)
+            for k in ("x", "points", "scaling", "quaternions", "strengths")}
+    out = field.field_values(leaf["x"], torch.from_numpy(case["nbr_idx"]).to(dev), leaf["points"], leaf["scaling"],
+                             leaf["quaternions"], leaf["strengths"], density_factor=case["density_factor"],
+                             density_threshold=case["density_threshold"], return_sdf=True,
+                             return_closest_gaussian_opacities=True, return_beta=True)
+    loss = sum((out[k] * torch.from_numpy(weights[k]).to(dev)).sum() for k in weights)
+    loss.backward()
+    return out, {k: v.grad for k, v in leaf.items()}
+
+
+@pytest.mark.parametrize("name", ["c1_1k_2k", "k8"])
+def test_field_matches_reference_golden(name):
+    from make_field_golden import CASES
+    from oracle import field_oracle as fo
+    gold = np.load(os.path.join(HERE, "golden", f"field_{name}.npz"))
+    case = fo.make_case(density_threshold=1.0, **CASES[name])
+    w = {k: gold["w_" + k] for k in ("density", "sdf", "beta", "closest_gaussian_opacities")}
+    out, grads = _run_ours(case, w)
+    for k in w:
+        assert h.rel_err(out[k].detach().cpu().numpy(), gold[k]) < 2e-5, k
+    for k, g in grads.items():
+        assert h.rel_err(g.cpu().numpy(), gold["grad_" + k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("P,N,K", [(5000, 20000, 16), (3000, 7001, 5), (2000, 4000, 32)])
+def test_field_matches_oracle(P, N, K):
+    from oracle import field_oracle as fo
+    case = fo.make_case(P=P, N=N, K=K, seed=P % 97, density_factor=1.0 / K)
+    rng = np.random.default_rng(1)
+    w = {"density": rng.normal(size=N).astype(np.float32), "sdf": rng.normal(size=N).astype(np.float32),
+         "beta": rng.normal(size=N).astype(np.float32),
+         "closest_gaussian_opacities": rng.normal(size=(N, K)).astype(np.float32)}
+    out, grads = _run_ours(case, w)
+    leaf = {k: torch.from_numpy(case[k]).clone().requires_grad_(True)
+            for k in ("x", "points", "scaling", "quaternions", "strengths")}
+    ref = fo.field_values_torch(leaf["x"], torch.from_numpy(case["nbr_idx"]), leaf["points"], leaf["scaling"],
+                                leaf["quaternions"], leaf["strengths"], case["density_factor"], 1.0)
+    sum((ref[k] * torch.from_numpy(w[k])).sum() for k in w).backward()
+    for k in w:
+        assert h.rel_err(out[k].detach().cpu().numpy(), ref[k].detach().numpy()) < 2e-5, k
+    for k, g in grads.items():
+        assert h.rel_err(g.cpu().numpy(), leaf[k].grad.numpy()) < 1e-4, k
+
+
+def test_compute_density_and_empty():
+    from oracle import field_oracle as fo
+    from sugar_b200 import field
+    case = fo.make_case(P=800, N=1500, K=16, seed=4, density_factor=1 / 16)
+    t = {k: torch.from_numpy(v).cuda() for k, v in case.items() if isinstance(v, np.ndarray)}
+    d, nb = field.compute_density(t["x"], t["nbr_idx"], t["points"], t["scaling"], t["quaternions"], t["strengths"],
+                                  density_factor=1 / 16, return_closest_gaussian_opacities=True)
+    ref = fo.field_values(**case)
+    assert h.rel_err(d.cpu().numpy(), ref["density"]) < 2e-5
+    assert h.rel_err(nb.cpu().numpy(), ref["closest_gaussian_opacities"]) < 2e-5
+    e = field.field_values(t["x"][:0], t["nbr_idx"][:0], t["points"], t["scaling"], t["quaternions"], t["strengths"])
+    assert e["density"].numel() == 0 and e["sdf"].numel() == 0

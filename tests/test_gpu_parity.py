@@ -84,12 +84,18 @@ def test_matches_reference_build(case):
     # backward
     a = h.run_module(ours, sc, bg, dL, **opts)
     b = h.run_module(ref, sc, bg, dL, **opts)
+    b2 = h.run_module(ref, sc, bg, dL, **opts)  # the reference's own atomics noise, run to run
     assert set(a["grads"]) == set(b["grads"])
+    bad = []
     for k in sorted(b["grads"]):
-        ga, gb = a["grads"][k].cpu().numpy(), b["grads"][k].cpu().numpy()
+        ga, gb, gb2 = (x["grads"][k].cpu().numpy() for x in (a, b, b2))
         assert ga.shape == gb.shape
-        err = h.rel_err(ga, gb)
-        assert err <= GRAD_RTOL, f"grad {k}: rel err {err:.3e}"
+        err, noise = h.rel_err(ga, gb), h.rel_err(gb2, gb)
+        # 1e-4, except where the reference cannot reproduce itself to 2e-5 (surface-aligned
+        # Gaussians with a 1e-6 axis: cancellation in the scale/rotation chain): there 5x its noise.
+        if err > max(GRAD_RTOL, 5.0 * noise):
+            bad.append(f"grad {k}: rel err {err:.3e} (reference run-to-run {noise:.1e})")
+    assert not bad, "; ".join(bad)
 
 
 @pytest.mark.parametrize("case", CASES[:5], ids=[c[0] for c in CASES[:5]])

@@ -1,0 +1,52 @@
+"""Host-side multi-rank logic on CPU (gloo, world_size 2): view sharding and the flat gradient
+arena all-reduce of sugar_b200.parallel.  No CUDA involved."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sugar_b200 import parallel
+    P, M = 50, 16
+    g = torch.Generator().manual_seed(100 + rank)
+    shapes = dict(means3D=(P, 3), shs=(P, M, 3), opacities=(P, 1), scales=(P, 3), rotations=(P, 4))
+    params = {k: torch.zeros(s, requires_grad=True) for k, s in shapes.items()}
+    for k, p in params.items():
+        p.grad = torch.randn(p.shape, generator=g)
+    local = {k: p.grad.clone() for k, p in params.items()}
+    arena = parallel.GradArena(P, M, "cpu")
+    arena.all_reduce_from(params, 1.0 / world)
+    arena.unpack_to(params)
+    q.put((rank, {k: v for k, v in local.items()}, {k: p.grad.clone() for k, p in params.items()},
+           parallel.shard_views(8, rank, world)))
+    dist.destroy_process_group()
+
+
+def test_arena_allreduce_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort(key=lambda r: r[0])
+    for k in res[0][1]:
+        mean = (res[0][1][k] + res[1][1][k]) / world
+        for r in res:
+            assert torch.allclose(r[2][k], mean, atol=1e-7), k
+    assert res[0][3] == [0, 2, 4, 6] and res[1][3] == [1, 3, 5, 7]
+    assert 59 * 50 == sum(n for _, n in __import__("sugar_b200.parallel", fromlist=["x"]).GradArena(50, 16, "cpu").offsets.values())
