@@ -262,10 +262,13 @@ def main():
     torch.cuda.synchronize()
     V_vis = int((radii > 0).sum())
 
+    if not use_ref:
+        _lib.profile(True)   # allocates the event pool
+        step_device()
+        torch.cuda.synchronize()
+        _lib.profile_read()
     launches0 = 0 if use_ref else _lib.lib.sgr_launch_count()
     clocks = ClockSampler(local)
-    if not use_ref:
-        _lib.profile(True)
     ms = timed(step_device, args.steps)
     prof = {}
     if not use_ref:

@@ -172,6 +172,7 @@ SGR_API int sgr_num_kernel_kinds(void);
 SGR_API const char *sgr_kernel_name(int kind);
 SGR_API int sgr_profile_enable(int on);
 SGR_API int sgr_profile_read(float *total_ms, int *counts);
+SGR_API int sgr_profile_timeline(int max_records, int *kinds, float *t_begin_ms, float *t_end_ms);
 
 SGR_API const char *sgr_last_error(void);
 SGR_API const char *sgr_version(void);

@@ -32,17 +32,38 @@ def _ptr(t: torch.Tensor, name: str):
     return t.data_ptr()
 
 
+_ROUND = 64 << 20  # arena sizes are rounded up to 64 MiB so the caching allocator sees few distinct sizes
+
+
+def _round_up(n: int, a: int) -> int:
+    return (n + a - 1) // a * a
+
+
 class _Arena:
-    """Allocator callback state: keeps the torch tensor alive and hands its pointer to C."""
+    """Allocator-callback state.  One torch allocation backs all three opaque buffers of a forward
+    (carved at 256-byte offsets): per-step allocations of stable, rounded sizes keep the caching
+    allocator from fragmenting (and from calling cudaMalloc, a device-wide stall) in steady state."""
 
-    def __init__(self, device):
+    def __init__(self, device, reserve_bytes: int):
         self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = _lib.ALLOC_FN(self._alloc)
+        self.block = torch.empty(_round_up(reserve_bytes, _ROUND), dtype=torch.uint8, device=device) if reserve_bytes else None
+        self.used = 0
+        self.parts = {}
+        self.cbs = {name: _lib.ALLOC_FN(lambda _ctx, n, name=name: self._alloc(name, n)) for name in ("geom", "binning", "img")}
 
-    def _alloc(self, _ctx, nbytes):
-        self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self.tensor.data_ptr()
+    def _alloc(self, name, nbytes):
+        nbytes = int(nbytes)
+        if self.block is not None and self.used + nbytes + 256 <= self.block.numel():
+            off = _round_up(self.block.data_ptr() + self.used, 256) - self.block.data_ptr()
+            t = self.block[off:off + nbytes]
+            self.used = off + nbytes
+        else:  # no (or too small a) reservation: plain allocation, still rounded
+            t = torch.empty(_round_up(nbytes, _ROUND), dtype=torch.uint8, device=self.device)[:nbytes]
+        self.parts[name] = t
+        return t.data_ptr()
+
+    def get(self, name):
+        return self.parts.get(name, torch.empty(0, dtype=torch.uint8, device=self.device))
 
 
 def _view_struct(bg, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, degree, campos, prefiltered,
@@ -92,24 +113,28 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     with torch.cuda.device(dev):
         out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom, binning, img = _Arena(dev), _Arena(dev), _Arena(dev)
+        key = (dev.index, H, W)
+        hint = _capacity_hint.get(key, 0) if _USE_HINT else 0
+        reserve = lib.sgr_geometry_bytes(P) + lib.sgr_image_bytes(W, H) + 1024
+        if hint:
+            reserve += lib.sgr_binning_bytes(hint)
+        arena = _Arena(dev, reserve if P else 0)
         means3D, colors, opacity, scales, rotations, cov3D_precomp, sh = map(
             _c, (means3D, colors, opacity, scales, rotations, cov3D_precomp, sh))
         background, viewmatrix, projmatrix, campos = map(_c, (background, viewmatrix, projmatrix, campos))
         view = _view_struct(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, degree,
                             campos, prefiltered, debug)
         g = _gauss_struct(P, M, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp)
-        key = (dev.index, H, W)
-        hint = _capacity_hint.get(key, 0) if _USE_HINT else 0
         rendered = C.c_int64(0)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        check(lib.sgr_rasterize_forward(C.byref(view), C.byref(g), geom.cb, None, binning.cb, None, img.cb, None,
-                                        out_color.data_ptr(), radii.data_ptr() if P else None, hint,
-                                        C.byref(rendered), stream))
+        check(lib.sgr_rasterize_forward(C.byref(view), C.byref(g), arena.cbs["geom"], None, arena.cbs["binning"], None,
+                                        arena.cbs["img"], None, out_color.data_ptr(), radii.data_ptr() if P else None,
+                                        hint, C.byref(rendered), stream))
         R = int(rendered.value)
         if P:
-            _capacity_hint[key] = int(R * 1.25) + 65536
-    return R, out_color, radii, geom.tensor, binning.tensor, img.tensor
+            # next view's optimistic capacity: 25% headroom, rounded to 1M instances (stable sizes)
+            _capacity_hint[key] = _round_up(int(R * 1.25) + 65536, 1 << 20)
+    return R, out_color, radii, arena.get("geom"), arena.get("binning"), arena.get("img")
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
@@ -120,20 +145,28 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     P, H, W = means3D.size(0), dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
     with torch.cuda.device(dev):
-        opts = dict(dtype=torch.float32, device=dev)
-        dL_dmeans3D = torch.empty((P, 3), **opts)
-        dL_dmeans2D = torch.empty((P, 3), **opts)
-        dL_dcolors = torch.empty((P, 3), **opts)
-        dL_dopacity = torch.empty((P, 1), **opts)
-        dL_dcov3D = torch.empty((P, 6), **opts)
-        dL_dsh = torch.empty((P, M, 3), **opts)
-        dL_dscales = torch.empty((P, 3), **opts)
-        dL_drotations = torch.empty((P, 4), **opts)
+        # all eight gradients + the accumulator scratch live in ONE rounded allocation (views below)
+        widths = (3, 3, 3, 1, 6, 3 * M, 3, 4)
+        n_scratch = (lib.sgr_backward_scratch_bytes(P) + 3) // 4 if P else 0
+        flat = torch.empty(_round_up(4 * (P * sum(widths) + n_scratch) + 256, _ROUND) // 4, dtype=torch.float32, device=dev)
+        offs, o = [], 0
+        for w in widths:
+            offs.append(o)
+            o += P * w
+        part = lambda k, shape: flat[offs[k]:offs[k] + P * widths[k]].view(shape)
+        dL_dmeans3D = part(0, (P, 3))
+        dL_dmeans2D = part(1, (P, 3))
+        dL_dcolors = part(2, (P, 3))
+        dL_dopacity = part(3, (P, 1))
+        dL_dcov3D = part(4, (P, 6))
+        dL_dsh = part(5, (P, M, 3))
+        dL_dscales = part(6, (P, 3))
+        dL_drotations = part(7, (P, 4))
         if P != 0:
             means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color = map(
                 _c, (means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color))
             background, viewmatrix, projmatrix, campos = map(_c, (background, viewmatrix, projmatrix, campos))
-            scratch = torch.empty(lib.sgr_backward_scratch_bytes(P), dtype=torch.uint8, device=dev)
+            scratch = flat[o:o + n_scratch]
             view = _view_struct(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, degree,
                                 campos, False, debug)
             # opacities are not an input of the reference's backward; the forward stored them

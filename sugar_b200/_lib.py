@@ -62,6 +62,7 @@ PROTOTYPES = {
     "sgr_kernel_name": (C.c_char_p, [C.c_int]),
     "sgr_profile_enable": (C.c_int, [C.c_int]),
     "sgr_profile_read": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgr_profile_timeline": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sgr_last_error": (C.c_char_p, []),
     "sgr_version": (C.c_char_p, []),
 }
@@ -99,3 +100,14 @@ def profile_read():
     cnt = (C.c_int * n)()
     check(lib.sgr_profile_read(ms, cnt))
     return {lib.sgr_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}
+
+
+def profile_timeline(max_records: int = 4096):
+    """-> [(kernel name, begin_ms, end_ms)] of every launch since profiling was enabled."""
+    kinds = (C.c_int * max_records)()
+    tb = (C.c_float * max_records)()
+    te = (C.c_float * max_records)()
+    n = lib.sgr_profile_timeline(max_records, kinds, tb, te)
+    if n < 0:
+        check(n)
+    return [(lib.sgr_kernel_name(kinds[i]).decode(), float(tb[i]), float(te[i])) for i in range(n)]

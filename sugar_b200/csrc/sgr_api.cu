@@ -189,9 +189,36 @@ const char *sgr_kernel_name(int kind) { return (kind >= 0 && kind < K_NUM_KINDS)
 
 int sgr_profile_enable(int on)
 {
+    if (on && g_prof_cap == 0) {  // create the event pool up front, outside any timed region
+        const int ncap = 8192;
+        ProfRec *np = (ProfRec *)malloc(sizeof(ProfRec) * ncap);
+        if (!np) {
+            set_error("out of host memory for the profile log");
+            return SGR_ENOMEM;
+        }
+        for (int i = 0; i < ncap; i++) {
+            SGR_CUDA(cudaEventCreate(&np[i].a));
+            SGR_CUDA(cudaEventCreate(&np[i].b));
+        }
+        g_prof = np;
+        g_prof_cap = ncap;
+    }
     g_prof_on = on != 0;
     if (on) g_prof_n = 0;
     return SGR_OK;
+}
+
+int sgr_profile_timeline(int max_records, int *kinds, float *t_begin_ms, float *t_end_ms)
+{
+    // per-launch begin/end times relative to the first recorded launch (does not reset the log)
+    const int n = g_prof_n < max_records ? g_prof_n : max_records;
+    for (int i = 0; i < n; i++) {
+        SGR_CUDA(cudaEventSynchronize(g_prof[i].b));
+        kinds[i] = g_prof[i].kind;
+        SGR_CUDA(cudaEventElapsedTime(&t_begin_ms[i], g_prof[0].a, g_prof[i].a));
+        SGR_CUDA(cudaEventElapsedTime(&t_end_ms[i], g_prof[0].a, g_prof[i].b));
+    }
+    return n;
 }
 
 int sgr_profile_read(float *total_ms, int *counts)

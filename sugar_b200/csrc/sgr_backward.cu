@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
     __shared__ float2 s_c[BWD_B];
     __shared__ uint32_t s_id[BWD_B];
     __shared__ float s_acc[BWD_NW][BWD_B][9];
-    __shared__ uint32_t s_mask[BWD_NW][BWD_B / 32];
+    __shared__ uint32_t s_member[BWD_NW][BWD_B / 32];  // splats whose footprint reaches strip w
+    __shared__ uint32_t s_touched[BWD_NW][BWD_B / 32]; // splats warp w produced partial sums for
 
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int tid = threadIdx.y * SGR_TILE + threadIdx.x;
@@ -78,14 +79,16 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
     const uint32_t pxi = blockIdx.x * SGR_TILE + threadIdx.x, pyi = blockIdx.y * SGR_TILE + threadIdx.y;
     const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
     const float pxf = (float)pxi, pyf = (float)pyi;
+    const float tx0 = (float)(blockIdx.x * SGR_TILE), ty0 = (float)(blockIdx.y * SGR_TILE);
     const uint32_t lo = tile_start[tile], hi = tile_start[tile + 1];
-    const int n = (int)(hi - lo);
-    if (n == 0) return;
+    if (hi == lo) return;
+    __shared__ int s_tile_last;
+    if (tid == 0) s_tile_last = 0;
 
     const size_t pix = (size_t)pyi * W + pxi, plane = (size_t)H * W;
     const float T_final = inside ? final_Ts[pix] : 0.0f;
     float T = T_final;
-    const uint32_t last_contributor = inside ? n_contrib[pix] : 0u;
+    const int last_contributor = inside ? (int)n_contrib[pix] : 0;
     float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
     if (inside) {
         dp0 = dL_dpixels[pix];
@@ -95,35 +98,58 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
     const float bg_dot = fmaf(bg[2], dp2, fmaf(bg[1], dp1, bg[0] * dp0));
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-    uint32_t contributor = (uint32_t)n;
+    // Splats behind the deepest last contributor of the warp (of the tile) cannot touch any of its
+    // pixels: the tile only walks list positions [0, tile_last), each warp only [0, warp_last).
+    const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
+    __syncthreads();
+    if (lane == 0 && warp_last > 0) atomicMax(&s_tile_last, warp_last);
+    __syncthreads();
+    const int n = s_tile_last;
+    if (n == 0) return;
 
     for (int b0 = 0; b0 < n; b0 += BWD_B) {
         __syncthreads();
-        if (tid < BWD_B && b0 + tid < n) {
-            const uint32_t id = plist[hi - 1 - (uint32_t)(b0 + tid)];
-            const float4 *r = rec + (size_t)id * 3;
-            const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-            s_id[tid] = id;
-            s_a[tid] = r0;
-            s_b[tid] = r1;
-            s_c[tid] = make_float2(r2.x, r2.y);
+        uint32_t mask = 0;
+        if (tid < BWD_B) {
+            if (b0 + tid < n) {
+                const uint32_t id = plist[lo + (uint32_t)(n - 1 - (b0 + tid))];  // back to front
+                const float4 *r = rec + (size_t)id * 3;
+                const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+                s_id[tid] = id;
+                s_a[tid] = r0;
+                s_b[tid] = r1;
+                s_c[tid] = make_float2(r2.x, r2.y);
+                mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+            }
+#pragma unroll
+            for (int sidx = 0; sidx < BWD_NW; sidx++) {
+                const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
+                if (lane == 0) s_member[sidx][wid] = word;
+            }
         }
         __syncthreads();
         const int m = min(BWD_B, n - b0);
+        const int jmin = n - b0 - warp_last;  // first batch slot whose list position is < warp_last
 #pragma unroll 1
         for (int c = 0; c * 32 < m; c++) {
             uint32_t touched = 0;
-            const int jend = min(32, m - c * 32);
+            uint32_t mw = s_member[wid][c];
+            const int cut = jmin - c * 32;
+            if (cut >= 32) mw = 0;
+            else if (cut > 0) mw &= ~((1u << cut) - 1u);
 #pragma unroll 1
-            for (int jj = 0; jj < jend; jj++) {
+            while (mw) {
+                const int jj = __ffs(mw) - 1;
+                mw &= mw - 1;
                 const int j = c * 32 + jj;
-                contributor--;
+                const int pos = n - 1 - (b0 + j);  // position in the front-to-back list
                 const float4 A = s_a[j];
                 const float4 B = s_b[j];
                 const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                 const float power = splat_power(dx, dy, A.z, A.w, B.x);
-                bool valid = inside && contributor < last_contributor && !(power > 0.0f) && !(power < B.y);
+                bool valid = pos < last_contributor && !(power > 0.0f) && !(power < B.y);
                 if (!__any_sync(0xffffffffu, valid)) continue;
+                // v[0..5] moments of S = dL/dG * G, v[6..7] + v8 colour gradients
                 float v[8], v8 = 0.f;
 #pragma unroll
                 for (int k = 0; k < 8; k++) v[k] = 0.f;
@@ -133,8 +159,7 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
                     valid = !(alpha < 1.0f / 255.0f);
                     if (valid) {
                         const float2 Cc = s_c[j];
-                        const float one_m = 1.0f - alpha;
-                        const float inv = __frcp_rn(one_m);
+                        const float inv = __fdividef(1.0f, 1.0f - alpha);  // 1-alpha in [0.01, 1): MUFU.RCP suffices
                         T = T * inv;
                         const float dchannel = alpha * T;
                         const float la = last_alpha, om_la = 1.0f - last_alpha;
@@ -150,16 +175,14 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
                         dL_dalpha *= T;
                         last_alpha = alpha;
                         dL_dalpha = fmaf(-T_final * inv, bg_dot, dL_dalpha);
-                        const float dL_dG = B.z * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * A.z - gdy * A.w;
-                        const float dG_ddely = -gdy * B.x - gdx * A.w;
-                        v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                        v[1] = dL_dG * dG_ddely * ddely_dy;
-                        v[2] = -0.5f * gdx * dx * dL_dG;
-                        v[3] = -0.5f * gdx * dy * dL_dG;
-                        v[4] = -0.5f * gdy * dy * dL_dG;
-                        v[5] = G * dL_dalpha;
+                        const float S = B.z * dL_dalpha * G;
+                        const float Sx = S * dx, Sy = S * dy;
+                        v[0] = S;
+                        v[1] = Sx;
+                        v[2] = Sy;
+                        v[3] = Sx * dx;
+                        v[4] = Sx * dy;
+                        v[5] = Sy * dy;
                         v[6] = dchannel * dp0;
                         v[7] = dchannel * dp1;
                         v8 = dchannel * dp2;
@@ -172,7 +195,7 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
                 if (lane == 1) s_acc[wid][j][8] = v8;
                 touched |= 1u << jj;
             }
-            if (lane == 0) s_mask[wid][c] = touched;
+            if (lane == 0) s_touched[wid][c] = touched;
         }
         __syncthreads();
         if (tid < m) {
@@ -182,16 +205,21 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
             bool any = false;
 #pragma unroll
             for (int w = 0; w < BWD_NW; w++) {
-                if ((s_mask[w][tid >> 5] >> (tid & 31)) & 1u) {
+                if ((s_touched[w][tid >> 5] >> (tid & 31)) & 1u) {
                     any = true;
 #pragma unroll
                     for (int k = 0; k < 9; k++) s[k] += s_acc[w][tid][k];
                 }
             }
             if (any) {
+                // moments -> gradients (backward.cu:537-554): dG/ddel = -G (Q d)
+                const float4 A = s_a[tid];
+                const float4 B = s_b[tid];
+                const float gmx = -(A.z * s[1] + A.w * s[2]) * ddelx_dx;
+                const float gmy = -(B.x * s[2] + A.w * s[1]) * ddely_dy;
                 float *g = gacc + (size_t)s_id[tid] * 12;
-                red_add_v4(g, s[0], s[1], s[2], s[3]);
-                red_add_v4(g + 4, s[4], s[5], s[6], s[7]);
+                red_add_v4(g, gmx, gmy, -0.5f * s[3], -0.5f * s[4]);
+                red_add_v4(g + 4, -0.5f * s[5], s[0] / B.z, s[6], s[7]);
                 atomicAdd(g + 8, s[8]);
             }
         }
@@ -199,7 +227,11 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-Gaussian backward (cov2D inverse, projection, SH, scale/rotation), one fused pass
+// per-Gaussian backward (cov2D inverse, projection, SH, scale/rotation), one fused pass.
+// HBM-bound: every input array is staged into shared memory with coalesced transfers (1-D bulk
+// copies through the TMA engine for the contiguous arrays, 16-byte cp.async into padded rows for
+// the SH block), each thread works on its own Gaussian out of shared memory, the SH gradient
+// overwrites the SH row in place, and all outputs leave through coalesced stores.
 // ------------------------------------------------------------------------------------------------
 struct PreBwdArgs {
     int P;
@@ -209,6 +241,7 @@ struct PreBwdArgs {
     const uint32_t *aux;  // clamp bits
     const float *gacc;
     float *dmeans2D, *dcolors, *dopacity, *dmeans3D, *dcov3D, *dsh, *dscales, *drots;
+    int bulk_ok, sh_stride, sh_vec;
 };
 
 #define SH_C0 0.28209479177387814f
@@ -222,246 +255,362 @@ __constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 struct f3 {
     float x, y, z;
 };
-__device__ __forceinline__ f3 operator*(float s, f3 a) { return {s * a.x, s * a.y, s * a.z}; }
-__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
-// SH backward (backward.cu:20-139).  sh/dsh rows are [M][3] floats in global memory.
-__device__ __forceinline__ void sh_backward(int deg, const float *__restrict__ sh, float *__restrict__ dsh, int M,
-                                            f3 dir_orig, f3 dRGB, f3 &dmean)
+// SH backward (backward.cu:20-139) on one shared-memory row [M][3], in place: row k is read once
+// (t_k = <sh_k, dL/dRGB> feeds the view-direction gradient) and then overwritten by dL/dsh_k.
+__device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *row, f3 dir_orig, f3 dRGB, f3 &dmean)
 {
     const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
     const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-    auto S = [&](int k) -> f3 { return {sh[k * 3], sh[k * 3 + 1], sh[k * 3 + 2]}; };
-    auto D = [&](int k, float w) {
-        dsh[k * 3] = w * dRGB.x;
-        dsh[k * 3 + 1] = w * dRGB.y;
-        dsh[k * 3 + 2] = w * dRGB.z;
-    };
-    f3 dx = {0, 0, 0}, dy = {0, 0, 0}, dz = {0, 0, 0};
-    D(0, SH_C0);
+    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#define SHB(k, w, cx, cy, cz)                                                          \
+    {                                                                                  \
+        float *q_ = row + (k) * 3;                                                     \
+        const float t_ = q_[0] * dRGB.x + q_[1] * dRGB.y + q_[2] * dRGB.z;             \
+        ddx += (cx) * t_;                                                              \
+        ddy += (cy) * t_;                                                              \
+        ddz += (cz) * t_;                                                              \
+        const float w_ = (w);                                                          \
+        q_[0] = w_ * dRGB.x;                                                           \
+        q_[1] = w_ * dRGB.y;                                                           \
+        q_[2] = w_ * dRGB.z;                                                           \
+    }
+    SHB(0, SH_C0, 0.f, 0.f, 0.f);
     if (deg > 0) {
-        D(1, -SH_C1 * y);
-        D(2, SH_C1 * z);
-        D(3, -SH_C1 * x);
-        dx = -SH_C1 * S(3);
-        dy = -SH_C1 * S(1);
-        dz = SH_C1 * S(2);
+        SHB(1, -SH_C1 * y, 0.f, -SH_C1, 0.f);
+        SHB(2, SH_C1 * z, 0.f, 0.f, SH_C1);
+        SHB(3, -SH_C1 * x, -SH_C1, 0.f, 0.f);
         if (deg > 1) {
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            D(4, b_SH_C2[0] * xy);
-            D(5, b_SH_C2[1] * yz);
-            D(6, b_SH_C2[2] * (2.f * zz - xx - yy));
-            D(7, b_SH_C2[3] * xz);
-            D(8, b_SH_C2[4] * (xx - yy));
-            const f3 s4 = S(4), s5 = S(5), s6 = S(6), s7 = S(7), s8 = S(8);
-            dx = dx + (b_SH_C2[0] * y) * s4 + (b_SH_C2[2] * 2.f * -x) * s6 + (b_SH_C2[3] * z) * s7 + (b_SH_C2[4] * 2.f * x) * s8;
-            dy = dy + (b_SH_C2[0] * x) * s4 + (b_SH_C2[1] * z) * s5 + (b_SH_C2[2] * 2.f * -y) * s6 + (b_SH_C2[4] * 2.f * -y) * s8;
-            dz = dz + (b_SH_C2[1] * y) * s5 + (b_SH_C2[2] * 2.f * 2.f * z) * s6 + (b_SH_C2[3] * x) * s7;
+            SHB(4, b_SH_C2[0] * xy, b_SH_C2[0] * y, b_SH_C2[0] * x, 0.f);
+            SHB(5, b_SH_C2[1] * yz, 0.f, b_SH_C2[1] * z, b_SH_C2[1] * y);
+            SHB(6, b_SH_C2[2] * (2.f * zz - xx - yy), b_SH_C2[2] * 2.f * -x, b_SH_C2[2] * 2.f * -y, b_SH_C2[2] * 2.f * 2.f * z);
+            SHB(7, b_SH_C2[3] * xz, b_SH_C2[3] * z, 0.f, b_SH_C2[3] * x);
+            SHB(8, b_SH_C2[4] * (xx - yy), b_SH_C2[4] * 2.f * x, b_SH_C2[4] * 2.f * -y, 0.f);
             if (deg > 2) {
-                D(9, b_SH_C3[0] * y * (3.f * xx - yy));
-                D(10, b_SH_C3[1] * xy * z);
-                D(11, b_SH_C3[2] * y * (4.f * zz - xx - yy));
-                D(12, b_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
-                D(13, b_SH_C3[4] * x * (4.f * zz - xx - yy));
-                D(14, b_SH_C3[5] * z * (xx - yy));
-                D(15, b_SH_C3[6] * x * (xx - 3.f * yy));
-                const f3 s9 = S(9), s10 = S(10), s11 = S(11), s12 = S(12), s13 = S(13), s14 = S(14), s15 = S(15);
-                dx = dx + (b_SH_C3[0] * 3.f * 2.f * xy) * s9 + (b_SH_C3[1] * yz) * s10 + (b_SH_C3[2] * -2.f * xy) * s11 +
-                     (b_SH_C3[3] * -3.f * 2.f * xz) * s12 + (b_SH_C3[4] * (-3.f * xx + 4.f * zz - yy)) * s13 +
-                     (b_SH_C3[5] * 2.f * xz) * s14 + (b_SH_C3[6] * 3.f * (xx - yy)) * s15;
-                dy = dy + (b_SH_C3[0] * 3.f * (xx - yy)) * s9 + (b_SH_C3[1] * xz) * s10 +
-                     (b_SH_C3[2] * (-3.f * yy + 4.f * zz - xx)) * s11 + (b_SH_C3[3] * -3.f * 2.f * yz) * s12 +
-                     (b_SH_C3[4] * -2.f * xy) * s13 + (b_SH_C3[5] * -2.f * yz) * s14 + (b_SH_C3[6] * -3.f * 2.f * xy) * s15;
-                dz = dz + (b_SH_C3[1] * xy) * s10 + (b_SH_C3[2] * 4.f * 2.f * yz) * s11 +
-                     (b_SH_C3[3] * 3.f * (2.f * zz - xx - yy)) * s12 + (b_SH_C3[4] * 4.f * 2.f * xz) * s13 +
-                     (b_SH_C3[5] * (xx - yy)) * s14;
+                SHB(9, b_SH_C3[0] * y * (3.f * xx - yy), b_SH_C3[0] * 3.f * 2.f * xy, b_SH_C3[0] * 3.f * (xx - yy), 0.f);
+                SHB(10, b_SH_C3[1] * xy * z, b_SH_C3[1] * yz, b_SH_C3[1] * xz, b_SH_C3[1] * xy);
+                SHB(11, b_SH_C3[2] * y * (4.f * zz - xx - yy), b_SH_C3[2] * -2.f * xy,
+                    b_SH_C3[2] * (-3.f * yy + 4.f * zz - xx), b_SH_C3[2] * 4.f * 2.f * yz);
+                SHB(12, b_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy), b_SH_C3[3] * -3.f * 2.f * xz,
+                    b_SH_C3[3] * -3.f * 2.f * yz, b_SH_C3[3] * 3.f * (2.f * zz - xx - yy));
+                SHB(13, b_SH_C3[4] * x * (4.f * zz - xx - yy), b_SH_C3[4] * (-3.f * xx + 4.f * zz - yy),
+                    b_SH_C3[4] * -2.f * xy, b_SH_C3[4] * 4.f * 2.f * xz);
+                SHB(14, b_SH_C3[5] * z * (xx - yy), b_SH_C3[5] * 2.f * xz, b_SH_C3[5] * -2.f * yz, b_SH_C3[5] * (xx - yy));
+                SHB(15, b_SH_C3[6] * x * (xx - 3.f * yy), b_SH_C3[6] * 3.f * (xx - yy), b_SH_C3[6] * -3.f * 2.f * xy, 0.f);
             }
         }
     }
+#undef SHB
     // rows above the active degree stay zero (the reference returns zero-filled dL_dsh)
-    const int used = (deg + 1) * (deg + 1);
-    for (int k = used; k < M; k++) {
-        dsh[k * 3] = 0.f;
-        dsh[k * 3 + 1] = 0.f;
-        dsh[k * 3 + 2] = 0.f;
-    }
-    const f3 ddir = {dot3(dx, dRGB), dot3(dy, dRGB), dot3(dz, dRGB)};
+    for (int k = (deg + 1) * (deg + 1) * 3; k < M * 3; k++) row[k] = 0.f;
     // dnormvdv (auxiliary.h:107-117)
     const f3 o = dir_orig;
     const float sum2 = o.x * o.x + o.y * o.y + o.z * o.z;
     const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-    dmean.x += ((+sum2 - o.x * o.x) * ddir.x - o.y * o.x * ddir.y - o.z * o.x * ddir.z) * invsum32;
-    dmean.y += (-o.x * o.y * ddir.x + (sum2 - o.y * o.y) * ddir.y - o.z * o.y * ddir.z) * invsum32;
-    dmean.z += (-o.x * o.z * ddir.x - o.y * o.z * ddir.y + (sum2 - o.z * o.z) * ddir.z) * invsum32;
+    dmean.x += ((+sum2 - o.x * o.x) * ddx - o.y * o.x * ddy - o.z * o.x * ddz) * invsum32;
+    dmean.y += (-o.x * o.y * ddx + (sum2 - o.y * o.y) * ddy - o.z * o.y * ddz) * invsum32;
+    dmean.z += (-o.x * o.z * ddx - o.y * o.z * ddy + (sum2 - o.z * o.z) * ddz) * invsum32;
 }
 
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(const PreBwdArgs a)
-{
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.P) return;
-    const int M = a.v.M;
-    const bool vis = a.radii[i] > 0;
-    if (!vis) {
-        a.dmeans2D[3 * i] = a.dmeans2D[3 * i + 1] = a.dmeans2D[3 * i + 2] = 0.f;
-        a.dcolors[3 * i] = a.dcolors[3 * i + 1] = a.dcolors[3 * i + 2] = 0.f;
-        a.dopacity[i] = 0.f;
-        a.dmeans3D[3 * i] = a.dmeans3D[3 * i + 1] = a.dmeans3D[3 * i + 2] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 6; k++) a.dcov3D[6 * i + k] = 0.f;
-        a.dscales[3 * i] = a.dscales[3 * i + 1] = a.dscales[3 * i + 2] = 0.f;
-        a.drots[4 * i] = a.drots[4 * i + 1] = a.drots[4 * i + 2] = a.drots[4 * i + 3] = 0.f;
-        if (a.dsh)
-            for (int k = 0; k < M * 3; k++) a.dsh[(size_t)i * M * 3 + k] = 0.f;
-        return;
-    }
-    const float4 *gr = (const float4 *)(a.gacc + (size_t)i * 12);
-    const float4 g0 = gr[0], g1 = gr[1];
-    const float g2 = a.gacc[(size_t)i * 12 + 8];
-    const float dmx = g0.x, dmy = g0.y;
-    const float dcx = g0.z, dcy = g0.w, dcz = g1.x;
-    a.dmeans2D[3 * i] = dmx;
-    a.dmeans2D[3 * i + 1] = dmy;
-    a.dmeans2D[3 * i + 2] = 0.f;
-    a.dopacity[i] = g1.y;
-    a.dcolors[3 * i] = g1.z;
-    a.dcolors[3 * i + 1] = g1.w;
-    a.dcolors[3 * i + 2] = g2;
+constexpr int PB_T = 256;
+// dynamic shared memory carve-up (floats): inputs then outputs then the SH block
+constexpr int PB_GACC = 0;                    // PB_T*12
+constexpr int PB_MEANS = PB_GACC + PB_T * 12; // PB_T*3
+constexpr int PB_SCALES = PB_MEANS + PB_T * 3;
+constexpr int PB_ROTS = PB_SCALES + PB_T * 3; // PB_T*4 (16B aligned: offset is a multiple of 4 floats)
+constexpr int PB_COV = PB_ROTS + PB_T * 4;    // PB_T*6
+constexpr int PB_O_M2D = PB_COV + PB_T * 6;   // outputs
+constexpr int PB_O_COL = PB_O_M2D + PB_T * 3;
+constexpr int PB_O_OPA = PB_O_COL + PB_T * 3;
+constexpr int PB_O_M3D = PB_O_OPA + PB_T;
+constexpr int PB_O_COV = PB_O_M3D + PB_T * 3;
+constexpr int PB_O_SCL = PB_O_COV + PB_T * 6;
+constexpr int PB_O_ROT = PB_O_SCL + PB_T * 3;  // multiple of 4 floats
+constexpr int PB_SH = PB_O_ROT + PB_T * 4;     // PB_T * sh_stride
+static_assert(PB_ROTS % 4 == 0 && PB_O_ROT % 4 == 0 && PB_SH % 4 == 0, "16-byte alignment of float4 regions");
 
-    const float *vm = a.v.viewmatrix, *proj = a.v.projmatrix;
-    const float mx = a.means[3 * i], my = a.means[3 * i + 1], mz = a.means[3 * i + 2];
-    float c3[6];
-    float4 q = make_float4(1, 0, 0, 0);
-    float sc0 = 0, sc1 = 0, sc2 = 0;
-    if (a.cov_pre) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) c3[k] = a.cov_pre[6 * i + k];
+__device__ __forceinline__ void pb_stage(float *dst, const float *__restrict__ src, int n)
+{
+    for (int i = threadIdx.x; i < n; i += PB_T) dst[i] = __ldg(src + i);
+}
+__device__ __forceinline__ void pb_flush(float *__restrict__ dst, const float *src, int n)
+{
+    for (int i = threadIdx.x; i < n; i += PB_T) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdArgs a)
+{
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * PB_T;
+    const int n = min(PB_T, a.P - base);
+    const int i = base + tid;
+    const int M = a.v.M;
+    const bool full = (n == PB_T);
+
+    if (a.bulk_ok && full) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            uint32_t bytes = PB_T * 48 + PB_T * 12;
+            if (a.scales) bytes += PB_T * 12 + PB_T * 16;
+            if (a.cov_pre) bytes += PB_T * 24;
+            mbar_expect_tx(&s_bar, bytes);
+            bulk_g2s(sm + PB_GACC, a.gacc + (size_t)base * 12, PB_T * 48, &s_bar);
+            bulk_g2s(sm + PB_MEANS, a.means + (size_t)base * 3, PB_T * 12, &s_bar);
+            if (a.scales) {
+                bulk_g2s(sm + PB_SCALES, a.scales + (size_t)base * 3, PB_T * 12, &s_bar);
+                bulk_g2s(sm + PB_ROTS, a.rots + (size_t)base * 4, PB_T * 16, &s_bar);
+            }
+            if (a.cov_pre) bulk_g2s(sm + PB_COV, a.cov_pre + (size_t)base * 6, PB_T * 24, &s_bar);
+        }
     } else {
-        sc0 = a.scales[3 * i], sc1 = a.scales[3 * i + 1], sc2 = a.scales[3 * i + 2];
-        q = ((const float4 *)a.rots)[i];
-        cov3d_from_scale_rot(sc0, sc1, sc2, a.v.scale_modifier, q, c3);
+        pb_stage(sm + PB_GACC, a.gacc + (size_t)base * 12, n * 12);
+        pb_stage(sm + PB_MEANS, a.means + (size_t)base * 3, n * 3);
+        if (a.scales) {
+            pb_stage(sm + PB_SCALES, a.scales + (size_t)base * 3, n * 3);
+            pb_stage(sm + PB_ROTS, a.rots + (size_t)base * 4, n * 4);
+        }
+        if (a.cov_pre) pb_stage(sm + PB_COV, a.cov_pre + (size_t)base * 6, n * 6);
     }
-    // ---- computeCov2DCUDA (backward.cu:144-274) ----
-    float tx = xf_row(vm, 0, mx, my, mz), ty = xf_row(vm, 1, mx, my, mz);
-    const float tzv = xf_row(vm, 2, mx, my, mz);
-    const float h_x = a.v.focal_x, h_y = a.v.focal_y;
-    const float limx = 1.3f * a.v.tanfovx, limy = 1.3f * a.v.tanfovy;
-    const float txtz = tx / tzv, tytz = ty / tzv;
-    tx = fminf(limx, fmaxf(-limx, txtz)) * tzv;
-    ty = fminf(limy, fmaxf(-limy, tytz)) * tzv;
-    const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
-    const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
-    const float J00 = h_x / tzv, J02 = -(h_x * tx) / (tzv * tzv), J11 = h_y / tzv, J12 = -(h_y * ty) / (tzv * tzv);
-    float T0[3], T1[3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        T0[r] = vm[4 * r] * J00 + vm[2 + 4 * r] * J02;
-        T1[r] = vm[1 + 4 * r] * J11 + vm[2 + 4 * r] * J12;
-    }
-    const float V[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
-    float p[3], qv[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        p[k] = T0[0] * V[k][0] + T0[1] * V[k][1] + T0[2] * V[k][2];
-        qv[k] = T1[0] * V[k][0] + T1[1] * V[k][1] + T1[2] * V[k][2];
-    }
-    const float ca = T0[0] * p[0] + T0[1] * p[1] + T0[2] * p[2] + 0.3f;
-    const float cb = T0[0] * qv[0] + T0[1] * qv[1] + T0[2] * qv[2];
-    const float cc = T1[0] * qv[0] + T1[1] * qv[1] + T1[2] * qv[2] + 0.3f;
-    const float denom = ca * cc - cb * cb;
-    float dL_da = 0, dL_db = 0, dL_dc = 0;
-    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-    float dcov[6];
-    if (denom2inv != 0) {
-        dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
-        dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
-        dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
-        dcov[0] = (T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc);
-        dcov[3] = (T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc);
-        dcov[5] = (T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc);
-        dcov[1] = 2 * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2 * T1[0] * T1[1] * dL_dc;
-        dcov[2] = 2 * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2 * T1[0] * T1[2] * dL_dc;
-        dcov[4] = 2 * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2 * T1[1] * T1[2] * dL_dc;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 6; k++) dcov[k] = 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 6; k++) a.dcov3D[6 * i + k] = dcov[k];
-    float dT0[3], dT1[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        dT0[k] = 2 * p[k] * dL_da + qv[k] * dL_db;
-        dT1[k] = 2 * qv[k] * dL_dc + p[k] * dL_db;
-    }
-    const float dJ00 = vm[0] * dT0[0] + vm[4] * dT0[1] + vm[8] * dT0[2];
-    const float dJ02 = vm[2] * dT0[0] + vm[6] * dT0[1] + vm[10] * dT0[2];
-    const float dJ11 = vm[1] * dT1[0] + vm[5] * dT1[1] + vm[9] * dT1[2];
-    const float dJ12 = vm[2] * dT1[0] + vm[6] * dT1[1] + vm[10] * dT1[2];
-    const float tz = 1.f / tzv, tz2 = tz * tz, tz3 = tz2 * tz;
-    const float dtx = x_grad_mul * -h_x * tz2 * dJ02;
-    const float dty = y_grad_mul * -h_y * tz2 * dJ12;
-    const float dtz = -h_x * tz2 * dJ00 - h_y * tz2 * dJ11 + (2 * h_x * tx) * tz3 * dJ02 + (2 * h_y * ty) * tz3 * dJ12;
-    f3 dmean = {vm[0] * dtx + vm[1] * dty + vm[2] * dtz, vm[4] * dtx + vm[5] * dty + vm[6] * dtz,
-                vm[8] * dtx + vm[9] * dty + vm[10] * dtz};
-    // ---- preprocessCUDA backward (backward.cu:346-396) ----
-    const float hw = xf_row(proj, 3, mx, my, mz);
-    const float m_w = 1.0f / (hw + 0.0000001f);
-    const float mul1 = (proj[0] * mx + proj[4] * my + proj[8] * mz + proj[12]) * m_w * m_w;
-    const float mul2 = (proj[1] * mx + proj[5] * my + proj[9] * mz + proj[13]) * m_w * m_w;
-    dmean.x += (proj[0] * m_w - proj[3] * mul1) * dmx + (proj[1] * m_w - proj[3] * mul2) * dmy;
-    dmean.y += (proj[4] * m_w - proj[7] * mul1) * dmx + (proj[5] * m_w - proj[7] * mul2) * dmy;
-    dmean.z += (proj[8] * m_w - proj[11] * mul1) * dmx + (proj[9] * m_w - proj[11] * mul2) * dmy;
+    float *s_sh = sm + PB_SH;
+    const int row_f = M * 3;
     if (a.shs) {
-        const uint32_t cl = a.aux[i];
-        const f3 dRGB = {(cl & 1u) ? 0.f : g1.z, (cl & 2u) ? 0.f : g1.w, (cl & 4u) ? 0.f : g2};
-        const float *cp = a.v.campos;
-        sh_backward(a.v.D, a.shs + (size_t)i * M * 3, a.dsh + (size_t)i * M * 3, M, {mx - cp[0], my - cp[1], mz - cp[2]},
-                    dRGB, dmean);
+        const float *src = a.shs + (size_t)base * row_f;
+        if (a.sh_vec) {
+            const int row_v = row_f >> 2, total = n * row_v;
+            int r = tid / row_v, c = tid - r * row_v;
+            const int dr = PB_T / row_v, dc = PB_T - dr * row_v;
+            for (int k = tid; k < total; k += PB_T) {
+                cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)k * 4);
+                r += dr;
+                c += dc;
+                if (c >= row_v) {
+                    c -= row_v;
+                    r++;
+                }
+            }
+        } else {
+            const int total = n * row_f;
+            for (int k = tid; k < total; k += PB_T) {
+                const int r = k / row_f, c = k - r * row_f;
+                cp_async4(s_sh + r * a.sh_stride + c, src + k);
+            }
+        }
+        cp_async_commit();
     }
-    a.dmeans3D[3 * i] = dmean.x;
-    a.dmeans3D[3 * i + 1] = dmean.y;
-    a.dmeans3D[3 * i + 2] = dmean.z;
-    // ---- computeCov3D backward (backward.cu:278-341) ----
-    if (a.scales) {
-        const float r = q.x, x = q.y, y = q.z, z = q.w;
-        // R[col][row], glm layout
-        const float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
-                               {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
-                               {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
-        const float s[3] = {a.v.scale_modifier * sc0, a.v.scale_modifier * sc1, a.v.scale_modifier * sc2};
-        const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
-                                {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
-                                {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-        // dL_dM[c][w] = sum_k 2 M[k][w] dS[c][k], M[k][w] = s[w] R[k][w];  dMt[c][w] = dM[w][c]
-        float dMt[3][3];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int w = 0; w < 3; w++)
-                dMt[w][c] = 2.0f * s[w] * R[0][w] * dS[c][0] + 2.0f * s[w] * R[1][w] * dS[c][1] + 2.0f * s[w] * R[2][w] * dS[c][2];
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            a.dscales[3 * i + k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-#pragma unroll
-            for (int w = 0; w < 3; w++) dMt[k][w] *= s[k];
-        float4 dq;
-        dq.x = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
-        dq.y = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) -
-               4 * x * (dMt[2][2] + dMt[1][1]);
-        dq.z = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) -
-               4 * y * (dMt[2][2] + dMt[0][0]);
-        dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) -
-               4 * z * (dMt[1][1] + dMt[0][0]);
-        ((float4 *)a.drots)[i] = dq;
-    } else {
-        a.dscales[3 * i] = a.dscales[3 * i + 1] = a.dscales[3 * i + 2] = 0.f;
-        ((float4 *)a.drots)[i] = make_float4(0, 0, 0, 0);
+    int radius = 0;
+    uint32_t cl = 0;
+    if (tid < n) {
+        radius = a.radii[i];
+        if (a.shs) cl = a.aux[i];
     }
-    if (!a.shs && a.dsh)
-        for (int k = 0; k < M * 3; k++) a.dsh[(size_t)i * M * 3 + k] = 0.f;
+    __syncthreads();
+    if (a.bulk_ok && full) mbar_wait(&s_bar, 0);
+    if (a.shs) {
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    if (tid < n) {
+        const bool vis = radius > 0;
+        float *o_m2d = sm + PB_O_M2D + tid * 3, *o_col = sm + PB_O_COL + tid * 3, *o_m3d = sm + PB_O_M3D + tid * 3;
+        float *o_cov = sm + PB_O_COV + tid * 6, *o_scl = sm + PB_O_SCL + tid * 3;
+        float4 *o_rot = (float4 *)(sm + PB_O_ROT) + tid;
+        float *row = s_sh + tid * a.sh_stride;
+        if (!vis) {
+            o_m2d[0] = o_m2d[1] = o_m2d[2] = 0.f;
+            o_col[0] = o_col[1] = o_col[2] = 0.f;
+            sm[PB_O_OPA + tid] = 0.f;
+            o_m3d[0] = o_m3d[1] = o_m3d[2] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++) o_cov[k] = 0.f;
+            o_scl[0] = o_scl[1] = o_scl[2] = 0.f;
+            *o_rot = make_float4(0, 0, 0, 0);
+            if (a.shs)
+                for (int k = 0; k < row_f; k++) row[k] = 0.f;
+        } else {
+            const float4 *gr = (const float4 *)(sm + PB_GACC) + tid * 3;
+            const float4 g0 = gr[0], g1 = gr[1];
+            const float g2 = gr[2].x;
+            const float dmx = g0.x, dmy = g0.y;
+            const float dcx = g0.z, dcy = g0.w, dcz = g1.x;
+            o_m2d[0] = dmx;
+            o_m2d[1] = dmy;
+            o_m2d[2] = 0.f;
+            sm[PB_O_OPA + tid] = g1.y;
+            o_col[0] = g1.z;
+            o_col[1] = g1.w;
+            o_col[2] = g2;
+
+            const float *vm = a.v.viewmatrix, *proj = a.v.projmatrix;
+            const float mx = sm[PB_MEANS + tid * 3], my = sm[PB_MEANS + tid * 3 + 1], mz = sm[PB_MEANS + tid * 3 + 2];
+            float c3[6];
+            float4 q = make_float4(1, 0, 0, 0);
+            float sc0 = 0, sc1 = 0, sc2 = 0;
+            if (a.cov_pre) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c3[k] = sm[PB_COV + tid * 6 + k];
+            } else {
+                sc0 = sm[PB_SCALES + tid * 3], sc1 = sm[PB_SCALES + tid * 3 + 1], sc2 = sm[PB_SCALES + tid * 3 + 2];
+                q = ((const float4 *)(sm + PB_ROTS))[tid];
+                cov3d_from_scale_rot(sc0, sc1, sc2, a.v.scale_modifier, q, c3);
+            }
+            // ---- computeCov2DCUDA (backward.cu:144-274) ----
+            float tx = xf_row(vm, 0, mx, my, mz), ty = xf_row(vm, 1, mx, my, mz);
+            const float tzv = xf_row(vm, 2, mx, my, mz);
+            const float h_x = a.v.focal_x, h_y = a.v.focal_y;
+            const float limx = 1.3f * a.v.tanfovx, limy = 1.3f * a.v.tanfovy;
+            const float txtz = tx / tzv, tytz = ty / tzv;
+            tx = fminf(limx, fmaxf(-limx, txtz)) * tzv;
+            ty = fminf(limy, fmaxf(-limy, tytz)) * tzv;
+            const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+            const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+            const float J00 = h_x / tzv, J02 = -(h_x * tx) / (tzv * tzv), J11 = h_y / tzv, J12 = -(h_y * ty) / (tzv * tzv);
+            float T0[3], T1[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                T0[r] = vm[4 * r] * J00 + vm[2 + 4 * r] * J02;
+                T1[r] = vm[1 + 4 * r] * J11 + vm[2 + 4 * r] * J12;
+            }
+            const float V[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+            float p[3], qv[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                p[k] = T0[0] * V[k][0] + T0[1] * V[k][1] + T0[2] * V[k][2];
+                qv[k] = T1[0] * V[k][0] + T1[1] * V[k][1] + T1[2] * V[k][2];
+            }
+            const float ca = T0[0] * p[0] + T0[1] * p[1] + T0[2] * p[2] + 0.3f;
+            const float cb = T0[0] * qv[0] + T0[1] * qv[1] + T0[2] * qv[2];
+            const float cc = T1[0] * qv[0] + T1[1] * qv[1] + T1[2] * qv[2] + 0.3f;
+            const float denom = ca * cc - cb * cb;
+            float dL_da = 0, dL_db = 0, dL_dc = 0;
+            const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+            float dcov[6];
+            if (denom2inv != 0) {
+                dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
+                dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
+                dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
+                dcov[0] = (T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc);
+                dcov[3] = (T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc);
+                dcov[5] = (T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc);
+                dcov[1] = 2 * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2 * T1[0] * T1[1] * dL_dc;
+                dcov[2] = 2 * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2 * T1[0] * T1[2] * dL_dc;
+                dcov[4] = 2 * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2 * T1[1] * T1[2] * dL_dc;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) dcov[k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) o_cov[k] = dcov[k];
+            float dT0[3], dT1[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                dT0[k] = 2 * p[k] * dL_da + qv[k] * dL_db;
+                dT1[k] = 2 * qv[k] * dL_dc + p[k] * dL_db;
+            }
+            const float dJ00 = vm[0] * dT0[0] + vm[4] * dT0[1] + vm[8] * dT0[2];
+            const float dJ02 = vm[2] * dT0[0] + vm[6] * dT0[1] + vm[10] * dT0[2];
+            const float dJ11 = vm[1] * dT1[0] + vm[5] * dT1[1] + vm[9] * dT1[2];
+            const float dJ12 = vm[2] * dT1[0] + vm[6] * dT1[1] + vm[10] * dT1[2];
+            const float tz = 1.f / tzv, tz2 = tz * tz, tz3 = tz2 * tz;
+            const float dtx = x_grad_mul * -h_x * tz2 * dJ02;
+            const float dty = y_grad_mul * -h_y * tz2 * dJ12;
+            const float dtz = -h_x * tz2 * dJ00 - h_y * tz2 * dJ11 + (2 * h_x * tx) * tz3 * dJ02 + (2 * h_y * ty) * tz3 * dJ12;
+            f3 dmean = {vm[0] * dtx + vm[1] * dty + vm[2] * dtz, vm[4] * dtx + vm[5] * dty + vm[6] * dtz,
+                        vm[8] * dtx + vm[9] * dty + vm[10] * dtz};
+            // ---- preprocessCUDA backward (backward.cu:346-396) ----
+            const float hw = xf_row(proj, 3, mx, my, mz);
+            const float m_w = 1.0f / (hw + 0.0000001f);
+            const float mul1 = (proj[0] * mx + proj[4] * my + proj[8] * mz + proj[12]) * m_w * m_w;
+            const float mul2 = (proj[1] * mx + proj[5] * my + proj[9] * mz + proj[13]) * m_w * m_w;
+            dmean.x += (proj[0] * m_w - proj[3] * mul1) * dmx + (proj[1] * m_w - proj[3] * mul2) * dmy;
+            dmean.y += (proj[4] * m_w - proj[7] * mul1) * dmx + (proj[5] * m_w - proj[7] * mul2) * dmy;
+            dmean.z += (proj[8] * m_w - proj[11] * mul1) * dmx + (proj[9] * m_w - proj[11] * mul2) * dmy;
+            if (a.shs) {
+                const f3 dRGB = {(cl & 1u) ? 0.f : g1.z, (cl & 2u) ? 0.f : g1.w, (cl & 4u) ? 0.f : g2};
+                const float *cp = a.v.campos;
+                sh_backward_inplace(a.v.D, M, row, {mx - cp[0], my - cp[1], mz - cp[2]}, dRGB, dmean);
+            }
+            o_m3d[0] = dmean.x;
+            o_m3d[1] = dmean.y;
+            o_m3d[2] = dmean.z;
+            // ---- computeCov3D backward (backward.cu:278-341) ----
+            if (a.scales) {
+                const float r = q.x, x = q.y, y = q.z, z = q.w;
+                const float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                                       {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                                       {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+                const float s[3] = {a.v.scale_modifier * sc0, a.v.scale_modifier * sc1, a.v.scale_modifier * sc2};
+                const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                        {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                        {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+                float dMt[3][3];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int w = 0; w < 3; w++)
+                        dMt[w][c] = 2.0f * s[w] * R[0][w] * dS[c][0] + 2.0f * s[w] * R[1][w] * dS[c][1] +
+                                    2.0f * s[w] * R[2][w] * dS[c][2];
+#pragma unroll
+                for (int k = 0; k < 3; k++) o_scl[k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+#pragma unroll
+                    for (int w = 0; w < 3; w++) dMt[k][w] *= s[k];
+                float4 dq;
+                dq.x = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+                dq.y = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) -
+                       4 * x * (dMt[2][2] + dMt[1][1]);
+                dq.z = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) -
+                       4 * y * (dMt[2][2] + dMt[0][0]);
+                dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) -
+                       4 * z * (dMt[1][1] + dMt[0][0]);
+                *o_rot = dq;
+            } else {
+                o_scl[0] = o_scl[1] = o_scl[2] = 0.f;
+                *o_rot = make_float4(0, 0, 0, 0);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- coalesced write-out -------------------------------------------------------------------
+    pb_flush(a.dmeans2D + (size_t)base * 3, sm + PB_O_M2D, n * 3);
+    pb_flush(a.dcolors + (size_t)base * 3, sm + PB_O_COL, n * 3);
+    pb_flush(a.dopacity + base, sm + PB_O_OPA, n);
+    pb_flush(a.dmeans3D + (size_t)base * 3, sm + PB_O_M3D, n * 3);
+    pb_flush(a.dcov3D + (size_t)base * 6, sm + PB_O_COV, n * 6);
+    pb_flush(a.dscales + (size_t)base * 3, sm + PB_O_SCL, n * 3);
+    pb_flush(a.drots + (size_t)base * 4, sm + PB_O_ROT, n * 4);
+    if (a.dsh && M > 0) {
+        float *dst = a.dsh + (size_t)base * row_f;
+        if (a.shs) {
+            if (a.sh_vec) {
+                const int row_v = row_f >> 2, total = n * row_v;
+                int r = tid / row_v, c = tid - r * row_v;
+                const int dr = PB_T / row_v, dc = PB_T - dr * row_v;
+                for (int k = tid; k < total; k += PB_T) {
+                    ((float4 *)dst)[k] = *(const float4 *)(s_sh + r * a.sh_stride + c * 4);
+                    r += dr;
+                    c += dc;
+                    if (c >= row_v) {
+                        c -= row_v;
+                        r++;
+                    }
+                }
+            } else {
+                const int total = n * row_f;
+                for (int k = tid; k < total; k += PB_T) {
+                    const int r = k / row_f, c = k - r * row_f;
+                    dst[k] = s_sh[r * a.sh_stride + c];
+                }
+            }
+        } else {
+            for (int k = tid; k < n * row_f; k += PB_T) dst[k] = 0.f;
+        }
+    }
 }
 
 int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
@@ -517,7 +666,31 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     a.dsh = dL_dsh;
     a.dscales = dL_dscales;
     a.drots = dL_drotations;
-    SGR_LAUNCH(K_PRE_BWD, st, preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, st>>>(a));
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    SGR_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[dev] = true;
+    }
+    auto al16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
+    a.bulk_ok = al16(gacc) && al16(g->means3D) && (!g->scales || al16(g->scales)) && (!g->rotations || al16(g->rotations)) &&
+                (!g->cov3D_precomp || al16(g->cov3D_precomp));
+    a.sh_stride = 0;
+    a.sh_vec = 0;
+    if (g->shs) {
+        const int row_f = g->M * 3;
+        if ((row_f % 4) == 0 && al16(g->shs) && al16(dL_dsh)) {
+            int s4 = row_f / 4;
+            if ((s4 & 1) == 0) s4 += 1;
+            a.sh_stride = s4 * 4;
+            a.sh_vec = 1;
+        } else {
+            a.sh_stride = (row_f & 1) ? row_f : row_f + 1;
+        }
+    }
+    const size_t dyn = (size_t)(PB_SH + PB_T * a.sh_stride) * sizeof(float);
+    SGR_LAUNCH(K_PRE_BWD, st, preprocess_backward_kernel<<<(P + PB_T - 1) / PB_T, PB_T, dyn, st>>>(a));
     SGR_CUDA(cudaGetLastError());
     if (view->debug) SGR_CUDA(cudaStreamSynchronize(st));
     return SGR_OK;

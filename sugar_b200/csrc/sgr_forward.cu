@@ -141,9 +141,16 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
         const float *src = a.shs + (size_t)base * row_f;
         if (a.sh_vec) {
             const int row_v = row_f >> 2, total = n * row_v;
+            int r = tid / row_v, c = tid - r * row_v;  // (row, 16-byte column) advanced without divisions
+            const int dr = PRE_T / row_v, dc = PRE_T - dr * row_v;
             for (int i = tid; i < total; i += PRE_T) {
-                const int r = i / row_v, c = i - r * row_v;
                 cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)i * 4);
+                r += dr;
+                c += dc;
+                if (c >= row_v) {
+                    c -= row_v;
+                    r++;
+                }
             }
         } else {
             const int total = n * row_f;
@@ -248,15 +255,21 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
         }
     }
 
-    // ---- per-tile instance counts: the warp walks its members' rects cooperatively -------------
+    // ---- per-tile instance counts.  Small rects (the common case) are walked by their own thread;
+    // rects of more than SMALL tiles are walked by the whole warp so one huge splat cannot stall it.
+    constexpr int SMALL = 6;
     const unsigned lane = tid & 31;
-    unsigned todo = __ballot_sync(0xffffffffu, visible);
+    const int rw = x1 - x0, rcnt = visible ? rw * (y1 - y0) : 0;
+    if (rcnt > 0 && rcnt <= SMALL) {
+        for (int ty = y0; ty < y1; ty++)
+            for (int tx = x0; tx < x1; tx++) atomicAdd(a.tile_count + ty * a.v.gx + tx, 1u);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, rcnt > SMALL);
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
         const int rx0 = __shfl_sync(0xffffffffu, x0, src), ry0 = __shfl_sync(0xffffffffu, y0, src);
-        const int rx1 = __shfl_sync(0xffffffffu, x1, src), ry1 = __shfl_sync(0xffffffffu, y1, src);
-        const int w = rx1 - rx0, cnt = w * (ry1 - ry0);
+        const int w = __shfl_sync(0xffffffffu, rw, src), cnt = __shfl_sync(0xffffffffu, rcnt, src);
         for (int k = lane; k < cnt; k += 32) {
             const int ty = k / w, tx = k - ty * w;
             atomicAdd(a.tile_count + (ry0 + ty) * a.v.gx + rx0 + tx, 1u);
@@ -339,17 +352,25 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, const ushor
         rc = rect[idx];
         if (rc.z > rc.x) dbits = __float_as_uint(depth[idx]);
     }
-    const bool has = (rc.z > rc.x) && (rc.w > rc.y);
-    unsigned todo = __ballot_sync(0xffffffffu, has);
+    constexpr int SMALL = 6;
+    const int rw = (int)rc.z - (int)rc.x, rcnt = (rc.z > rc.x && rc.w > rc.y) ? rw * ((int)rc.w - (int)rc.y) : 0;
+    if (rcnt > 0 && rcnt <= SMALL) {
+        const uint64_t word = ((uint64_t)dbits << 32) | (uint32_t)idx;
+        for (int ty = rc.y; ty < rc.w; ty++)
+            for (int tx = rc.x; tx < rc.z; tx++) {
+                const uint32_t slot = atomicAdd(cursor + ty * gx + tx, 1u);
+                inst[slot] = word;
+            }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, rcnt > SMALL);
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
         const int rx0 = __shfl_sync(0xffffffffu, (int)rc.x, src), ry0 = __shfl_sync(0xffffffffu, (int)rc.y, src);
-        const int rx1 = __shfl_sync(0xffffffffu, (int)rc.z, src), ry1 = __shfl_sync(0xffffffffu, (int)rc.w, src);
+        const int w = __shfl_sync(0xffffffffu, rw, src), cnt = __shfl_sync(0xffffffffu, rcnt, src);
         const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
         const int gid = (idx - (int)lane) + src;
         const uint64_t word = ((uint64_t)db << 32) | (uint32_t)gid;
-        const int w = rx1 - rx0, cnt = w * (ry1 - ry0);
         for (int k = lane; k < cnt; k += 32) {
             const int ty = k / w, tx = k - ty * w;
             const uint32_t slot = atomicAdd(cursor + (ry0 + ty) * gx + rx0 + tx, 1u);
@@ -364,7 +385,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, const ushor
 // in shared memory; the GLOBAL variant (tiles with more than SORT_CAP instances) ping-pongs
 // between inst_a and inst_b in L2/HBM with the same code.
 // ------------------------------------------------------------------------------------------------
-constexpr int SORT_CAP = 4096;
+constexpr int SORT_CAP = 8192;  // largest shared-memory (bitonic) class; above it: global radix
 
 template <int THREADS, bool GLOBAL>
 __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t *__restrict__ tile_start,
@@ -487,10 +508,105 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t *__re
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward blend: one CTA per 16x16 tile, one thread per pixel, splat records gathered
-// once per tile into shared memory.  power / alpha / T / C follow the reference's rounding exactly
-// (forward.cu:261-374), so final_T, n_contrib and the image are bit-identical to the reference;
-// the conservative `power < tau` test only skips pairs the exact alpha test would reject.
+// per-tile sort, shared-memory path: merge sort on the 64-bit (depth|id) words of one tile.
+// Every thread sorts VT=8 words in registers with a 19-comparator network, then log2(n/8) rounds
+// of pairwise run merging in shared memory; in each round a thread finds its output window with a
+// merge-path binary search and merges 8 outputs serially.  The words are distinct (the id is part
+// of the key) so the result is the unique total order = the reference's stable sort by depth.
+// Size classes (LOWER, CAP]: each class is its own launch over all tiles with early exit, so the
+// shared-memory footprint (and occupancy) matches the tile population.
+// ------------------------------------------------------------------------------------------------
+constexpr int SORT_VT = 8;
+
+__device__ __forceinline__ void cswap(uint64_t &a, uint64_t &b)
+{
+    const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo;
+    b = hi;
+}
+
+template <int CAP, int LOWER>
+__global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const uint32_t *__restrict__ tile_start,
+                                                                        const uint32_t *__restrict__ counters,
+                                                                        uint64_t capacity,
+                                                                        const uint64_t *__restrict__ inst,
+                                                                        uint32_t *__restrict__ plist)
+{
+    constexpr int VT = SORT_VT;
+    extern __shared__ __align__(16) uint64_t s_keys[];  // CAP words
+    if ((uint64_t)counters[0] > capacity) return;
+    const int tile = blockIdx.x;
+    const uint32_t lo = tile_start[tile];
+    const int n = (int)(tile_start[tile + 1] - lo);
+    if (n <= LOWER || n > CAP) return;
+    const int tid = threadIdx.x;
+    const int nact = (n + VT - 1) / VT;  // threads that own a window
+    const int L = nact * VT;             // padded length (pad words = all ones sort last)
+    uint64_t r[VT];
+    if (tid < nact) {
+#pragma unroll
+        for (int k = 0; k < VT; k++) {
+            const int i = tid * VT + k;
+            r[k] = i < n ? inst[lo + i] : ~0ull;
+        }
+        cswap(r[0], r[1]); cswap(r[2], r[3]); cswap(r[4], r[5]); cswap(r[6], r[7]);
+        cswap(r[0], r[2]); cswap(r[1], r[3]); cswap(r[4], r[6]); cswap(r[5], r[7]);
+        cswap(r[1], r[2]); cswap(r[5], r[6]);
+        cswap(r[0], r[4]); cswap(r[1], r[5]); cswap(r[2], r[6]); cswap(r[3], r[7]);
+        cswap(r[2], r[4]); cswap(r[3], r[5]);
+        cswap(r[1], r[2]); cswap(r[3], r[4]); cswap(r[5], r[6]);
+#pragma unroll
+        for (int k = 0; k < VT; k++) s_keys[tid * VT + k] = r[k];
+    }
+    for (int run = VT; run < L; run <<= 1) {
+        __syncthreads();
+        if (tid < nact) {
+            const int out0 = tid * VT;
+            const int a0 = out0 & ~(2 * run - 1);
+            const int la = min(run, L - a0);
+            const int b0 = a0 + run;
+            const int lb = max(0, min(run, L - b0));
+            const int diag = out0 - a0;
+            int slo = max(0, diag - lb), shi = min(diag, la);
+            while (slo < shi) {
+                const int mid = (slo + shi) >> 1;
+                if (s_keys[a0 + mid] <= s_keys[b0 + diag - 1 - mid]) slo = mid + 1;
+                else shi = mid;
+            }
+            int i = slo, j = diag - slo;
+            uint64_t ka = i < la ? s_keys[a0 + i] : ~0ull;
+            uint64_t kb = j < lb ? s_keys[b0 + j] : ~0ull;
+#pragma unroll
+            for (int k = 0; k < VT; k++) {
+                const bool takeA = (j >= lb) || (i < la && ka <= kb);
+                r[k] = takeA ? ka : kb;
+                if (takeA) {
+                    i++;
+                    ka = i < la ? s_keys[a0 + i] : ~0ull;
+                } else {
+                    j++;
+                    kb = j < lb ? s_keys[b0 + j] : ~0ull;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < nact) {
+#pragma unroll
+            for (int k = 0; k < VT; k++) s_keys[tid * VT + k] = r[k];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += CAP / VT) plist[lo + i] = (uint32_t)s_keys[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward blend: one CTA per 16x16 tile, one thread per pixel, one warp per 16x2 pixel strip.
+// Splat records are gathered once per tile into shared memory together with an 8-bit strip mask;
+// each warp then walks only the splats whose footprint can reach its strip (ffs over a per-strip
+// membership word) instead of testing every splat of the tile.  power / alpha / T / C follow the
+// reference's rounding exactly (forward.cu:261-374), so final_T, n_contrib and the image are
+// bit-identical to the reference; the strip mask and the `power < tau` test only skip pairs the
+// exact alpha test would reject.
 // ------------------------------------------------------------------------------------------------
 constexpr int BLEND_T = 256;
 
@@ -506,19 +622,22 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
     __shared__ float4 s_a[BLEND_T];  // x, y, conic a, conic b
     __shared__ float4 s_b[BLEND_T];  // conic c, tau, opacity, r
     __shared__ float2 s_c[BLEND_T];  // g, b
+    __shared__ uint32_t s_member[8][BLEND_T / 32];
     if ((uint64_t)counters[0] > capacity) return;
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int tid = threadIdx.y * SGR_TILE + threadIdx.x;
+    const unsigned lane = tid & 31, wid = tid >> 5;
     const uint32_t pxi = blockIdx.x * SGR_TILE + threadIdx.x, pyi = blockIdx.y * SGR_TILE + threadIdx.y;
     const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
     const float pxf = (float)pxi, pyf = (float)pyi;
+    const float tx0 = (float)(blockIdx.x * SGR_TILE), ty0 = (float)(blockIdx.y * SGR_TILE);
     const uint32_t lo = tile_start[tile], hi = tile_start[tile + 1];
-    int todo = (int)(hi - lo);
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint32_t contributor = 0, last = 0;
-    for (uint32_t b0 = lo; b0 < hi; b0 += BLEND_T, todo -= BLEND_T) {
+    uint32_t last = 0;
+    for (uint32_t b0 = lo; b0 < hi; b0 += BLEND_T) {
         if (__syncthreads_count(done) == BLEND_T) break;
+        uint32_t mask = 0;
         if (b0 + tid < hi) {
             const uint32_t id = plist[b0 + tid];
             const float4 *r = rec + (size_t)id * 3;
@@ -526,29 +645,45 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
             s_a[tid] = r0;
             s_b[tid] = r1;
             s_c[tid] = make_float2(r2.x, r2.y);
+            mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+        }
+#pragma unroll
+        for (int sidx = 0; sidx < 8; sidx++) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
+            if (lane == 0) s_member[sidx][wid] = word;
         }
         __syncthreads();
-        const int m = min(BLEND_T, todo);
-        for (int j = 0; !done && j < m; j++) {
-            contributor++;
-            const float4 A = s_a[j];
-            const float4 B = s_b[j];
-            const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
-            const float power = splat_power(dx, dy, A.z, A.w, B.x);
-            if (power > 0.0f || power < B.y) continue;
-            const float alpha = fminf(0.99f, __fmul_rn(B.z, expf(power)));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            if (test_T < 0.0001f) {
-                done = true;
-                continue;
+        const uint32_t base_pos = b0 - lo;
+        if (!__all_sync(0xffffffffu, done)) {
+#pragma unroll 1
+            for (int k = 0; k < BLEND_T / 32; k++) {
+                uint32_t mw = s_member[wid][k];
+#pragma unroll 1
+                while (mw) {
+                    const int j = (k << 5) + __ffs(mw) - 1;
+                    mw &= mw - 1;
+                    if (done) continue;
+                    const float4 A = s_a[j];
+                    const float4 B = s_b[j];
+                    const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
+                    const float power = splat_power(dx, dy, A.z, A.w, B.x);
+                    if (power > 0.0f || power < B.y) continue;
+                    const float alpha = fminf(0.99f, __fmul_rn(B.z, expf(power)));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                    if (test_T < 0.0001f) {
+                        done = true;
+                        continue;
+                    }
+                    const float2 Cc = s_c[j];
+                    C0 = __fmaf_rn(T, __fmul_rn(alpha, B.w), C0);
+                    C1 = __fmaf_rn(T, __fmul_rn(alpha, Cc.x), C1);
+                    C2 = __fmaf_rn(T, __fmul_rn(alpha, Cc.y), C2);
+                    T = test_T;
+                    last = base_pos + (uint32_t)j + 1u;
+                }
+                if (__all_sync(0xffffffffu, done)) break;
             }
-            const float2 Cc = s_c[j];
-            C0 = __fmaf_rn(T, __fmul_rn(alpha, B.w), C0);
-            C1 = __fmaf_rn(T, __fmul_rn(alpha, Cc.x), C1);
-            C2 = __fmaf_rn(T, __fmul_rn(alpha, Cc.y), C2);
-            T = test_T;
-            last = contributor;
         }
     }
     if (inside) {
@@ -595,8 +730,8 @@ static int get_slot(DeviceSlot **out)
     }
     if (!s.attrs_set) {
         SGR_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SGR_CUDA(cudaFuncSetAttribute(tile_sort_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      2 * SORT_CAP * 8));
+        SGR_CUDA(cudaFuncSetAttribute(tile_sort_merge_kernel<8192, 2048>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
         s.attrs_set = true;
     }
     *out = &s;
@@ -612,9 +747,14 @@ static int launch_binning_and_blend(const ViewConsts &v, int P, const GeomState 
     SGR_LAUNCH(K_SCATTER, st,
                scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, v.gx, geom.rect, geom.depth, img.tile_cursor,
                                                                img.counters, capacity, bin.inst_a));
-    SGR_LAUNCH(K_SORT_SMEM, st,
-               tile_sort_kernel<256, false><<<T, 256, 2 * SORT_CAP * 8, st>>>(img.tile_start, img.counters, capacity,
-                                                                             bin.inst_a, bin.inst_b, bin.plist));
+    sgr::prof_begin(K_SORT_SMEM, st);
+    tile_sort_merge_kernel<512, 0><<<T, 512 / SORT_VT, 512 * 8, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
+                                                                      bin.plist);
+    tile_sort_merge_kernel<2048, 512><<<T, 2048 / SORT_VT, 2048 * 8, st>>>(img.tile_start, img.counters, capacity,
+                                                                           bin.inst_a, bin.plist);
+    tile_sort_merge_kernel<8192, 2048><<<T, 8192 / SORT_VT, 8192 * 8, st>>>(img.tile_start, img.counters, capacity,
+                                                                            bin.inst_a, bin.plist);
+    sgr::prof_end(st);
     SGR_LAUNCH(K_SORT_GLOBAL, st,
                tile_sort_kernel<1024, true><<<T, 1024, 0, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
                                                                bin.inst_b, bin.plist));

@@ -251,6 +251,33 @@ __device__ __forceinline__ float splat_power(float dx, float dy, float a, float 
     return __fmaf_rn(q, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, b)));
 }
 
+
+// Conservative footprint of one splat inside a 16x16 tile, as an 8-bit mask over the tile's eight
+// 16x2 pixel strips (= warps of the blend kernels).  {d : power(d) >= tau} is the ellipse
+// d^T Q d <= -2 tau, Q = [[a,b],[b,c]], whose half extents are sqrt(-2 tau c/det), sqrt(-2 tau a/det).
+// A strip whose bit is clear cannot hold a pixel that passes the alpha test (tau already carries
+// a 1e-4 margin; 0.02 px + 1e-4 relative slack covers the rounding here), so skipping it never
+// changes a result.  Degenerate / non-finite inputs fall back to "every strip".
+__device__ __forceinline__ uint32_t strip_mask(float gx, float gy, float a, float b, float c, float tau, float tile_x0,
+                                               float tile_y0)
+{
+    if (tau > 0.0f) return 0u;  // power <= 0 < tau for every pixel: never contributes
+    const float det = a * c - b * b, k = -2.0f * tau;
+    float ex = 3.0e38f, ey = 3.0e38f;
+    if (det > 0.0f && a > 0.0f && k < 3.0e38f) {
+        const float inv = 1.0f / det;
+        ex = sqrtf(k * c * inv) * 1.0001f + 0.02f;
+        ey = sqrtf(k * a * inv) * 1.0001f + 0.02f;
+    }
+    const float lx = gx - ex - tile_x0, hx = gx + ex - tile_x0;
+    const float ly = gy - ey - tile_y0, hy = gy + ey - tile_y0;
+    if (hx < 0.0f || lx > 15.0f || hy < 0.0f || ly > 15.0f) return 0u;
+    const int r0 = (int)ceilf(fmaxf(ly, 0.0f)), r1 = (int)floorf(fminf(hy, 15.0f));
+    if (r1 < r0) return 0u;  // between two pixel rows
+    const int s0 = r0 >> 1, s1 = r1 >> 1;
+    return ((2u << s1) - 1u) & ~((1u << s0) - 1u);
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
