@@ -194,7 +194,8 @@ def main():
     projmatrix_h = torch.from_numpy((V.T @ Pm.T).astype(np.float32)).pin_memory()
     campos_h = torch.zeros(3).pin_memory()
     bg_h = torch.zeros(3).pin_memory()
-    dL_h = torch.from_numpy(scenes.upstream_grad(W, H, seed=1 + rank)).pin_memory()
+    # loss = mean over the batch's views: the 1/world factor is folded into the upstream gradient
+    dL_h = torch.from_numpy(scenes.upstream_grad(W, H, seed=1 + rank) / max(world, 1)).pin_memory()
     viewmatrix, projmatrix, campos, bg, dL = (x.to(dev) for x in (viewmatrix_h, projmatrix_h, campos_h, bg_h, dL_h))
 
     def settings(vm, pm, cp, b):
@@ -218,7 +219,7 @@ def main():
                             shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
         torch.autograd.backward(color, dL)
         if arena is not None:
-            arena.all_reduce_from(params, 1.0 / world)
+            arena.all_reduce_from(params)
         zero_grads()
         return radii
 
@@ -232,7 +233,7 @@ def main():
         loss = (color * g).sum()
         loss.backward()
         if arena is not None:
-            arena.all_reduce_from(params, 1.0 / world)
+            arena.all_reduce_from(params)
         val = loss.item()  # device -> host read of the step's result
         zero_grads()
         return val

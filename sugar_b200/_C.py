@@ -145,8 +145,11 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     P, H, W = means3D.size(0), dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
     with torch.cuda.device(dev):
-        # all eight gradients + the accumulator scratch live in ONE rounded allocation (views below)
-        widths = (3, 3, 3, 1, 6, 3 * M, 3, 4)
+        # All eight gradients + the accumulator scratch live in ONE rounded allocation.  The first
+        # (3 + 1 + 3M + 3 + 4) * P floats are exactly the multi-GPU all-reduce arena
+        # [means3D | opacity | sh | scales | rotations] (sugar_b200/parallel.py), so the view-parallel
+        # step reduces them in place without packing.
+        widths = (3, 1, 3 * M, 3, 4, 3, 3, 6)
         n_scratch = (lib.sgr_backward_scratch_bytes(P) + 3) // 4 if P else 0
         flat = torch.empty(_round_up(4 * (P * sum(widths) + n_scratch) + 256, _ROUND) // 4, dtype=torch.float32, device=dev)
         offs, o = [], 0
@@ -155,13 +158,13 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             o += P * w
         part = lambda k, shape: flat[offs[k]:offs[k] + P * widths[k]].view(shape)
         dL_dmeans3D = part(0, (P, 3))
-        dL_dmeans2D = part(1, (P, 3))
-        dL_dcolors = part(2, (P, 3))
-        dL_dopacity = part(3, (P, 1))
-        dL_dcov3D = part(4, (P, 6))
-        dL_dsh = part(5, (P, M, 3))
-        dL_dscales = part(6, (P, 3))
-        dL_drotations = part(7, (P, 4))
+        dL_dopacity = part(1, (P, 1))
+        dL_dsh = part(2, (P, M, 3))
+        dL_dscales = part(3, (P, 3))
+        dL_drotations = part(4, (P, 4))
+        dL_dmeans2D = part(5, (P, 3))
+        dL_dcolors = part(6, (P, 3))
+        dL_dcov3D = part(7, (P, 6))
         if P != 0:
             means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color = map(
                 _c, (means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color))

@@ -14,7 +14,7 @@ from typing import Dict
 import torch
 import torch.distributed as dist
 
-ARENA_FIELDS = ("means3D", "shs", "opacities", "scales", "rotations")
+ARENA_FIELDS = ("means3D", "opacities", "shs", "scales", "rotations")  # = layout of the backward's flat buffer
 
 
 def shard_views(num_views: int, rank: int, world: int):
@@ -49,16 +49,40 @@ class GradArena:
             else:
                 v.copy_(g.reshape(-1))
 
+    def _shared_base(self, params: Dict[str, torch.Tensor]):
+        """If the gradients already sit back to back in one buffer in arena order (they do when they
+        come from sugar_b200's backward), return that slice so the reduction needs no packing."""
+        g0 = params[self.fields[0]].grad
+        base = getattr(g0, "_base", None) if g0 is not None else None
+        if base is None or base.dim() != 1 or base.dtype != torch.float32:
+            return None
+        esz, start = base.element_size(), base.data_ptr()
+        for f in self.fields:
+            g = params[f].grad
+            o, n = self.offsets[f]
+            if g is None or getattr(g, "_base", None) is not base or not g.is_contiguous() or g.numel() != n \
+                    or g.data_ptr() != start + o * esz:
+                return None
+        return base[:self.flat.numel()]
+
     def all_reduce_from(self, params: Dict[str, torch.Tensor], scale: float = 1.0) -> torch.Tensor:
-        """Pack the ranks' local gradients, sum them over the process group, scale (1/num_views)."""
-        self.pack(params)
+        """Sum the ranks' local gradients over the process group (in place when possible) and scale
+        by 1/num_views.  Returns the reduced flat arena."""
+        buf = self._shared_base(params)
+        if buf is None:
+            self.pack(params)
+            buf = self.flat
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         if scale != 1.0:
-            self.flat.mul_(scale)
-        return self.flat
+            buf.mul_(scale)
+        self.reduced = buf
+        return buf
 
     def unpack_to(self, params: Dict[str, torch.Tensor]) -> None:
         """Write the reduced gradients back as .grad of the (replicated) parameters."""
+        src = getattr(self, "reduced", self.flat)
         for f in self.fields:
-            params[f].grad = self.view(f).view_as(params[f]).clone()
+            o, n = self.offsets[f]
+            if params[f].grad is None or params[f].grad.data_ptr() != src.data_ptr() + o * 4:
+                params[f].grad = src[o:o + n].view_as(params[f]).clone()
