@@ -34,6 +34,41 @@ def _ptr(t: torch.Tensor, name: str):
 
 _ROUND = 64 << 20  # arena sizes are rounded up to 64 MiB so the caching allocator sees few distinct sizes
 
+# Optional workspace cache (SGR_WORKSPACE_CACHE=1).  The per-call buffers of this op are large
+# (0.5-1 GB at 3M Gaussians); a cudaMalloc inside the training loop is a 10-160 ms device-wide
+# stall.  By default torch's caching allocator is enough: each call makes one rounded allocation
+# for the forward state and one for the gradients, and `_Arena.release()` breaks the callback
+# reference cycle so they are returned by reference counting, not at the next cyclic GC (which is
+# what used to fragment the allocator; scripts/step_times.py shows the difference).  With the
+# cache on, blocks are additionally pinned here and handed out again as soon as nothing references
+# their storage (stream-ordered reuse, like the caching allocator's).
+_ws_cache = {}
+_WS_MAX_PER_KEY = 6
+_USE_WS_CACHE = os.environ.get("SGR_WORKSPACE_CACHE", "0") == "1"
+
+
+def _use_count(t: torch.Tensor) -> int:
+    return torch._C._storage_Use_Count(t.untyped_storage()._cdata)
+
+
+def _big_empty(numel: int, dtype, device) -> torch.Tensor:
+    """1-D tensor of `numel` elements for a per-call arena, recycled once all its views are dead."""
+    if not _USE_WS_CACHE:
+        return torch.empty(numel, dtype=dtype, device=device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, dtype, numel)
+    entries = _ws_cache.setdefault(key, [])
+    for blk, baseline in entries:
+        if _use_count(blk) == baseline:
+            return blk
+    blk = torch.empty(numel, dtype=dtype, device=device)
+    if len(entries) < _WS_MAX_PER_KEY:
+        entries.append((blk, _use_count(blk)))
+    return blk
+
+
+def clear_workspace_cache() -> None:
+    _ws_cache.clear()
+
 
 def _round_up(n: int, a: int) -> int:
     return (n + a - 1) // a * a
@@ -46,7 +81,7 @@ class _Arena:
 
     def __init__(self, device, reserve_bytes: int):
         self.device = device
-        self.block = torch.empty(_round_up(reserve_bytes, _ROUND), dtype=torch.uint8, device=device) if reserve_bytes else None
+        self.block = _big_empty(_round_up(reserve_bytes, _ROUND), torch.uint8, device) if reserve_bytes else None
         self.used = 0
         self.parts = {}
         self.cbs = {name: _lib.ALLOC_FN(lambda _ctx, n, name=name: self._alloc(name, n)) for name in ("geom", "binning", "img")}
@@ -58,12 +93,19 @@ class _Arena:
             t = self.block[off:off + nbytes]
             self.used = off + nbytes
         else:  # no (or too small a) reservation: plain allocation, still rounded
-            t = torch.empty(_round_up(nbytes, _ROUND), dtype=torch.uint8, device=self.device)[:nbytes]
+            t = _big_empty(_round_up(nbytes, _ROUND), torch.uint8, self.device)[:nbytes]
         self.parts[name] = t
         return t.data_ptr()
 
     def get(self, name):
         return self.parts.get(name, torch.empty(0, dtype=torch.uint8, device=self.device))
+
+    def release(self):
+        """Break the arena <-> callback reference cycle so the block is released by reference
+        counting as soon as the autograd graph lets go of the views (not at the next cyclic GC)."""
+        self.cbs = None
+        self.block = None
+        self.parts = {}
 
 
 def _view_struct(bg, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, degree, campos, prefiltered,
@@ -134,7 +176,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         if P:
             # next view's optimistic capacity: 25% headroom, rounded to 1M instances (stable sizes)
             _capacity_hint[key] = _round_up(int(R * 1.25) + 65536, 1 << 20)
-    return R, out_color, radii, arena.get("geom"), arena.get("binning"), arena.get("img")
+    geom_t, binning_t, img_t = arena.get("geom"), arena.get("binning"), arena.get("img")
+    arena.release()
+    return R, out_color, radii, geom_t, binning_t, img_t
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
@@ -151,7 +195,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         # step reduces them in place without packing.
         widths = (3, 1, 3 * M, 3, 4, 3, 3, 6)
         n_scratch = (lib.sgr_backward_scratch_bytes(P) + 3) // 4 if P else 0
-        flat = torch.empty(_round_up(4 * (P * sum(widths) + n_scratch) + 256, _ROUND) // 4, dtype=torch.float32, device=dev)
+        flat = _big_empty(_round_up(4 * (P * sum(widths) + n_scratch) + 256, _ROUND) // 4, torch.float32, dev)
         offs, o = [], 0
         for w in widths:
             offs.append(o)

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib", "libsugar_b200.so")
+LIB = os.environ.get("SGR_LIB_OUT", os.path.join(HERE, "lib", "libsugar_b200.so"))
 SOURCES = ["sgr_api.cu", "sgr_forward.cu", "sgr_backward.cu", "sgr_field.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -38,7 +38,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(HERE, "lib", src.replace(".cu", ".o"))
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--shared"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = obj if "SGR_LIB_OUT" not in os.environ else LIB + "." + src.replace(".cu", ".o")
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--shared"] + os.environ.get("SGR_NVCC_EXTRA", "").split() + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

@@ -313,7 +313,10 @@ __device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *row, 
     dmean.z += (-o.x * o.z * ddx - o.y * o.z * ddy + (sum2 - o.z * o.z) * ddz) * invsum32;
 }
 
-constexpr int PB_T = 256;
+#ifndef SGR_PB_T
+#define SGR_PB_T 256
+#endif
+constexpr int PB_T = SGR_PB_T;
 // dynamic shared memory carve-up (floats): inputs then outputs then the SH block
 constexpr int PB_GACC = 0;                    // PB_T*12
 constexpr int PB_MEANS = PB_GACC + PB_T * 12; // PB_T*3

@@ -25,7 +25,10 @@ namespace sgr {
 // ------------------------------------------------------------------------------------------------
 // preprocess
 // ------------------------------------------------------------------------------------------------
-constexpr int PRE_T = 256;
+#ifndef SGR_PRE_T
+#define SGR_PRE_T 256
+#endif
+constexpr int PRE_T = SGR_PRE_T;
 
 struct PreArgs {
     int P;
