@@ -27,6 +27,10 @@ CASES = [
     ("covpre_posed", 2000, 96, 64, "posed", False, 0, True, (0.0, 0.0, 0.0)),
     ("mesh_bound", 3000, 160, 96, "posed", True, 3, False, (0.0, 0.0, 0.0)),
     ("big_splats", 600, 160, 96, "identity", False, 0, False, (0.0, 0.0, 0.0)),
+    # dense tiles: ~6k-30k instances per tile -> exercises the 8192-word sort class and the global
+    # radix fallback (tiles above 8192 instances)
+    ("dense_tiles", 120000, 64, 48, "posed", False, 0, False, (0.0, 0.0, 0.0)),
+    ("mid_tiles", 35000, 64, 48, "posed", True, 1, False, (0.5, 0.5, 0.5)),
 ]
 
 
@@ -37,6 +41,9 @@ def _scene(name, P, W, H, camera):
         kw["mesh_bound"] = True
     if name == "big_splats":
         kw["px_sigma"] = 25.0
+    if name in ("dense_tiles", "mid_tiles"):
+        kw["px_sigma"] = 0.8
+        kw["lateral"] = 0.9
     return scenes.make_scene(P, W, H, seed=hash(name) % 1000 if False else len(name) * 7 + P % 13, camera=camera, **kw)
 
 
