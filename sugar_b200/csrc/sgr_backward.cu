@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
     __syncthreads();
     const int n = s_tile_last;
     if (n == 0) return;
+    const uint32_t sa = smem_addr_pinned(s_a), sb = smem_addr_pinned(s_b), sc = smem_addr_pinned(s_c);
 
     for (int b0 = 0; b0 < n; b0 += BWD_B) {
         __syncthreads();
@@ -143,8 +144,8 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
                 mw &= mw - 1;
                 const int j = c * 32 + jj;
                 const int pos = n - 1 - (b0 + j);  // position in the front-to-back list
-                const float4 A = s_a[j];
-                const float4 B = s_b[j];
+                const float4 A = lds128(sa + j * 16);
+                const float4 B = lds128(sb + j * 16);
                 const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                 const float power = splat_power(dx, dy, A.z, A.w, B.x);
                 bool valid = pos < last_contributor && !(power > 0.0f) && !(power < B.y);
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
                     const float alpha = fminf(0.99f, __fmul_rn(B.z, G));
                     valid = !(alpha < 1.0f / 255.0f);
                     if (valid) {
-                        const float2 Cc = s_c[j];
+                        const float2 Cc = lds64(sc + j * 8);
                         const float inv = __fdividef(1.0f, 1.0f - alpha);  // 1-alpha in [0.01, 1): MUFU.RCP suffices
                         T = T * inv;
                         const float dchannel = alpha * T;
@@ -314,7 +315,7 @@ __device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *row, 
 }
 
 #ifndef SGR_PB_T
-#define SGR_PB_T 256
+#define SGR_PB_T 64
 #endif
 constexpr int PB_T = SGR_PB_T;
 // dynamic shared memory carve-up (floats): inputs then outputs then the SH block

@@ -638,6 +638,7 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0;
+    const uint32_t sa = smem_addr_pinned(s_a), sb = smem_addr_pinned(s_b), sc = smem_addr_pinned(s_c);
     for (uint32_t b0 = lo; b0 < hi; b0 += BLEND_T) {
         if (__syncthreads_count(done) == BLEND_T) break;
         uint32_t mask = 0;
@@ -666,8 +667,8 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
                     const int j = (k << 5) + __ffs(mw) - 1;
                     mw &= mw - 1;
                     if (done) continue;
-                    const float4 A = s_a[j];
-                    const float4 B = s_b[j];
+                    const float4 A = lds128(sa + j * 16);
+                    const float4 B = lds128(sb + j * 16);
                     const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                     const float power = splat_power(dx, dy, A.z, A.w, B.x);
                     if (power > 0.0f || power < B.y) continue;
@@ -678,7 +679,7 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
                         done = true;
                         continue;
                     }
-                    const float2 Cc = s_c[j];
+                    const float2 Cc = lds64(sc + j * 8);
                     C0 = __fmaf_rn(T, __fmul_rn(alpha, B.w), C0);
                     C1 = __fmaf_rn(T, __fmul_rn(alpha, Cc.x), C1);
                     C2 = __fmaf_rn(T, __fmul_rn(alpha, Cc.y), C2);

@@ -336,6 +336,30 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// 16-byte shared-memory load from a precomputed 32-bit shared-window address.  Indexing a
+// __shared__ array with a runtime index inside the splat loop makes nvcc rebuild the window base
+// (S2R SR_CgaCtaId + LEA ...) every iteration; the blend kernels compute the base once instead.
+// Shared-window address of a __shared__ object, pinned in a register: the asm barrier stops nvcc
+// from re-materialising the (S2R + LEA) sequence at every use inside the loops.
+__device__ __forceinline__ uint32_t smem_addr_pinned(const void *p)
+{
+    uint32_t a = smem_u32(p), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
 #endif  // __CUDACC__
 
 // host-side stage entry points (defined in the .cu files)
