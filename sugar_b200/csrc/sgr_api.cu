@@ -59,6 +59,8 @@ void prof_begin(int kind, cudaStream_t st)
     cudaEventRecord(g_prof[g_prof_n].a, st);
 }
 
+void note_launches(int extra) { g_launches += (unsigned long long)extra; }
+
 void prof_end(cudaStream_t st)
 {
     if (!g_prof_on || g_prof_n >= g_prof_cap) return;

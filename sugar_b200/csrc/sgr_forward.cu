@@ -519,7 +519,10 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t *__re
 // Size classes (LOWER, CAP]: each class is its own launch over all tiles with early exit, so the
 // shared-memory footprint (and occupancy) matches the tile population.
 // ------------------------------------------------------------------------------------------------
-constexpr int SORT_VT = 8;
+#ifndef SGR_SORT_VT
+#define SGR_SORT_VT 8
+#endif
+constexpr int SORT_VT = SGR_SORT_VT;  // words per thread in the per-tile merge sort
 
 __device__ __forceinline__ void cswap(uint64_t &a, uint64_t &b)
 {
@@ -552,12 +555,28 @@ __global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const ui
             const int i = tid * VT + k;
             r[k] = i < n ? inst[lo + i] : ~0ull;
         }
-        cswap(r[0], r[1]); cswap(r[2], r[3]); cswap(r[4], r[5]); cswap(r[6], r[7]);
-        cswap(r[0], r[2]); cswap(r[1], r[3]); cswap(r[4], r[6]); cswap(r[5], r[7]);
-        cswap(r[1], r[2]); cswap(r[5], r[6]);
-        cswap(r[0], r[4]); cswap(r[1], r[5]); cswap(r[2], r[6]); cswap(r[3], r[7]);
-        cswap(r[2], r[4]); cswap(r[3], r[5]);
-        cswap(r[1], r[2]); cswap(r[3], r[4]); cswap(r[5], r[6]);
+        // Batcher odd-even merge sort network on the VT registers (19 comparators for 8, 63 for 16)
+        static_assert(VT == 8 || VT == 16, "sorting network written out for 8 or 16 words per thread");
+        if constexpr (VT == 8) {
+            cswap(r[0], r[1]); cswap(r[2], r[3]); cswap(r[4], r[5]); cswap(r[6], r[7]); cswap(r[0], r[2]);
+            cswap(r[1], r[3]); cswap(r[4], r[6]); cswap(r[5], r[7]); cswap(r[1], r[2]); cswap(r[5], r[6]);
+            cswap(r[0], r[4]); cswap(r[1], r[5]); cswap(r[2], r[6]); cswap(r[3], r[7]); cswap(r[2], r[4]);
+            cswap(r[3], r[5]); cswap(r[1], r[2]); cswap(r[3], r[4]); cswap(r[5], r[6]);
+        } else {
+            cswap(r[0], r[1]); cswap(r[2], r[3]); cswap(r[4], r[5]); cswap(r[6], r[7]); cswap(r[8], r[9]);
+            cswap(r[10], r[11]); cswap(r[12], r[13]); cswap(r[14], r[15]); cswap(r[0], r[2]);
+            cswap(r[1], r[3]); cswap(r[4], r[6]); cswap(r[5], r[7]); cswap(r[8], r[10]); cswap(r[9], r[11]);
+            cswap(r[12], r[14]); cswap(r[13], r[15]); cswap(r[1], r[2]); cswap(r[5], r[6]); cswap(r[9], r[10]);
+            cswap(r[13], r[14]); cswap(r[0], r[4]); cswap(r[1], r[5]); cswap(r[2], r[6]); cswap(r[3], r[7]);
+            cswap(r[8], r[12]); cswap(r[9], r[13]); cswap(r[10], r[14]); cswap(r[11], r[15]);
+            cswap(r[2], r[4]); cswap(r[3], r[5]); cswap(r[10], r[12]); cswap(r[11], r[13]); cswap(r[1], r[2]);
+            cswap(r[3], r[4]); cswap(r[5], r[6]); cswap(r[9], r[10]); cswap(r[11], r[12]); cswap(r[13], r[14]);
+            cswap(r[0], r[8]); cswap(r[1], r[9]); cswap(r[2], r[10]); cswap(r[3], r[11]); cswap(r[4], r[12]);
+            cswap(r[5], r[13]); cswap(r[6], r[14]); cswap(r[7], r[15]); cswap(r[4], r[8]); cswap(r[5], r[9]);
+            cswap(r[6], r[10]); cswap(r[7], r[11]); cswap(r[2], r[4]); cswap(r[3], r[5]); cswap(r[6], r[8]);
+            cswap(r[7], r[9]); cswap(r[10], r[12]); cswap(r[11], r[13]); cswap(r[1], r[2]); cswap(r[3], r[4]);
+            cswap(r[5], r[6]); cswap(r[7], r[8]); cswap(r[9], r[10]); cswap(r[11], r[12]); cswap(r[13], r[14]);
+        }
 #pragma unroll
         for (int k = 0; k < VT; k++) s_keys[tid * VT + k] = r[k];
     }
@@ -751,7 +770,8 @@ static int launch_binning_and_blend(const ViewConsts &v, int P, const GeomState 
     SGR_LAUNCH(K_SCATTER, st,
                scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, v.gx, geom.rect, geom.depth, img.tile_cursor,
                                                                img.counters, capacity, bin.inst_a));
-    sgr::prof_begin(K_SORT_SMEM, st);
+    sgr::prof_begin(K_SORT_SMEM, st);  // one timing bracket around the three size classes ...
+    sgr::note_launches(2);             // ... but three launches
     tile_sort_merge_kernel<512, 0><<<T, 512 / SORT_VT, 512 * 8, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
                                                                       bin.plist);
     tile_sort_merge_kernel<2048, 512><<<T, 2048 / SORT_VT, 2048 * 8, st>>>(img.tile_start, img.counters, capacity,

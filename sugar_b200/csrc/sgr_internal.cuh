@@ -123,6 +123,7 @@ enum KernelKind {
 };
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(cudaStream_t st);
+void note_launches(int extra);  // launches not individually bracketed by prof_begin
 #define SGR_LAUNCH(kind, st, ...)     \
     do {                              \
         sgr::prof_begin((kind), (st)); \
