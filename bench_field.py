@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""Secondary benchmark: SuGaR density/SDF field (get_field_values) forward+backward.
+
+    python bench_field.py [--gaussians 1000000] [--samples 1000000] [--k 16] [--steps 20]
+
+BASELINE.md section 2 "B-cpu-density" / config 1 and 3: fused sugar_b200 kernels vs the reference's op chain
+(restated in oracle/field_oracle.py) run with PyTorch on the same GPU and on the host cores (bounded sample).
+Prints one JSON line.  Not the driver's bench (that is bench.py); numbers are copied to profiles/.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--samples", type=int, default=1_000_000)
+    ap.add_argument("--k", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=20)
+    a = ap.parse_args()
+    import torch
+    from oracle import field_oracle as fo
+    from sugar_b200 import field, _lib
+    dev = torch.device("cuda")
+    P, N, K = a.gaussians, a.samples, a.k
+    g = torch.Generator(device="cpu").manual_seed(0)
+    points = torch.randn(P, 3, generator=g).to(dev)
+    scaling = torch.exp(torch.randn(P, 3, generator=g) * 0.5 - 4.0).to(dev)
+    quats = torch.nn.functional.normalize(torch.randn(P, 4, generator=g), dim=-1).to(dev)
+    strengths = torch.sigmoid(torch.randn(P, generator=g) * 2).to(dev)
+    # neighbours: K random nearby indices (a K-NN build is not part of this path); samples inside Gaussians
+    gi = torch.randint(0, P, (N,), generator=g).to(dev)
+    nbr = (gi[:, None] + torch.randint(-4096, 4096, (N, K), generator=g).to(dev)).clamp_(0, P - 1)
+    nbr[:, 0] = gi
+    x = points[gi] + fo.quaternion_apply(quats[gi], 1.5 * scaling[gi] * torch.randn(N, 3, generator=g).to(dev))
+    leaves = [t.clone().requires_grad_(True) for t in (x, points, scaling, quats, strengths)]
+    w = torch.randn(N, device=dev)
+
+    def ours():
+        f = field.field_values(leaves[0], nbr, *leaves[1:], density_factor=1.0 / K, return_sdf=True,
+                               return_closest_gaussian_opacities=True, return_beta=True)
+        (f["sdf"] * w).sum().backward()
+        for t in leaves:
+            t.grad = None
+
+    def torch_ref():
+        f = fo.field_values_torch(leaves[0], nbr, *leaves[1:], density_factor=1.0 / K)
+        (f["sdf"] * w).sum().backward()
+        for t in leaves:
+            t.grad = None
+
+    def timeit(fn, steps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    _lib.profile(True)
+    ours(); torch.cuda.synchronize(); _lib.profile_read()
+    ms = timeit(ours, a.steps)
+    prof = _lib.profile_read()
+    _lib.profile(False)
+    ms_ref = timeit(torch_ref, max(3, a.steps // 4))
+    # CPU: the same op chain on the host cores, bounded sample
+    ns = min(N, 100_000)
+    cl = [t.detach().cpu()[:ns].clone().requires_grad_(True) if i == 0 else t.detach().cpu().clone().requires_grad_(True)
+          for i, t in enumerate(leaves)]
+    nbr_c, w_c = nbr[:ns].cpu(), w[:ns].cpu()
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.perf_counter()
+    f = fo.field_values_torch(cl[0], nbr_c, *cl[1:], density_factor=1.0 / K)
+    (f["sdf"] * w_c).sum().backward()
+    cpu_s = time.perf_counter() - t0
+    fwd_bytes = N * (12 + 8 * K + 48 * K)
+    stages = {k: {"ms": round(v[0] / v[1], 4)} for k, v in prof.items()}
+    if "field_forward" in stages:
+        stages["field_forward"]["gbs"] = round(fwd_bytes / (stages["field_forward"]["ms"] * 1e-3) / 1e9, 1)
+    print(json.dumps({
+        "metric": "density/SDF field samples/sec fwd+bwd", "value": N / (ms * 1e-3), "unit": "samples/s",
+        "ms_per_step": ms, "config": {"workload": f"{P} Gaussians, {N} samples, K={K}"},
+        "torch_same_gpu": {"value": N / (ms_ref * 1e-3), "ms_per_step": ms_ref},
+        "cpu_baseline": {"value": ns / cpu_s, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{ns} samples of the workload, PyTorch op chain of sugar_model.py:1247-1316"},
+        "stages": stages}))
+
+
+if __name__ == "__main__":
+    main()

@@ -105,3 +105,34 @@ def compute_density(x, closest_gaussians_idx, points, scaling, quaternions, stre
     density, nbr, _, _ = _Field.apply(x, closest_gaussians_idx, points, scaling, quaternions, strengths,
                                       density_factor, 1.0, 1e-16)
     return (density, nbr) if return_closest_gaussian_opacities else density
+
+
+def quaternion_apply(q: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """Rotate points p by quaternions q (real part first), as pytorch3d.transforms.quaternion_apply."""
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    R = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return (R.reshape(q.shape[:-1] + (3, 3)) @ p[..., None])[..., 0]
+
+
+def sample_points_in_gaussians(points, scaling, quaternions, strengths, num_samples, sampling_scale_factor=1.,
+                               mask=None, probabilities_proportional_to_opacity=False,
+                               probabilities_proportional_to_volume=True, generator=None):
+    """SuGaR.sample_points_in_gaussians (sugar_scene/sugar_model.py:885-928): multinomial over volume (x opacity)
+    weights, then x = mu + R(q) (scale_factor * s * N(0,1)).  Kept in PyTorch on purpose: it is RNG-bound and this
+    keeps the reference's random streams.  Returns (samples [N,3], gaussian indices [N])."""
+    sc = scaling if mask is None else scaling[mask]
+    areas = sc[..., 0] * sc[..., 1] * sc[..., 2] if probabilities_proportional_to_volume else torch.ones_like(sc[..., 0])
+    if probabilities_proportional_to_opacity:
+        st = strengths.view(-1)
+        areas = areas * (st if mask is None else st[mask])
+    areas = areas.abs()
+    idx = torch.multinomial(areas / areas.sum(dim=-1, keepdim=True), num_samples=num_samples, replacement=True,
+                            generator=generator)
+    if mask is not None:
+        idx = torch.arange(points.shape[0], device=points.device)[mask][idx]
+    noise = torch.randn(points[idx].shape, device=points.device, dtype=points.dtype, generator=generator)
+    x = points[idx] + quaternion_apply(quaternions[idx], sampling_scale_factor * scaling[idx] * noise)
+    return x, idx

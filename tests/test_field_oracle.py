@@ -45,3 +45,24 @@ def test_c1_config_sizes():
     assert out["density"].shape == (2000,) and out["closest_gaussian_opacities"].shape == (2000, 16)
     assert np.isfinite(out["sdf"]).all() and (out["density"] >= 0).all() and (out["density"] <= 1.0).all()
     assert (case["nbr_idx"][:, 0] >= 0).all()
+
+
+def test_sampling_matches_reference_semantics():
+    """field.sample_points_in_gaussians vs the oracle's restatement of sugar_model.py:885-928 (same RNG stream)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sgr_field_nolib", os.path.join(HERE, "..", "sugar_b200", "field.py"))
+    src = open(spec.origin).read()
+    # field.py imports the CUDA library at module import; only its pure-torch helpers are needed here
+    ns = {}
+    head = src.index("def quaternion_apply")
+    exec("import torch\n" + src[head:], ns)
+    g = torch.Generator().manual_seed(5)
+    P, N = 200, 1000
+    points = torch.randn(P, 3, generator=g); scaling = torch.exp(torch.randn(P, 3, generator=g) - 2)
+    q = torch.nn.functional.normalize(torch.randn(P, 4, generator=g), dim=-1); st = torch.rand(P, generator=g)
+    g1, g2 = torch.Generator().manual_seed(9), torch.Generator().manual_seed(9)
+    x, idx = ns["sample_points_in_gaussians"](points, scaling, q, st, N, 1.5, generator=g1)
+    areas = (scaling[:, 0] * scaling[:, 1] * scaling[:, 2]).abs()
+    gi = torch.multinomial(areas / areas.sum(), N, replacement=True, generator=g2)
+    ref = points[gi] + fo.quaternion_apply(q[gi], 1.5 * scaling[gi] * torch.randn(N, 3, generator=g2))
+    assert torch.equal(idx, gi) and torch.allclose(x, ref, atol=1e-6)
