@@ -195,3 +195,74 @@ def test_full_size_properties():
         for k in b["grads"]:
             err = h.rel_err(a["grads"][k].cpu().numpy(), b["grads"][k].cpu().numpy())
             assert err <= GRAD_RTOL, f"grad {k}: rel err {err:.3e}"
+
+
+def _run_raw(mod, t, sc, bg, dL, sh_degree, shs, device="cuda"):
+    """Call GaussianRasterizer of `mod` on explicit torch tensors (for layout / alignment variants)."""
+    import torch
+    leaf = lambda x: x.detach().requires_grad_(True)
+    means3D, opac, scales, rots, shs = (leaf(x) for x in (t["means3D"], t["opacities"], t["scales"], t["rotations"], shs))
+    means2D = torch.zeros_like(means3D, requires_grad=True)
+    st = mod.GaussianRasterizationSettings(sc.height, sc.width, sc.tanfovx, sc.tanfovy,
+                                           torch.tensor(bg, dtype=torch.float32, device=device), 1.0, t["viewmatrix"],
+                                           t["projmatrix"], sh_degree, t["campos"], False, False)
+    color, radii = mod.GaussianRasterizer(st)(means3D=means3D, means2D=means2D, opacities=opac, shs=shs, scales=scales,
+                                              rotations=rots)
+    (color * torch.from_numpy(dL).to(device)).sum().backward()
+    return color.detach(), radii.detach(), dict(means3D=means3D.grad, opacities=opac.grad, scales=scales.grad,
+                                                rotations=rots.grad, shs=shs.grad, means2D=means2D.grad)
+
+
+@pytest.mark.parametrize("M,deg", [(16, 3), (9, 2), (4, 1), (1, 0), (16, 1)])
+def test_sh_layouts_and_misaligned_inputs(M, deg):
+    """Stored SH count M != 16 (rows not 16-byte multiples -> 4-byte cp.async path) and inputs that start at a
+    12-byte offset (no TMA bulk copy possible -> plain staging path); forward bit-exact, grads 1e-4."""
+    import torch
+    if not h.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from sugar_b200 import diff_gaussian_rasterization as ours, scenes
+    ref = h.load_ref_module()
+    P, W, H = 3001, 150, 90
+    sc = scenes.make_scene(P + 1, W, H, seed=40 + M, camera="posed")
+    dL = scenes.upstream_grad(W, H)
+    t = h.to_torch(sc)
+    # slices that start one row into a larger allocation: contiguous but NOT 16-byte aligned (except rotations)
+    tt = {k: (v[1:] if k in ("means3D", "scales", "rotations", "opacities", "shs") else v) for k, v in t.items()}
+    shs = tt["shs"][:, :M, :].contiguous() if M != 16 else tt["shs"]
+    assert tt["means3D"].data_ptr() % 16 != 0
+    a = _run_raw(ours, tt, sc, (0.2, 0.1, 0.3), dL, deg, shs)
+    b = _run_raw(ref, tt, sc, (0.2, 0.1, 0.3), dL, deg, shs)
+    assert torch.equal(a[1], b[1])
+    assert torch.equal(a[0].view(torch.int32), b[0].view(torch.int32)), "image not bit-exact"
+    for k in b[2]:
+        assert a[2][k].shape == b[2][k].shape
+        err = h.rel_err(a[2][k].cpu().numpy(), b[2][k].cpu().numpy())
+        assert err <= GRAD_RTOL, f"grad {k}: {err:.2e}"
+
+
+def test_debug_flag_and_argument_errors():
+    import torch
+    from sugar_b200 import diff_gaussian_rasterization as ours, scenes, _lib
+    sc = scenes.make_scene(500, 64, 48, seed=2)
+    out = h.run_module(ours, sc, (0, 0, 0), scenes.upstream_grad(64, 48), use_sh=True, sh_degree=3, debug=True)
+    assert bool(torch.isfinite(out["color"]).all())
+    t = h.to_torch(sc)
+    st = ours.GaussianRasterizationSettings(48, 64, sc.tanfovx, sc.tanfovy, torch.zeros(3, device="cuda"), 1.0,
+                                            t["viewmatrix"], t["projmatrix"], 3, t["campos"], False, False)
+    r = ours.GaussianRasterizer(st)
+    with pytest.raises(Exception, match="excatly one"):
+        r(means3D=t["means3D"], means2D=t["means3D"], opacities=t["opacities"], shs=t["shs"],
+          colors_precomp=t["colors_precomp"], scales=t["scales"], rotations=t["rotations"])
+    with pytest.raises(Exception, match="exactly one"):
+        r(means3D=t["means3D"], means2D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"])
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        r(means3D=t["means3D"].reshape(-1), means2D=t["means3D"], opacities=t["opacities"], shs=t["shs"],
+          scales=t["scales"], rotations=t["rotations"])
+    with pytest.raises(_lib.SgrError):  # sh_degree 3 needs 16 coefficients
+        r(means3D=t["means3D"], means2D=t["means3D"], opacities=t["opacities"], shs=t["shs"][:, :4].contiguous(),
+          scales=t["scales"], rotations=t["rotations"])
+    with pytest.raises(Exception):      # CPU tensors: no CPU path
+        cpu = {k: v.cpu() for k, v in t.items()}
+        st2 = st._replace(bg=torch.zeros(3), viewmatrix=cpu["viewmatrix"], projmatrix=cpu["projmatrix"], campos=cpu["campos"])
+        ours.GaussianRasterizer(st2)(means3D=cpu["means3D"], means2D=cpu["means3D"], opacities=cpu["opacities"],
+                                     shs=cpu["shs"], scales=cpu["scales"], rotations=cpu["rotations"])
