@@ -358,12 +358,23 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, const ushor
     constexpr int SMALL = 6;
     const int rw = (int)rc.z - (int)rc.x, rcnt = (rc.z > rc.x && rc.w > rc.y) ? rw * ((int)rc.w - (int)rc.y) : 0;
     if (rcnt > 0 && rcnt <= SMALL) {
+        // claim all slots first (independent returning atomics in flight together), then store
         const uint64_t word = ((uint64_t)dbits << 32) | (uint32_t)idx;
-        for (int ty = rc.y; ty < rc.w; ty++)
-            for (int tx = rc.x; tx < rc.z; tx++) {
-                const uint32_t slot = atomicAdd(cursor + ty * gx + tx, 1u);
-                inst[slot] = word;
+        uint32_t slot[SMALL];
+        int tx = 0, trow = (int)rc.y * gx + (int)rc.x;
+#pragma unroll
+        for (int k = 0; k < SMALL; k++) {
+            if (k < rcnt) {
+                slot[k] = atomicAdd(cursor + trow + tx, 1u);
+                if (++tx == rw) {
+                    tx = 0;
+                    trow += gx;
+                }
             }
+        }
+#pragma unroll
+        for (int k = 0; k < SMALL; k++)
+            if (k < rcnt) inst[slot[k]] = word;
     }
     unsigned todo = __ballot_sync(0xffffffffu, rcnt > SMALL);
     while (todo) {
@@ -394,7 +405,7 @@ template <int THREADS, bool GLOBAL>
 __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t *__restrict__ tile_start,
                                                             const uint32_t *__restrict__ counters, uint64_t capacity,
                                                             uint64_t *__restrict__ inst_a, uint64_t *__restrict__ inst_b,
-                                                            uint32_t *__restrict__ plist)
+                                                            uint32_t *__restrict__ plist, int num_tiles)
 {
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) uint64_t s_keys[];  // SMEM variant: 2 * SORT_CAP
@@ -403,12 +414,12 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t *__re
     __shared__ uint32_t s_wsum[32];
 
     if ((uint64_t)counters[0] > capacity) return;
-    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const uint32_t lo = tile_start[tile];
     const int n = (int)(tile_start[tile + 1] - lo);
-    if (GLOBAL ? (n <= SORT_CAP) : (n > SORT_CAP || n == 0)) return;
+    if (GLOBAL ? (n <= SORT_CAP) : (n > SORT_CAP || n == 0)) continue;
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint64_t *src, *dst;
     if (GLOBAL) {
         src = inst_a + lo;
@@ -508,6 +519,8 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t *__re
         dst = t;
     }
     for (int i = tid; i < n; i += THREADS) plist[lo + i] = (uint32_t)src[i];
+    __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -536,16 +549,17 @@ __global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const ui
                                                                         const uint32_t *__restrict__ counters,
                                                                         uint64_t capacity,
                                                                         const uint64_t *__restrict__ inst,
-                                                                        uint32_t *__restrict__ plist)
+                                                                        uint32_t *__restrict__ plist, int num_tiles)
 {
     constexpr int VT = SORT_VT;
     extern __shared__ __align__(16) uint64_t s_keys[];  // CAP words
     if ((uint64_t)counters[0] > capacity) return;
-    const int tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    // grid-stride over tiles: rare size classes are launched with a small grid and skip cheaply
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const uint32_t lo = tile_start[tile];
     const int n = (int)(tile_start[tile + 1] - lo);
-    if (n <= LOWER || n > CAP) return;
-    const int tid = threadIdx.x;
+    if (n <= LOWER || n > CAP) continue;
     const int nact = (n + VT - 1) / VT;  // threads that own a window
     const int L = nact * VT;             // padded length (pad words = all ones sort last)
     uint64_t r[VT];
@@ -619,6 +633,8 @@ __global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const ui
     }
     __syncthreads();
     for (int i = tid; i < n; i += CAP / VT) plist[lo + i] = (uint32_t)s_keys[i];
+    __syncthreads();  // s_keys is reused by the next tile of this CTA
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -772,16 +788,17 @@ static int launch_binning_and_blend(const ViewConsts &v, int P, const GeomState 
                                                                img.counters, capacity, bin.inst_a));
     sgr::prof_begin(K_SORT_SMEM, st);  // one timing bracket around the three size classes ...
     sgr::note_launches(2);             // ... but three launches
+    const int small_grid = T < 296 ? T : 296;  // 2 CTAs per SM, grid-stride over tiles
     tile_sort_merge_kernel<512, 0><<<T, 512 / SORT_VT, 512 * 8, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
-                                                                      bin.plist);
+                                                                      bin.plist, T);
     tile_sort_merge_kernel<2048, 512><<<T, 2048 / SORT_VT, 2048 * 8, st>>>(img.tile_start, img.counters, capacity,
-                                                                           bin.inst_a, bin.plist);
-    tile_sort_merge_kernel<8192, 2048><<<T, 8192 / SORT_VT, 8192 * 8, st>>>(img.tile_start, img.counters, capacity,
-                                                                            bin.inst_a, bin.plist);
+                                                                           bin.inst_a, bin.plist, T);
+    tile_sort_merge_kernel<8192, 2048><<<small_grid, 8192 / SORT_VT, 8192 * 8, st>>>(img.tile_start, img.counters,
+                                                                                     capacity, bin.inst_a, bin.plist, T);
     sgr::prof_end(st);
     SGR_LAUNCH(K_SORT_GLOBAL, st,
-               tile_sort_kernel<1024, true><<<T, 1024, 0, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
-                                                               bin.inst_b, bin.plist));
+               tile_sort_kernel<1024, true><<<small_grid, 1024, 0, st>>>(img.tile_start, img.counters, capacity,
+                                                                        bin.inst_a, bin.inst_b, bin.plist, T));
     SGR_LAUNCH(K_BLEND_FWD, st,
                blend_forward_kernel<<<dim3(v.gx, v.gy), dim3(SGR_TILE, SGR_TILE), 0, st>>>(
                    img.tile_start, bin.plist, geom.rec, img.counters, capacity, v.W, v.H, v.gx, v.bg, img.final_T,
