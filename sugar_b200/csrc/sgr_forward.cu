@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
         if (a.colors) stage_plain(s_col, a.colors + (size_t)base * 3, n * 3);
     }
     // ---- SH rows: coalesced cp.async into bank-conflict-free padded rows -----------------------
-    if (a.shs) {
+    // (sh_stride == 0 selects the direct path: each surviving thread reads its own row from global)
+    if (a.shs && a.sh_stride) {
         const int row_f = a.v.M * 3;
         const float *src = a.shs + (size_t)base * row_f;
         if (a.sh_vec) {
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
             }
         }
     }
-    if (a.shs) {
+    if (a.shs && a.sh_stride) {
         cp_async_wait<0>();
         __syncthreads();
     }
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
                 const float dx = __fsub_rn(mx, cp[0]), dy = __fsub_rn(my, cp[1]), dz = __fsub_rn(mz, cp[2]);
                 const float len = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
                 const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
-                const float *row = s_sh + tid * a.sh_stride;
+                const float *row = a.sh_stride ? s_sh + tid * a.sh_stride : a.shs + (size_t)idx * a.v.M * 3;
                 r = sh_channel(a.v.D, row + 0, x, y, z);
                 g = sh_channel(a.v.D, row + 1, x, y, z);
                 b = sh_channel(a.v.D, row + 2, x, y, z);
@@ -873,6 +874,11 @@ int launch_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc geom_all
             a.sh_stride = (row_f & 1) ? row_f : row_f + 1;
         }
         dyn = (size_t)PRE_T * a.sh_stride * sizeof(float);
+#ifdef SGR_PRE_DIRECT_SH
+        a.sh_stride = 0;
+        a.sh_vec = 0;
+        dyn = 0;
+#endif
     }
     a.geom = geom;
     a.radii = radii;
