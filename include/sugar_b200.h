@@ -164,6 +164,18 @@ SGR_API int sgr_field_backward(const SgrFieldParams *p, const float *x, const in
                        float *g_x, float *g_points, float *g_scaling, float *g_quaternions,
                        float *g_strengths, void *scratch, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Exact K-nearest-neighbour search (uniform grid).  Replaces pytorch3d.ops.knn_points as SuGaR
+ * calls it: reset_neighbors (sugar_model.py:1013-1030, queries == points, K = 16) and
+ * get_gaussians_closest_to_samples (sugar_model.py:1335-1343).
+ *   points f32[P,3] reference cloud, queries f32[Q,3]; 0 < K <= min(P, 64)
+ *   idx i64[Q,K], dist2 f32[Q,K]: neighbours ordered by increasing squared distance.
+ * `workspace` must hold sgr_knn_workspace_bytes(P).
+ * ------------------------------------------------------------------------------------------ */
+SGR_API size_t sgr_knn_workspace_bytes(int32_t P);
+SGR_API int sgr_knn(int32_t P, const float *points, int32_t Q, const float *queries, int32_t K, int64_t *idx,
+                    float *dist2, void *workspace, void *stream);
+
 /* Measurement hooks (bench.py): number of kernels this library has launched in this process;
  * optional CUDA-event bracketing of every launch on its own stream.  sgr_profile_read fills
  * total_ms[kind] / counts[kind] for kind < sgr_num_kernel_kinds() and resets the log. */

@@ -57,6 +57,9 @@ PROTOTYPES = {
     "sgr_field_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_field_forward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 12),
     "sgr_field_backward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 17),
+    "sgr_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "sgr_knn": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                          C.c_void_p]),
     "sgr_launch_count": (C.c_ulonglong, []),
     "sgr_num_kernel_kinds": (C.c_int, []),
     "sgr_kernel_name": (C.c_char_p, [C.c_int]),

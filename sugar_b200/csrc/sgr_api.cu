@@ -30,7 +30,8 @@ int cuda_fail(cudaError_t e, const char *what)
 // ---- launch counter + optional event profiling (not thread-safe: one profiling client at a time)
 static const char *const g_kind_names[K_NUM_KINDS] = {
     "preprocess", "tile_scan", "scatter", "tile_sort_smem", "tile_sort_global", "blend_forward", "blend_backward",
-    "preprocess_backward", "field_pack", "field_forward", "field_backward", "field_unpack", "misc"};
+    "preprocess_backward", "field_pack", "field_forward", "field_backward", "field_unpack", "knn_build", "knn_query",
+    "misc"};
 struct ProfRec {
     cudaEvent_t a, b;
     int kind;

@@ -545,22 +545,15 @@ __device__ __forceinline__ void cswap(uint64_t &a, uint64_t &b)
     b = hi;
 }
 
-template <int CAP, int LOWER>
-__global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const uint32_t *__restrict__ tile_start,
-                                                                        const uint32_t *__restrict__ counters,
-                                                                        uint64_t capacity,
-                                                                        const uint64_t *__restrict__ inst,
-                                                                        uint32_t *__restrict__ plist, int num_tiles)
+#define SGR_NET16 cswap(r[0], r[1]); cswap(r[2], r[3]); cswap(r[4], r[5]); cswap(r[6], r[7]); cswap(r[8], r[9]); cswap(r[10], r[11]); cswap(r[12], r[13]); cswap(r[14], r[15]); cswap(r[0], r[2]); cswap(r[1], r[3]); cswap(r[4], r[6]); cswap(r[5], r[7]); cswap(r[8], r[10]); cswap(r[9], r[11]); cswap(r[12], r[14]); cswap(r[13], r[15]); cswap(r[1], r[2]); cswap(r[5], r[6]); cswap(r[9], r[10]); cswap(r[13], r[14]); cswap(r[0], r[4]); cswap(r[1], r[5]); cswap(r[2], r[6]); cswap(r[3], r[7]); cswap(r[8], r[12]); cswap(r[9], r[13]); cswap(r[10], r[14]); cswap(r[11], r[15]); cswap(r[2], r[4]); cswap(r[3], r[5]); cswap(r[10], r[12]); cswap(r[11], r[13]); cswap(r[1], r[2]); cswap(r[3], r[4]); cswap(r[5], r[6]); cswap(r[9], r[10]); cswap(r[11], r[12]); cswap(r[13], r[14]); cswap(r[0], r[8]); cswap(r[1], r[9]); cswap(r[2], r[10]); cswap(r[3], r[11]); cswap(r[4], r[12]); cswap(r[5], r[13]); cswap(r[6], r[14]); cswap(r[7], r[15]); cswap(r[4], r[8]); cswap(r[5], r[9]); cswap(r[6], r[10]); cswap(r[7], r[11]); cswap(r[2], r[4]); cswap(r[3], r[5]); cswap(r[6], r[8]); cswap(r[7], r[9]); cswap(r[10], r[12]); cswap(r[11], r[13]); cswap(r[1], r[2]); cswap(r[3], r[4]); cswap(r[5], r[6]); cswap(r[7], r[8]); cswap(r[9], r[10]); cswap(r[11], r[12]); cswap(r[13], r[14]);
+
+// In-place merge sort of s_keys[0..n) by the NT threads of the CTA (all must call).  s_keys must
+// have room for ceil(n/VT)*VT words; n <= NT*VT.
+template <int NT>
+__device__ __forceinline__ void block_merge_sort(uint64_t *s_keys, const int n)
 {
     constexpr int VT = SORT_VT;
-    extern __shared__ __align__(16) uint64_t s_keys[];  // CAP words
-    if ((uint64_t)counters[0] > capacity) return;
     const int tid = threadIdx.x;
-    // grid-stride over tiles: rare size classes are launched with a small grid and skip cheaply
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint32_t lo = tile_start[tile];
-    const int n = (int)(tile_start[tile + 1] - lo);
-    if (n <= LOWER || n > CAP) continue;
     const int nact = (n + VT - 1) / VT;  // threads that own a window
     const int L = nact * VT;             // padded length (pad words = all ones sort last)
     uint64_t r[VT];
@@ -568,7 +561,7 @@ __global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const ui
 #pragma unroll
         for (int k = 0; k < VT; k++) {
             const int i = tid * VT + k;
-            r[k] = i < n ? inst[lo + i] : ~0ull;
+            r[k] = i < n ? s_keys[i] : ~0ull;
         }
         // Batcher odd-even merge sort network on the VT registers (19 comparators for 8, 63 for 16)
         static_assert(VT == 8 || VT == 16, "sorting network written out for 8 or 16 words per thread");
@@ -578,20 +571,11 @@ __global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const ui
             cswap(r[0], r[4]); cswap(r[1], r[5]); cswap(r[2], r[6]); cswap(r[3], r[7]); cswap(r[2], r[4]);
             cswap(r[3], r[5]); cswap(r[1], r[2]); cswap(r[3], r[4]); cswap(r[5], r[6]);
         } else {
-            cswap(r[0], r[1]); cswap(r[2], r[3]); cswap(r[4], r[5]); cswap(r[6], r[7]); cswap(r[8], r[9]);
-            cswap(r[10], r[11]); cswap(r[12], r[13]); cswap(r[14], r[15]); cswap(r[0], r[2]);
-            cswap(r[1], r[3]); cswap(r[4], r[6]); cswap(r[5], r[7]); cswap(r[8], r[10]); cswap(r[9], r[11]);
-            cswap(r[12], r[14]); cswap(r[13], r[15]); cswap(r[1], r[2]); cswap(r[5], r[6]); cswap(r[9], r[10]);
-            cswap(r[13], r[14]); cswap(r[0], r[4]); cswap(r[1], r[5]); cswap(r[2], r[6]); cswap(r[3], r[7]);
-            cswap(r[8], r[12]); cswap(r[9], r[13]); cswap(r[10], r[14]); cswap(r[11], r[15]);
-            cswap(r[2], r[4]); cswap(r[3], r[5]); cswap(r[10], r[12]); cswap(r[11], r[13]); cswap(r[1], r[2]);
-            cswap(r[3], r[4]); cswap(r[5], r[6]); cswap(r[9], r[10]); cswap(r[11], r[12]); cswap(r[13], r[14]);
-            cswap(r[0], r[8]); cswap(r[1], r[9]); cswap(r[2], r[10]); cswap(r[3], r[11]); cswap(r[4], r[12]);
-            cswap(r[5], r[13]); cswap(r[6], r[14]); cswap(r[7], r[15]); cswap(r[4], r[8]); cswap(r[5], r[9]);
-            cswap(r[6], r[10]); cswap(r[7], r[11]); cswap(r[2], r[4]); cswap(r[3], r[5]); cswap(r[6], r[8]);
-            cswap(r[7], r[9]); cswap(r[10], r[12]); cswap(r[11], r[13]); cswap(r[1], r[2]); cswap(r[3], r[4]);
-            cswap(r[5], r[6]); cswap(r[7], r[8]); cswap(r[9], r[10]); cswap(r[11], r[12]); cswap(r[13], r[14]);
+            SGR_NET16
         }
+    }
+    __syncthreads();  // every thread has read its window before anyone overwrites it
+    if (tid < nact) {
 #pragma unroll
         for (int k = 0; k < VT; k++) s_keys[tid * VT + k] = r[k];
     }
@@ -633,8 +617,143 @@ __global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const ui
         }
     }
     __syncthreads();
-    for (int i = tid; i < n; i += CAP / VT) plist[lo + i] = (uint32_t)s_keys[i];
-    __syncthreads();  // s_keys is reused by the next tile of this CTA
+}
+
+template <int CAP, int LOWER>
+__global__ void __launch_bounds__(CAP / SORT_VT) tile_sort_merge_kernel(const uint32_t *__restrict__ tile_start,
+                                                                        const uint32_t *__restrict__ counters,
+                                                                        uint64_t capacity,
+                                                                        const uint64_t *__restrict__ inst,
+                                                                        uint32_t *__restrict__ plist, int num_tiles)
+{
+    extern __shared__ __align__(16) uint64_t s_keys[];  // CAP words
+    if ((uint64_t)counters[0] > capacity) return;
+    const int tid = threadIdx.x;
+    // grid-stride over tiles: rare size classes are launched with a small grid and skip cheaply
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t lo = tile_start[tile];
+        const int n = (int)(tile_start[tile + 1] - lo);
+        if (n <= LOWER || n > CAP) continue;
+        for (int i = tid; i < n; i += CAP / SORT_VT) s_keys[i] = inst[lo + i];
+        __syncthreads();
+        block_merge_sort<CAP / SORT_VT>(s_keys, n);
+        for (int i = tid; i < n; i += CAP / SORT_VT) plist[lo + i] = (uint32_t)s_keys[i];
+        __syncthreads();  // s_keys is reused by the next tile of this CTA
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-tile sort, fast path for the common size class (512 < n <= 2048): one MSD bucket pass on the
+// depth bits + insertion sort inside the (tiny) buckets.
+//   bucket(word) = (depth_bits - min_bits) >> sh   with sh chosen so that the tile's depth range
+// maps onto at most NB = 1024 buckets: monotone in the key, so concatenating the sorted buckets
+// is the sorted tile.  Counting (shared int atomics), one exclusive scan, an atomic-cursor
+// scatter, then every thread insertion-sorts NB/256 buckets on the full 64-bit words (total
+// order incl. the Gaussian id, so the result is identical to the merge sort's).  Depth
+// distributions that put more than BUCKET_MAX words in one bucket (e.g. many equal depths) take
+// the merge sort instead -- same kernel, same buffers.
+// ------------------------------------------------------------------------------------------------
+constexpr int BK_CAP = 2048, BK_T = 256, BK_NB = 1024, BK_LOG2NB = 10, BUCKET_MAX = 24;
+
+__global__ void __launch_bounds__(BK_T) tile_sort_bucket_kernel(const uint32_t *__restrict__ tile_start,
+                                                                 const uint32_t *__restrict__ counters, uint64_t capacity,
+                                                                 const uint64_t *__restrict__ inst,
+                                                                 uint32_t *__restrict__ plist, int num_tiles, int lower)
+{
+    __shared__ __align__(16) uint64_t s_a[BK_CAP];
+    __shared__ __align__(16) uint64_t s_b[BK_CAP];
+    __shared__ uint32_t s_cnt[BK_NB];
+    __shared__ uint32_t s_off[BK_NB];
+    __shared__ uint32_t s_red[4];  // min bits, max bits, max bucket count, scan carry helper
+    __shared__ uint32_t s_wsum[BK_T / 32];
+    if ((uint64_t)counters[0] > capacity) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t lo = tile_start[tile];
+        const int n = (int)(tile_start[tile + 1] - lo);
+        if (n <= lower || n > BK_CAP) continue;
+        if (tid == 0) {
+            s_red[0] = 0xffffffffu;
+            s_red[1] = 0u;
+            s_red[2] = 0u;
+        }
+        for (int i = tid; i < BK_NB; i += BK_T) s_cnt[i] = 0;
+        __syncthreads();
+        uint32_t mn = 0xffffffffu, mx = 0u;
+        for (int i = tid; i < n; i += BK_T) {
+            const uint64_t k = inst[lo + i];
+            s_a[i] = k;
+            const uint32_t d = (uint32_t)(k >> 32);
+            mn = min(mn, d);
+            mx = max(mx, d);
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) {
+            atomicMin(&s_red[0], mn);
+            atomicMax(&s_red[1], mx);
+        }
+        __syncthreads();
+        const uint32_t dmin = s_red[0], range = s_red[1] - dmin;
+        const int sh = max(0, 32 - __clz(range) - BK_LOG2NB);  // (range >> sh) < NB
+        for (int i = tid; i < n; i += BK_T) atomicAdd(&s_cnt[((uint32_t)(s_a[i] >> 32) - dmin) >> sh], 1u);
+        __syncthreads();
+        // exclusive scan of the NB counts (4 consecutive buckets per thread) + max count
+        {
+            uint32_t c[4], sum = 0, cm = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                c[k] = s_cnt[tid * 4 + k];
+                sum += c[k];
+                cm = max(cm, c[k]);
+            }
+            cm = __reduce_max_sync(0xffffffffu, cm);
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_wsum[wid] = inc;
+            if (lane == 0) atomicMax(&s_red[2], cm);
+            __syncthreads();
+            uint32_t basev = inc - sum;
+            for (int w = 0; w < wid; w++) basev += s_wsum[w];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                s_off[tid * 4 + k] = basev;
+                s_cnt[tid * 4 + k] = 0;  // reused as the scatter cursor
+                basev += c[k];
+            }
+        }
+        __syncthreads();
+        if (s_red[2] > (uint32_t)BUCKET_MAX) {
+            block_merge_sort<BK_T>(s_a, n);  // skewed depths: generic path (ends with a barrier)
+            for (int i = tid; i < n; i += BK_T) plist[lo + i] = (uint32_t)s_a[i];
+        } else {
+            for (int i = tid; i < n; i += BK_T) {
+                const uint64_t k = s_a[i];
+                const uint32_t b = ((uint32_t)(k >> 32) - dmin) >> sh;
+                s_b[s_off[b] + atomicAdd(&s_cnt[b], 1u)] = k;
+            }
+            __syncthreads();
+            for (int b = tid; b < BK_NB; b += BK_T) {
+                const int c = (int)s_cnt[b];
+                uint64_t *q = s_b + s_off[b];
+                for (int i = 1; i < c; i++) {
+                    const uint64_t key = q[i];
+                    int j = i - 1;
+                    while (j >= 0 && q[j] > key) {
+                        q[j + 1] = q[j];
+                        j--;
+                    }
+                    q[j + 1] = key;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += BK_T) plist[lo + i] = (uint32_t)s_b[i];
+        }
+        __syncthreads();
     }
 }
 
@@ -792,8 +911,12 @@ static int launch_binning_and_blend(const ViewConsts &v, int P, const GeomState 
     const int small_grid = T < 296 ? T : 296;  // 2 CTAs per SM, grid-stride over tiles
     tile_sort_merge_kernel<512, 0><<<T, 512 / SORT_VT, 512 * 8, st>>>(img.tile_start, img.counters, capacity, bin.inst_a,
                                                                       bin.plist, T);
+#ifdef SGR_SORT_MERGE_ONLY
     tile_sort_merge_kernel<2048, 512><<<T, 2048 / SORT_VT, 2048 * 8, st>>>(img.tile_start, img.counters, capacity,
                                                                            bin.inst_a, bin.plist, T);
+#else
+    tile_sort_bucket_kernel<<<T, BK_T, 0, st>>>(img.tile_start, img.counters, capacity, bin.inst_a, bin.plist, T, 512);
+#endif
     tile_sort_merge_kernel<8192, 2048><<<small_grid, 8192 / SORT_VT, 8192 * 8, st>>>(img.tile_start, img.counters,
                                                                                      capacity, bin.inst_a, bin.plist, T);
     sgr::prof_end(st);

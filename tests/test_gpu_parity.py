@@ -31,6 +31,10 @@ CASES = [
     # radix fallback (tiles above 8192 instances)
     ("dense_tiles", 120000, 64, 48, "posed", False, 0, False, (0.0, 0.0, 0.0)),
     ("mid_tiles", 35000, 64, 48, "posed", True, 1, False, (0.5, 0.5, 0.5)),
+    # every Gaussian at the same camera depth: all sort keys of a tile tie on depth, order = Gaussian id
+    ("coplanar", 20000, 160, 96, "identity", False, 0, False, (0.0, 0.0, 0.0)),
+    # two thin depth shells: very skewed per-tile depth histogram (bucket sort falls back to merge)
+    ("two_shells", 60000, 128, 96, "identity", False, 0, False, (0.0, 0.0, 0.0)),
 ]
 
 
@@ -41,10 +45,22 @@ def _scene(name, P, W, H, camera):
         kw["mesh_bound"] = True
     if name == "big_splats":
         kw["px_sigma"] = 25.0
+    if name == "coplanar":
+        kw["zrange"] = (5.0, 5.0)
+        kw["frac_behind"] = 0.0
+    if name == "two_shells":
+        kw["px_sigma"] = 0.8
     if name in ("dense_tiles", "mid_tiles"):
         kw["px_sigma"] = 0.8
         kw["lateral"] = 0.9
-    return scenes.make_scene(P, W, H, seed=hash(name) % 1000 if False else len(name) * 7 + P % 13, camera=camera, **kw)
+    sc = scenes.make_scene(P, W, H, seed=len(name) * 7 + P % 13, camera=camera, **kw)
+    if name == "two_shells":  # snap depths onto two thin shells (identity camera: depth == z)
+        m = sc.means3D.copy()
+        front = m[:, 2] > 0.3
+        shell = np.where(np.arange(P) % 2 == 0, 3.0, 7.0) + (np.arange(P) % 7) * 1e-6
+        m[front, 2] = shell[front].astype(np.float32)
+        sc = sc._replace(means3D=m)
+    return sc
 
 
 def _cov_from_oracle(sc):
