@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sh-factors", action="store_true",
+                    help="N>1: all-reduce the full dL_dsh instead of all-gathering the SH factors")
     return ap.parse_args()
 
 
@@ -207,6 +209,10 @@ def main():
     if dist is not None:
         from sugar_b200 import parallel
         arena = parallel.GradArena(P, 16, dev)
+        if not args.no_sh_factors:
+            # all-gather 12 B/Gaussian SH factors instead of all-reducing 192 B/Gaussian of dL_dsh
+            from sugar_b200 import _C as _Cmod
+            _Cmod.SH_FACTOR_MODE = True
 
     def zero_grads():
         for p in params.values():
@@ -219,7 +225,7 @@ def main():
                             shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
         torch.autograd.backward(color, dL)
         if arena is not None:
-            arena.all_reduce_from(params)
+            arena.all_reduce_from(params, campos=campos, sh_degree=D)
         zero_grads()
         return radii
 
@@ -251,7 +257,7 @@ def main():
         loss = (color * g).sum()
         loss.backward()
         if arena is not None:
-            arena.all_reduce_from(params)
+            arena.all_reduce_from(params, campos=cp, sh_degree=D)
         val = loss.item()  # device -> host read of the step's result
         zero_grads()
         return val
@@ -305,7 +311,9 @@ def main():
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{P} Gaussians (SH deg {D}, M=16) {W}x{H}, 1 view per GPU per step, fwd+bwd",
                       "visible": V_vis, "l2_policy": "inputs (708 MB of Gaussian parameters) larger than L2; no flush",
-                      "parallelism": f"view-dp{world}" if world > 1 else "single"},
+                      "parallelism": f"view-dp{world}" if world > 1 else "single",
+                      "exchange": ("none" if world == 1 else "all-reduce 236 B/Gaussian" if args.no_sh_factors else
+                                   "all-reduce 44 B/Gaussian + all-gather 12 B/Gaussian/view SH factors")},
            "clocks": clk}
     n_e2e = 1 if use_ref else world
     out["e2e"] = {"value": n_e2e / (ms_e2e * 1e-3), "unit": "views/s",

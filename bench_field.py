@@ -85,6 +85,18 @@ def main():
     f = fo.field_values_torch(cl[0], nbr_c, *cl[1:], density_factor=1.0 / K)
     (f["sdf"] * w_c).sum().backward()
     cpu_s = time.perf_counter() - t0
+    # K-NN table build (reset_neighbors): cloud against itself
+    from sugar_b200 import knn
+    for _ in range(2):
+        knn.reset_neighbors(points, K)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        kd, ki = knn.reset_neighbors(points, K)
+    e1.record()
+    torch.cuda.synchronize()
+    knn_ms = e0.elapsed_time(e1) / 5
     fwd_bytes = N * (12 + 8 * K + 48 * K)
     stages = {k: {"ms": round(v[0] / v[1], 4)} for k, v in prof.items()}
     if "field_forward" in stages:
@@ -95,6 +107,8 @@ def main():
         "torch_same_gpu": {"value": N / (ms_ref * 1e-3), "ms_per_step": ms_ref},
         "cpu_baseline": {"value": ns / cpu_s, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{ns} samples of the workload, PyTorch op chain of sugar_model.py:1247-1316"},
+        "knn_reset_neighbors": {"ms": knn_ms, "points_per_s": P / (knn_ms * 1e-3), "K": K,
+                                "note": "exact K-NN of the cloud against itself (uniform grid), replaces pytorch3d.knn_points"},
         "stages": stages}))
 
 

@@ -93,8 +93,10 @@ SGR_API int sgr_rasterize_forward(const SgrView *view, const SgrGaussians *g,
  * every output row is written by the kernels (zeros for culled Gaussians), so the caller may
  * pass uninitialised memory.  `grad_scratch` must hold sgr_backward_scratch_bytes(P).
  *   dL_dmeans2D f32[P,3], dL_dcolors f32[P,3], dL_dopacity f32[P,1], dL_dmeans3D f32[P,3],
- *   dL_dcov3D f32[P,6], dL_dsh f32[P,M,3] (may be NULL when M==0), dL_dscales f32[P,3],
- *   dL_drotations f32[P,4]. */
+ *   dL_dcov3D f32[P,6], dL_dsh f32[P,M,3], dL_dscales f32[P,3], dL_drotations f32[P,4].
+ * dL_dsh may be NULL: when M == 0, or with SH present to select "factor mode" -- dL_dsh is not
+ * produced and dL_dcolors holds the clamp-masked dL/dRGB per Gaussian, from which
+ * sgr_sh_grad_from_factors rebuilds (the sum over views of) dL_dsh.  All other outputs are unchanged. */
 SGR_API int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii,
                            const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
                            int64_t num_rendered, const float *dL_dout_color,
@@ -102,6 +104,13 @@ SGR_API int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, c
                            float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh,
                            float *dL_dscales, float *dL_drotations,
                            void *grad_scratch, void *stream);
+
+/* dL_dsh[P,M,3] = sum over views v of basis_k(normalize(mean - campos[v])) * dRGB[v][P,3]  (the SH
+ * part of backward.cu:20-139 is an outer product per view).  Used by the view-parallel step: ranks
+ * all-gather the 12 B/Gaussian factors instead of all-reducing 12*M B/Gaussian of dL_dsh.
+ *   campos f32[V,3], dRGB f32[V,P,3] (clamp-masked, from factor mode), dL_dsh f32[P,M,3] fully written. */
+SGR_API int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float *means3D,
+                                     const float *campos, const float *dRGB, float *dL_dsh, void *stream);
 
 /* markVisible (rasterizer_impl.cu:141-153): present[i] = view-space z > 0.2. */
 SGR_API int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,

@@ -181,6 +181,12 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     return R, out_color, radii, geom_t, binning_t, img_t
 
 
+# View-parallel "SH factor mode" (sugar_b200/parallel.py): when True the backward does not produce
+# dL_dsh (the returned tensor is the uninitialised arena slot) and dL_dcolors carries the clamp-masked
+# dL/dRGB factor; parallel.GradArena rebuilds the summed dL_dsh after an all-gather of the factors.
+SH_FACTOR_MODE = False
+
+
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh,
                                  degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
@@ -223,7 +229,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                 C.byref(view), C.byref(g), radii.data_ptr(), geomBuffer.data_ptr(), binningBuffer.data_ptr(),
                 imageBuffer.data_ptr(), int(R), _ptr(dL_dout_color, "dL_dout_color"), dL_dmeans2D.data_ptr(),
                 dL_dcolors.data_ptr(), dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(),
-                dL_dsh.data_ptr() if M else None, dL_dscales.data_ptr(), dL_drotations.data_ptr(),
+                dL_dsh.data_ptr() if (M and not SH_FACTOR_MODE) else None, dL_dscales.data_ptr(), dL_drotations.data_ptr(),
                 scratch.data_ptr(), stream))
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "sgr_rasterize_backward": (C.c_int, [C.POINTER(SgrView), C.POINTER(SgrGaussians)] + [C.c_void_p] * 4 +
                                [C.c_int64] + [C.c_void_p] * 11),
     "sgr_mark_visible": (C.c_int, [C.c_int32] + [C.c_void_p] * 5),
+    "sgr_sh_grad_from_factors": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "sgr_geometry_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_binning_bytes": (C.c_size_t, [C.c_int64]),
     "sgr_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),

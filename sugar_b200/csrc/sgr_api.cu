@@ -281,8 +281,7 @@ int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int
     if (rc) return rc;
     if (g->P == 0) return SGR_OK;
     if (!radii || !geom_buffer || !binning_buffer || !image_buffer || !dL_dout_color || !dL_dmeans2D || !dL_dcolors ||
-        !dL_dopacity || !dL_dmeans3D || !dL_dcov3D || !dL_dscales || !dL_drotations || !grad_scratch ||
-        (g->M > 0 && !dL_dsh)) {
+        !dL_dopacity || !dL_dmeans3D || !dL_dcov3D || !dL_dscales || !dL_drotations || !grad_scratch) {
         set_error("null pointer passed to sgr_rasterize_backward");
         return SGR_EINVAL;
     }

@@ -445,9 +445,13 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             o_m2d[1] = dmy;
             o_m2d[2] = 0.f;
             sm[PB_O_OPA + tid] = g1.y;
-            o_col[0] = g1.z;
-            o_col[1] = g1.w;
-            o_col[2] = g2;
+            // dL/dcolour of the Gaussian.  In SH "factor mode" (SH present but no dL_dsh buffer: the
+            // view-parallel path rebuilds dL_dsh from per-view factors, sgr_sh_grad_from_factors) this
+            // output carries the clamp-masked gradient, i.e. exactly the factor dL/dRGB.
+            const bool factor_mode = a.shs && !a.dsh;
+            o_col[0] = (factor_mode && (cl & 1u)) ? 0.f : g1.z;
+            o_col[1] = (factor_mode && (cl & 2u)) ? 0.f : g1.w;
+            o_col[2] = (factor_mode && (cl & 4u)) ? 0.f : g2;
 
             const float *vm = a.v.viewmatrix, *proj = a.v.projmatrix;
             const float mx = sm[PB_MEANS + tid * 3], my = sm[PB_MEANS + tid * 3 + 1], mz = sm[PB_MEANS + tid * 3 + 2];
@@ -617,6 +621,86 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// dL_dsh from per-view factors (view-parallel multi-GPU step).  One thread per Gaussian keeps the
+// 3*M accumulators in registers, loops over the views' (camera position, dL/dRGB) pairs, and the
+// block writes the rows out through shared memory with 16-byte coalesced stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int SF_T = 128;
+
+__global__ void __launch_bounds__(SF_T) sh_grad_from_factors_kernel(int P, int M, int deg, int nviews,
+                                                                     const float *__restrict__ means,
+                                                                     const float *__restrict__ campos,
+                                                                     const float *__restrict__ dRGB, float *__restrict__ dsh)
+{
+    extern __shared__ __align__(16) float s_rows[];  // SF_T rows x stride floats
+    const int tid = threadIdx.x, base = blockIdx.x * SF_T, i = base + tid;
+    const int n = min(SF_T, P - base);
+    const int row_f = M * 3;
+    const int stride = (row_f & 1) ? row_f : row_f + 1;  // odd stride: conflict-free scalar access
+    float acc[16][3];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+    if (tid < n) {
+        const float mx = means[3 * i], my = means[3 * i + 1], mz = means[3 * i + 2];
+        for (int v = 0; v < nviews; v++) {
+            const float *g = dRGB + ((size_t)v * P + i) * 3;
+            const float gr = g[0], gg = g[1], gb = g[2];
+            if (gr == 0.f && gg == 0.f && gb == 0.f) continue;  // not visible in this view
+            const float ox = mx - campos[3 * v], oy = my - campos[3 * v + 1], oz = mz - campos[3 * v + 2];
+            const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
+            const float x = ox * inv, y = oy * inv, z = oz * inv;
+            float w[16];
+            w[0] = SH_C0;
+            if (deg > 0) {
+                w[1] = -SH_C1 * y;
+                w[2] = SH_C1 * z;
+                w[3] = -SH_C1 * x;
+                if (deg > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    w[4] = b_SH_C2[0] * xy;
+                    w[5] = b_SH_C2[1] * yz;
+                    w[6] = b_SH_C2[2] * (2.f * zz - xx - yy);
+                    w[7] = b_SH_C2[3] * xz;
+                    w[8] = b_SH_C2[4] * (xx - yy);
+                    if (deg > 2) {
+                        w[9] = b_SH_C3[0] * y * (3.f * xx - yy);
+                        w[10] = b_SH_C3[1] * xy * z;
+                        w[11] = b_SH_C3[2] * y * (4.f * zz - xx - yy);
+                        w[12] = b_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                        w[13] = b_SH_C3[4] * x * (4.f * zz - xx - yy);
+                        w[14] = b_SH_C3[5] * z * (xx - yy);
+                        w[15] = b_SH_C3[6] * x * (xx - 3.f * yy);
+                    }
+                }
+            }
+            const int used = (deg + 1) * (deg + 1);
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (k < used) {
+                    acc[k][0] = fmaf(w[k], gr, acc[k][0]);
+                    acc[k][1] = fmaf(w[k], gg, acc[k][1]);
+                    acc[k][2] = fmaf(w[k], gb, acc[k][2]);
+                }
+        }
+        float *row = s_rows + tid * stride;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (k < M) {
+                row[k * 3] = acc[k][0];
+                row[k * 3 + 1] = acc[k][1];
+                row[k * 3 + 2] = acc[k][2];
+            }
+        for (int k = 16; k < M; k++) row[k * 3] = row[k * 3 + 1] = row[k * 3 + 2] = 0.f;
+    }
+    __syncthreads();
+    float *dst = dsh + (size_t)base * row_f;
+    for (int k = tid; k < n * row_f; k += SF_T) {
+        const int r = k / row_f, c = k - r * row_f;
+        dst[k] = s_rows[r * stride + c];
+    }
+}
+
 int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
                     const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
                     const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
@@ -701,3 +785,24 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
 }
 
 }  // namespace sgr
+
+
+extern "C" int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float *means3D,
+                                        const float *campos, const float *dRGB, float *dL_dsh, void *stream)
+{
+    using namespace sgr;
+    if (P < 0 || M <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M || num_views <= 0 ||
+        (P > 0 && (!means3D || !campos || !dRGB || !dL_dsh))) {
+        set_error("bad arguments to sgr_sh_grad_from_factors");
+        return SGR_EINVAL;
+    }
+    if (P == 0) return SGR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int row_f = M * 3, stride = (row_f & 1) ? row_f : row_f + 1;
+    const size_t dyn = (size_t)SF_T * stride * sizeof(float);
+    SGR_LAUNCH(K_MISC, st,
+               sh_grad_from_factors_kernel<<<(P + SF_T - 1) / SF_T, SF_T, dyn, st>>>(P, M, sh_degree, num_views, means3D,
+                                                                                     campos, dRGB, dL_dsh));
+    SGR_CUDA(cudaGetLastError());
+    return SGR_OK;
+}

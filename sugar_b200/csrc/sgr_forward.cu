@@ -356,26 +356,37 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, const ushor
         rc = rect[idx];
         if (rc.z > rc.x) dbits = __float_as_uint(depth[idx]);
     }
-    constexpr int SMALL = 6;
+    // Rects of up to SMALL tiles are walked by their own thread, BATCH slots at a time (the returning
+    // atomics of a batch are in flight together; all lanes of the warp work concurrently); only very
+    // large rects are walked cooperatively by the whole warp.
+#ifndef SGR_SCATTER_SMALL
+#define SGR_SCATTER_SMALL 6
+#endif
+#ifndef SGR_SCATTER_BATCH
+#define SGR_SCATTER_BATCH 6
+#endif
+    constexpr int SMALL = SGR_SCATTER_SMALL, BATCH = SGR_SCATTER_BATCH;
     const int rw = (int)rc.z - (int)rc.x, rcnt = (rc.z > rc.x && rc.w > rc.y) ? rw * ((int)rc.w - (int)rc.y) : 0;
     if (rcnt > 0 && rcnt <= SMALL) {
-        // claim all slots first (independent returning atomics in flight together), then store
         const uint64_t word = ((uint64_t)dbits << 32) | (uint32_t)idx;
-        uint32_t slot[SMALL];
         int tx = 0, trow = (int)rc.y * gx + (int)rc.x;
+        for (int done = 0; done < rcnt; done += BATCH) {
+            uint32_t slot[BATCH];
+            const int m = min(BATCH, rcnt - done);
 #pragma unroll
-        for (int k = 0; k < SMALL; k++) {
-            if (k < rcnt) {
-                slot[k] = atomicAdd(cursor + trow + tx, 1u);
-                if (++tx == rw) {
-                    tx = 0;
-                    trow += gx;
+            for (int k = 0; k < BATCH; k++) {
+                if (k < m) {
+                    slot[k] = atomicAdd(cursor + trow + tx, 1u);
+                    if (++tx == rw) {
+                        tx = 0;
+                        trow += gx;
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < SMALL; k++)
-            if (k < rcnt) inst[slot[k]] = word;
+            for (int k = 0; k < BATCH; k++)
+                if (k < m) inst[slot[k]] = word;
+        }
     }
     unsigned todo = __ballot_sync(0xffffffffu, rcnt > SMALL);
     while (todo) {

@@ -105,6 +105,18 @@ def make_scene(P: int, width: int, height: int, seed: int = 0, fov_x_deg: float 
                  campos, float(np.float32(tanfovx)), float(np.float32(tanfovy)), width, height)
 
 
+def with_camera_offset(sc: Scene, yaw: float, shift) -> Scene:
+    """The same cloud seen from a camera moved relative to `sc`'s: x_cam' = R_y(yaw) x_cam + shift."""
+    V = sc.viewmatrix.astype(np.float64).T
+    D = np.eye(4)
+    D[:3, :3] = _rot(np.array([0.0, 1.0, 0.0]), yaw)
+    D[:3, 3] = np.asarray(shift, np.float64)
+    V2 = D @ V
+    Pm = projection_matrix(0.01, 100.0, sc.tanfovx, sc.tanfovy)
+    campos = (-V2[:3, :3].T @ V2[:3, 3]).astype(np.float32)
+    return sc._replace(viewmatrix=V2.T.astype(np.float32), projmatrix=(V2.T @ Pm.T).astype(np.float32), campos=campos)
+
+
 def upstream_grad(width: int, height: int, seed: int = 1) -> np.ndarray:
     """Fixed dL/dimage: loss = (image * Wt).sum(), Wt ~ N(0,1)/(3HW)."""
     rng = np.random.Generator(np.random.PCG64(seed))

@@ -50,3 +50,44 @@ def test_arena_allreduce_gloo_world2():
             assert torch.allclose(r[2][k], mean, atol=1e-7), k
     assert res[0][3] == [0, 2, 4, 6] and res[1][3] == [1, 3, 5, 7]
     assert 59 * 50 == sum(n for _, n in __import__("sugar_b200.parallel", fromlist=["x"]).GradArena(50, 16, "cpu").offsets.values())
+
+
+def test_arena_reduces_backward_buffer_in_place():
+    """Gradients handed out by an autograd Function as slices of one flat buffer (what sugar_b200's
+    backward does) are recognised and reduced in place: no packing copy."""
+    import torch
+    from sugar_b200 import parallel
+    P, M = 10, 2
+    widths = (3, 1, 3 * M, 3, 4, 3, 3, 6)
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, *a):
+            return sum(x.sum() for x in a).reshape(1)
+
+        @staticmethod
+        def backward(ctx, g):
+            flat = torch.arange(8 + P * sum(widths) + 20, dtype=torch.float32)[8:]  # nonzero storage offset
+            outs, o = [], 0
+            for k in widths[:5]:
+                outs.append(flat[o:o + P * k])
+                o += P * k
+            return (outs[0].view(P, 3), outs[1].view(P, 1), outs[2].view(P, M, 3), outs[3].view(P, 3),
+                    outs[4].view(P, 4))
+
+    ps = dict(means3D=torch.zeros(P, 3), opacities=torch.zeros(P, 1), shs=torch.zeros(P, M, 3),
+              scales=torch.zeros(P, 3), rotations=torch.zeros(P, 4))
+    ps = {k: v.requires_grad_(True) for k, v in ps.items()}
+    Fn.apply(*ps.values()).sum().backward()
+    arena = parallel.GradArena(P, M, "cpu")
+    buf = arena._shared_base(ps)
+    assert buf is not None and buf.numel() == arena.flat.numel()
+    assert buf.data_ptr() == ps["means3D"].grad.data_ptr()
+    out = arena.all_reduce_from(ps, scale=2.0)
+    assert out.data_ptr() == buf.data_ptr()
+    assert float(ps["means3D"].grad[0, 0]) == 16.0  # scaled through the alias
+    # separate tensors (e.g. after gradient accumulation) fall back to packing
+    ps2 = {k: v.detach().clone().requires_grad_(True) for k, v in ps.items()}
+    for v in ps2.values():
+        v.grad = torch.ones_like(v)
+    assert arena._shared_base(ps2) is None
