@@ -200,6 +200,9 @@ def main():
     dL_h = torch.from_numpy(scenes.upstream_grad(W, H, seed=1 + rank) / max(world, 1)).pin_memory()
     viewmatrix, projmatrix, campos, bg, dL = (x.to(dev) for x in (viewmatrix_h, projmatrix_h, campos_h, bg_h, dL_h))
 
+    # every rank knows the whole batch's cameras (seeded view schedule): all positions, [world,3]
+    campos_all = campos.reshape(1, 3).repeat(max(world, 1), 1).contiguous()
+
     def settings(vm, pm, cp, b):
         return mod.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy,
                                                  bg=b, scale_modifier=1.0, viewmatrix=vm, projmatrix=pm, sh_degree=D,
@@ -211,8 +214,7 @@ def main():
         arena = parallel.GradArena(P, 16, dev)
         if not args.no_sh_factors:
             # all-gather 12 B/Gaussian SH factors instead of all-reducing 192 B/Gaussian of dL_dsh
-            from sugar_b200 import _C as _Cmod
-            _Cmod.SH_FACTOR_MODE = True
+            parallel.set_sh_factor_mode(True)
 
     def zero_grads():
         for p in params.values():
@@ -225,7 +227,7 @@ def main():
                             shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
         torch.autograd.backward(color, dL)
         if arena is not None:
-            arena.all_reduce_from(params, campos=campos, sh_degree=D)
+            arena.all_reduce_from(params, campos=campos_all, sh_degree=D)
         zero_grads()
         return radii
 
@@ -257,7 +259,7 @@ def main():
         loss = (color * g).sum()
         loss.backward()
         if arena is not None:
-            arena.all_reduce_from(params, campos=cp, sh_degree=D)
+            arena.all_reduce_from(params, campos=campos_all, sh_degree=D)
         val = loss.item()  # device -> host read of the step's result
         zero_grads()
         return val

@@ -105,6 +105,21 @@ SGR_API int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, c
                            float *dL_dscales, float *dL_drotations,
                            void *grad_scratch, void *stream);
 
+/* The same backward with a stage hook.  In factor mode (SH present, dL_dsh == NULL) and with a
+ * non-NULL hook, the masked dL/dRGB factors are produced by their own small kernel right after the
+ * blend pass and `hook(hook_ctx, SGR_STAGE_SH_FACTORS_READY)` is called on the host at that point of
+ * the enqueue: everything enqueued on `stream` so far makes dL_dcolors final, so the caller can record
+ * an event / start the all-gather of the factors there and have it overlap the per-Gaussian backward
+ * that is enqueued next.  Otherwise identical to sgr_rasterize_backward. */
+#define SGR_STAGE_SH_FACTORS_READY 1
+typedef void (*SgrStageHook)(void *ctx, int32_t stage);
+SGR_API int sgr_rasterize_backward_staged(const SgrView *view, const SgrGaussians *g, const int32_t *radii,
+                                          const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
+                                          int64_t num_rendered, const float *dL_dout_color, float *dL_dmeans2D,
+                                          float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D, float *dL_dcov3D,
+                                          float *dL_dsh, float *dL_dscales, float *dL_drotations, void *grad_scratch,
+                                          void *stream, SgrStageHook hook, void *hook_ctx);
+
 /* dL_dsh[P,M,3] = sum over views v of basis_k(normalize(mean - campos[v])) * dRGB[v][P,3]  (the SH
  * part of backward.cu:20-139 is an outer product per view).  Used by the view-parallel step: ranks
  * all-gather the 12 B/Gaussian factors instead of all-reducing 12*M B/Gaussian of dL_dsh.

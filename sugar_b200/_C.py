@@ -185,6 +185,10 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 # dL_dsh (the returned tensor is the uninitialised arena slot) and dL_dcolors carries the clamp-masked
 # dL/dRGB factor; parallel.GradArena rebuilds the summed dL_dsh after an all-gather of the factors.
 SH_FACTOR_MODE = False
+# Optional callable(dRGB [P,3]) invoked (factor mode only) at the point of the backward's enqueue where
+# the factors are final on the stream, i.e. before the per-Gaussian backward is enqueued: the
+# view-parallel step starts its all-gather there (include/sugar_b200.h, sgr_rasterize_backward_staged).
+FACTOR_HOOK = None
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
@@ -196,10 +200,10 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
     with torch.cuda.device(dev):
         # All eight gradients + the accumulator scratch live in ONE rounded allocation.  The first
-        # (3 + 1 + 3M + 3 + 4) * P floats are exactly the multi-GPU all-reduce arena
-        # [means3D | opacity | sh | scales | rotations] (sugar_b200/parallel.py), so the view-parallel
-        # step reduces them in place without packing.
-        widths = (3, 1, 3 * M, 3, 4, 3, 3, 6)
+        # (3 + 1 + 3 + 4 + 3M) * P floats are exactly the multi-GPU all-reduce arena
+        # [means3D | opacity | scales | rotations | sh] (sugar_b200/parallel.py), so the view-parallel
+        # step reduces them in place without packing (sh last: factor mode reduces only the 11P prefix).
+        widths = (3, 1, 3, 4, 3 * M, 3, 3, 6)
         n_scratch = (lib.sgr_backward_scratch_bytes(P) + 3) // 4 if P else 0
         flat = _big_empty(_round_up(4 * (P * sum(widths) + n_scratch) + 256, _ROUND) // 4, torch.float32, dev)
         offs, o = [], 0
@@ -209,9 +213,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         part = lambda k, shape: flat[offs[k]:offs[k] + P * widths[k]].view(shape)
         dL_dmeans3D = part(0, (P, 3))
         dL_dopacity = part(1, (P, 1))
-        dL_dsh = part(2, (P, M, 3))
-        dL_dscales = part(3, (P, 3))
-        dL_drotations = part(4, (P, 4))
+        dL_dscales = part(2, (P, 3))
+        dL_drotations = part(3, (P, 4))
+        dL_dsh = part(4, (P, M, 3))
         dL_dmeans2D = part(5, (P, 3))
         dL_dcolors = part(6, (P, 3))
         dL_dcov3D = part(7, (P, 6))
@@ -225,12 +229,26 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             # opacities are not an input of the reference's backward; the forward stored them
             g = _gauss_struct(P, M, means3D, None, sh, colors, scales, rotations, cov3D_precomp)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            check(lib.sgr_rasterize_backward(
-                C.byref(view), C.byref(g), radii.data_ptr(), geomBuffer.data_ptr(), binningBuffer.data_ptr(),
-                imageBuffer.data_ptr(), int(R), _ptr(dL_dout_color, "dL_dout_color"), dL_dmeans2D.data_ptr(),
-                dL_dcolors.data_ptr(), dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(),
-                dL_dsh.data_ptr() if (M and not SH_FACTOR_MODE) else None, dL_dscales.data_ptr(), dL_drotations.data_ptr(),
-                scratch.data_ptr(), stream))
+            args = (C.byref(view), C.byref(g), radii.data_ptr(), geomBuffer.data_ptr(), binningBuffer.data_ptr(),
+                    imageBuffer.data_ptr(), int(R), _ptr(dL_dout_color, "dL_dout_color"), dL_dmeans2D.data_ptr(),
+                    dL_dcolors.data_ptr(), dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(),
+                    dL_dsh.data_ptr() if (M and not SH_FACTOR_MODE) else None, dL_dscales.data_ptr(),
+                    dL_drotations.data_ptr(), scratch.data_ptr(), stream)
+            if M and SH_FACTOR_MODE and FACTOR_HOOK is not None:
+                failure = []
+
+                def _stage(_ctx, _stage_id):
+                    try:
+                        FACTOR_HOOK(dL_dcolors)
+                    except BaseException as e:  # never unwind through the C frame
+                        failure.append(e)
+
+                cb = _lib.STAGE_HOOK(_stage)
+                check(lib.sgr_rasterize_backward_staged(*args, cb, None))
+                if failure:
+                    raise failure[0]
+            else:
+                check(lib.sgr_rasterize_backward(*args))
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 

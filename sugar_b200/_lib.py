@@ -40,6 +40,7 @@ class SgrFieldParams(C.Structure):
 
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+STAGE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32)
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 PROTOTYPES = {
@@ -48,6 +49,8 @@ PROTOTYPES = {
                                         C.POINTER(C.c_int64), C.c_void_p]),
     "sgr_rasterize_backward": (C.c_int, [C.POINTER(SgrView), C.POINTER(SgrGaussians)] + [C.c_void_p] * 4 +
                                [C.c_int64] + [C.c_void_p] * 11),
+    "sgr_rasterize_backward_staged": (C.c_int, [C.POINTER(SgrView), C.POINTER(SgrGaussians)] + [C.c_void_p] * 4 +
+                                      [C.c_int64] + [C.c_void_p] * 11 + [STAGE_HOOK, C.c_void_p]),
     "sgr_mark_visible": (C.c_int, [C.c_int32] + [C.c_void_p] * 5),
     "sgr_sh_grad_from_factors": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "sgr_geometry_bytes": (C.c_size_t, [C.c_int32]),

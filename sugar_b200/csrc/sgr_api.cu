@@ -271,11 +271,11 @@ int sgr_rasterize_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc g
                           radii, capacity_hint, num_rendered, st);
 }
 
-int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
+int sgr_rasterize_backward_staged(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
                            const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
                            const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
                            float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales,
-                           float *dL_drotations, void *grad_scratch, void *stream)
+                           float *dL_drotations, void *grad_scratch, void *stream, SgrStageHook hook, void *hook_ctx)
 {
     int rc = validate(view, g, false);
     if (rc) return rc;
@@ -287,7 +287,18 @@ int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int
     }
     return launch_backward(view, g, radii, geom_buffer, binning_buffer, image_buffer, num_rendered, dL_dout_color,
                            dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
-                           dL_drotations, grad_scratch, (cudaStream_t)stream);
+                           dL_drotations, grad_scratch, (cudaStream_t)stream, hook, hook_ctx);
+}
+
+int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
+                           const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
+                           const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
+                           float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales,
+                           float *dL_drotations, void *grad_scratch, void *stream)
+{
+    return sgr_rasterize_backward_staged(view, g, radii, geom_buffer, binning_buffer, image_buffer, num_rendered,
+                                         dL_dout_color, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D,
+                                         dL_dsh, dL_dscales, dL_drotations, grad_scratch, stream, nullptr, nullptr);
 }
 
 int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,

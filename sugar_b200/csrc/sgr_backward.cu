@@ -243,6 +243,7 @@ struct PreBwdArgs {
     const float *gacc;
     float *dmeans2D, *dcolors, *dopacity, *dmeans3D, *dcov3D, *dsh, *dscales, *drots;
     int bulk_ok, sh_stride, sh_vec;
+    int skip_dcolors;  // dL_dcolors was already produced by sh_factor_kernel
 };
 
 #define SH_C0 0.28209479177387814f
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
     __syncthreads();
     // ---- coalesced write-out -------------------------------------------------------------------
     pb_flush(a.dmeans2D + (size_t)base * 3, sm + PB_O_M2D, n * 3);
-    pb_flush(a.dcolors + (size_t)base * 3, sm + PB_O_COL, n * 3);
+    if (!a.skip_dcolors) pb_flush(a.dcolors + (size_t)base * 3, sm + PB_O_COL, n * 3);
     pb_flush(a.dopacity + base, sm + PB_O_OPA, n);
     pb_flush(a.dmeans3D + (size_t)base * 3, sm + PB_O_M3D, n * 3);
     pb_flush(a.dcov3D + (size_t)base * 6, sm + PB_O_COV, n * 6);
@@ -701,11 +702,25 @@ __global__ void __launch_bounds__(SF_T) sh_grad_from_factors_kernel(int P, int M
     }
 }
 
+// Factor mode, staged: the clamp-masked dL/dRGB straight from the blend accumulators, so that the
+// caller can start exchanging it (hook) while preprocess_backward is still running.
+__global__ void __launch_bounds__(256) sh_factor_kernel(int P, const int32_t *__restrict__ radii,
+                                                        const uint32_t *__restrict__ aux, const float *__restrict__ gacc,
+                                                        float *__restrict__ dcolors)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= 3 * P) return;
+    const int i = k / 3, c = k - 3 * i;
+    float v = 0.f;
+    if (radii[i] > 0 && !((aux[i] >> c) & 1u)) v = gacc[(size_t)i * 12 + 6 + c];
+    dcolors[k] = v;
+}
+
 int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
                     const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
                     const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
                     float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
-                    void *grad_scratch, cudaStream_t st)
+                    void *grad_scratch, cudaStream_t st, SgrStageHook hook, void *hook_ctx)
 {
     const int P = g->P, W = view->image_width, H = view->image_height;
     const int gx = (W + SGR_TILE - 1) / SGR_TILE, gy = (H + SGR_TILE - 1) / SGR_TILE;
@@ -720,8 +735,14 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
                        img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T, img.n_contrib,
                        dL_dout_color, gacc));
     }
+    const bool staged_factors = hook && g->shs && !dL_dsh;
+    if (staged_factors) {
+        SGR_LAUNCH(K_MISC, st, sh_factor_kernel<<<(3 * P + 255) / 256, 256, 0, st>>>(P, radii, geom.aux, gacc, dL_dcolors));
+        hook(hook_ctx, SGR_STAGE_SH_FACTORS_READY);
+    }
     PreBwdArgs a;
     a.P = P;
+    a.skip_dcolors = staged_factors ? 1 : 0;
     a.means = g->means3D;
     a.scales = g->scales;
     a.rots = g->rotations;

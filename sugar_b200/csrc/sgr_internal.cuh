@@ -371,6 +371,6 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
                     const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
                     const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
                     float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
-                    void *grad_scratch, cudaStream_t stream);
+                    void *grad_scratch, cudaStream_t stream, SgrStageHook hook, void *hook_ctx);
 
 }  // namespace sgr

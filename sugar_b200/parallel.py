@@ -4,7 +4,7 @@ NVLink 5 / NVSwitch (the reference is strictly 1 view / 1 
 sugar_trainers/coarse_sdf.py:98,507, so this is new behaviour: loss = mean over the batch's views).
 
 The path has no other exchange step.  The flat arena
-    [ points 3 | opacity 1 | sh 3M | scales 3 | quaternions 4 ]  x P   fp32
+    [ points 3 | opacity 1 | scales 3 | quaternions 4 | sh 3M ]  x P   fp32
 is reduced in place by `torch.distributed.all_reduce` (backend "nccl", or "gloo" in CPU tests).
 
 SH factor mode (`sh_factor_mode()`): 3M of the 11+3M floats per Gaussian are dL_dsh, and each view's
@@ -23,7 +23,7 @@ from typing import Dict
 import torch
 import torch.distributed as dist
 
-ARENA_FIELDS = ("means3D", "opacities", "shs", "scales", "rotations")  # = layout of the backward's flat buffer
+ARENA_FIELDS = ("means3D", "opacities", "scales", "rotations", "shs")  # = layout of the backward's flat buffer
 
 
 def shard_views(num_views: int, rank: int, world: int):
@@ -36,12 +36,33 @@ def sh_factor_mode(enabled: bool = True):
     """Within this context sugar_b200's rasterizer backward emits SH factors instead of dL_dsh; the
     gradients must then go through `GradArena.all_reduce_from(..., campos=, sh_degree=)`."""
     from . import _C
-    old = _C.SH_FACTOR_MODE
-    _C.SH_FACTOR_MODE = bool(enabled)
+    old = (_C.SH_FACTOR_MODE, _C.FACTOR_HOOK)
+    set_sh_factor_mode(enabled)
     try:
         yield
     finally:
-        _C.SH_FACTOR_MODE = old
+        _C.SH_FACTOR_MODE, _C.FACTOR_HOOK = old
+        _early_gather.clear()
+
+
+_early_gather = {}  # data_ptr of the factor tensor -> (gathered [world,P,3], work handle)
+
+
+def _start_gather(dRGB: torch.Tensor) -> None:
+    """Stage hook of the backward: the factors are final on the current stream, the per-Gaussian
+    backward is not enqueued yet -> the all-gather runs on NCCL's stream underneath it."""
+    world = dist.get_world_size()
+    d_all = torch.empty((world,) + tuple(dRGB.shape), dtype=dRGB.dtype, device=dRGB.device)
+    _early_gather.clear()
+    _early_gather[dRGB.data_ptr()] = (d_all, dist.all_gather_into_tensor(d_all, dRGB, async_op=True))
+
+
+def set_sh_factor_mode(enabled: bool = True) -> None:
+    """Process-wide switch behind `sh_factor_mode()` (for loops that do not want a context manager)."""
+    from . import _C
+    _C.SH_FACTOR_MODE = bool(enabled)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    _C.FACTOR_HOOK = _start_gather if (enabled and multi) else None
 
 
 def gather_factors(dRGB: torch.Tensor, campos: torch.Tensor):
@@ -117,28 +138,48 @@ class GradArena:
         return self._base[:self.flat.numel()]
 
     def _all_reduce_factored(self, params, buf, campos, sh_degree):
-        """SH factor mode: all-reduce everything but the sh slot, all-gather the factors, rebuild dL_dsh."""
+        """SH factor mode: all-reduce everything but the sh slot, all-gather the factors, rebuild dL_dsh.
+        The collectives are issued asynchronously (factors first) so that the rebuild kernel overlaps
+        the all-reduce of the other fields."""
         P = self.P
         o_sh, n_sh = self.offsets["shs"]
         M = n_sh // (3 * P)
         # dL_dcolors sits behind [arena | dL_dmeans2D 3P] in the backward's buffer (sugar_b200/_C.py)
         o_col = self.flat.numel() + 3 * P
         dRGB = self._base[o_col:o_col + 3 * P]
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if multi:
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        pending = []
+        if world > 1:
+            early = _early_gather.pop(dRGB.data_ptr(), None)  # started by the backward's stage hook?
+            if early is not None:
+                d_all, hg = early[0].view(world, P, 3), [early[1]]
+            else:
+                d_all = torch.empty((world, P, 3), dtype=torch.float32, device=buf.device)
+                hg = [dist.all_gather_into_tensor(d_all, dRGB, async_op=True)]
+            if campos.dim() == 1:  # this rank's camera only: gather the others'
+                c_all = torch.empty((world, 3), dtype=torch.float32, device=buf.device)
+                hg.append(dist.all_gather_into_tensor(c_all, campos.reshape(3).contiguous(), async_op=True))
+            else:                  # [world,3]: the caller already knows every rank's camera
+                c_all = campos.contiguous()
             # fields before / after the sh slot are contiguous runs of the arena
             if o_sh > 0:
-                dist.all_reduce(buf[:o_sh], op=dist.ReduceOp.SUM)
+                pending.append(dist.all_reduce(buf[:o_sh], op=dist.ReduceOp.SUM, async_op=True))
             if o_sh + n_sh < buf.numel():
-                dist.all_reduce(buf[o_sh + n_sh:], op=dist.ReduceOp.SUM)
-        d_all, c_all = gather_factors(dRGB, campos)
+                pending.append(dist.all_reduce(buf[o_sh + n_sh:], op=dist.ReduceOp.SUM, async_op=True))
+            for h in hg:
+                h.wait()
+        else:
+            d_all, c_all = dRGB.view(1, P, 3), campos.reshape(-1, 3)[:1].contiguous()
         sh_grad_from_factors(params["means3D"].detach(), c_all, d_all, M, sh_degree, out=buf[o_sh:o_sh + n_sh])
+        for h in pending:
+            h.wait()
 
     def all_reduce_from(self, params: Dict[str, torch.Tensor], scale: float = 1.0, campos: torch.Tensor = None,
                         sh_degree: int = None) -> torch.Tensor:
         """Sum the ranks' local gradients over the process group (in place when possible) and scale
         by 1/num_views.  Returns the reduced flat arena.  Under `sh_factor_mode()` pass this rank's
-        camera position and the active SH degree."""
+        camera position ([3]; or all ranks' positions [world,3], saving a tiny all-gather) and the active
+        SH degree."""
         from . import _C
         buf = self._shared_base(params)
         if _C.SH_FACTOR_MODE and "shs" in self.offsets and self.offsets["shs"][1] > 0:

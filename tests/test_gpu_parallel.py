@@ -57,3 +57,42 @@ def test_sh_factors_match_summed_dsh(deg):
     used = (deg + 1) ** 2
     if used < 16:
         assert float(got[:, used:].abs().max()) == 0.0
+
+
+def test_staged_backward_hook_sees_final_factors():
+    """sgr_rasterize_backward_staged: at hook time the factors enqueued so far are already the final
+    masked dL/dRGB, and the remaining gradients equal the unstaged factor-mode backward."""
+    import torch
+    from sugar_b200 import _C, parallel, scenes
+    from sugar_b200 import diff_gaussian_rasterization as mod
+    P, W, H, deg = 5000, 160, 96, 3
+    sc = scenes.make_scene(P, W, H, seed=77, camera="posed")
+    dL = torch.from_numpy(scenes.upstream_grad(W, H, seed=9)).cuda()
+    t = h.to_torch(sc)
+
+    def run(hook):
+        ps = {k: t[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+        means2D = torch.zeros_like(ps["means3D"], requires_grad=True)
+        st = mod.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy, bg=torch.zeros(3, device="cuda"),
+            scale_modifier=1.0, viewmatrix=t["viewmatrix"], projmatrix=t["projmatrix"], sh_degree=deg,
+            campos=t["campos"], prefiltered=False, debug=False)
+        with parallel.sh_factor_mode():
+            _C.FACTOR_HOOK = hook
+            color, _ = mod.GaussianRasterizer(st)(means3D=ps["means3D"], means2D=means2D, opacities=ps["opacities"],
+                                                  shs=ps["shs"], scales=ps["scales"], rotations=ps["rotations"])
+            (color * dL).sum().backward()
+            arena = parallel.GradArena(P, 16, "cuda")
+            assert arena._shared_base(ps) is not None
+            o_col = arena.flat.numel() + 3 * P
+            final = arena._base[o_col:o_col + 3 * P].clone().view(P, 3)
+        return ps, final
+
+    seen = []
+    ps_a, fin_a = run(lambda d: seen.append(d.clone()))   # clone is stream-ordered: snapshot at hook time
+    ps_b, fin_b = run(None)
+    assert len(seen) == 1 and seen[0].shape == (P, 3)
+    assert torch.equal(seen[0], fin_a)
+    assert _err(fin_a, fin_b) <= 1e-4 and float(fin_a.abs().max()) > 0
+    for k in ("means3D", "opacities", "scales", "rotations"):
+        assert _err(ps_a[k].grad, ps_b[k].grad) <= 1e-4, k

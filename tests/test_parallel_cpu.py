@@ -35,7 +35,10 @@ def test_arena_allreduce_gloo_world2():
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:  # a free port for the rendezvous
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -58,7 +61,7 @@ def test_arena_reduces_backward_buffer_in_place():
     import torch
     from sugar_b200 import parallel
     P, M = 10, 2
-    widths = (3, 1, 3 * M, 3, 4, 3, 3, 6)
+    widths = (3, 1, 3, 4, 3 * M, 3, 3, 6)
 
     class Fn(torch.autograd.Function):
         @staticmethod
@@ -72,8 +75,8 @@ def test_arena_reduces_backward_buffer_in_place():
             for k in widths[:5]:
                 outs.append(flat[o:o + P * k])
                 o += P * k
-            return (outs[0].view(P, 3), outs[1].view(P, 1), outs[2].view(P, M, 3), outs[3].view(P, 3),
-                    outs[4].view(P, 4))
+            return (outs[0].view(P, 3), outs[1].view(P, 1), outs[4].view(P, M, 3), outs[2].view(P, 3),
+                    outs[3].view(P, 4))
 
     ps = dict(means3D=torch.zeros(P, 3), opacities=torch.zeros(P, 1), shs=torch.zeros(P, M, 3),
               scales=torch.zeros(P, 3), rotations=torch.zeros(P, 4))
