@@ -97,6 +97,20 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     knn_ms = e0.elapsed_time(e1) / 5
+    # "better normal" loss (coarse_sdf.py:688-716): fused kernels vs the reference's op chain on the same GPU
+    with torch.no_grad():
+        opac = field.field_values(x, nbr, points, scaling, quats, strengths, density_factor=1.0 / K,
+                                  return_closest_gaussian_opacities=True)["closest_gaussian_opacities"]
+    ql = quats.clone().requires_grad_(True)
+
+    def normal_ours():
+        field.better_normal_loss(x, gi, nbr, points, scaling, ql, opac).mean().backward()
+        ql.grad = None
+
+    def normal_ref():
+        fo.better_normal_loss_torch(x, gi, nbr, points, scaling, ql, opac).mean().backward()
+        ql.grad = None
+    nl_ms, nl_ref_ms = timeit(normal_ours, a.steps), timeit(normal_ref, max(3, a.steps // 4))
     fwd_bytes = N * (12 + 8 * K + 48 * K)
     stages = {k: {"ms": round(v[0] / v[1], 4)} for k, v in prof.items()}
     if "field_forward" in stages:
@@ -109,6 +123,7 @@ def main():
                          "sample": f"{ns} samples of the workload, PyTorch op chain of sugar_model.py:1247-1316"},
         "knn_reset_neighbors": {"ms": knn_ms, "points_per_s": P / (knn_ms * 1e-3), "K": K,
                                 "note": "exact K-NN of the cloud against itself (uniform grid), replaces pytorch3d.knn_points"},
+        "better_normal_loss": {"ms_fwd_bwd": nl_ms, "torch_same_gpu_ms": nl_ref_ms, "samples_per_s": N / (nl_ms * 1e-3)},
         "stages": stages}))
 
 

@@ -189,6 +189,28 @@ SGR_API int sgr_field_backward(const SgrFieldParams *p, const float *x, const in
                        float *g_strengths, void *scratch, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * "Better normal" regularisation of the trainers (sugar_trainers/coarse_sdf.py:688-716, with
+ * SuGaR.get_normals(estimate_from_points=False) -> get_smallest_axis, sugar_model.py:930-968), in the
+ * trainers' only mode sdf_better_normal_gradient_through_normal_only=True (weights and signs detached):
+ *   n_g = column argmin_j scaling[g][j] of R(quaternions[g]);  m_k = sign(<n_k, n_own>) n_k
+ *   w_k = nbr_opacity[n,k] |<x_n - mu_k, m_k>| / max(min_j scaling[k][j], 1e-6)^2, / max(sum_k w_k, 1e-6)
+ *   loss[n] = | n_own - sum_k w_k m_k |^2
+ * Inputs: x f32[N,3], own_idx i64[N] (sdf_gaussian_idx), nbr_idx i64[N,K] (knn_idx[own_idx]),
+ * points/scaling f32[P,3], quaternions f32[P,4], nbr_opacity f32[N,K] (fields['closest_gaussian_opacities']).
+ * Backward: g_loss f32[N] -> g_quaternions f32[P,4], fully written (the only differentiable input).
+ * `scratch` must hold sgr_normal_scratch_bytes(P).
+ * ------------------------------------------------------------------------------------------ */
+SGR_API size_t sgr_normal_scratch_bytes(int32_t P);
+SGR_API int sgr_normal_loss_forward(int32_t N, int32_t K, int32_t P, const float *x, const int64_t *own_idx,
+                                    const int64_t *nbr_idx, const float *points, const float *scaling,
+                                    const float *quaternions, const float *nbr_opacity, float *loss, void *scratch,
+                                    void *stream);
+SGR_API int sgr_normal_loss_backward(int32_t N, int32_t K, int32_t P, const float *x, const int64_t *own_idx,
+                                     const int64_t *nbr_idx, const float *points, const float *scaling,
+                                     const float *quaternions, const float *nbr_opacity, const float *g_loss,
+                                     float *g_quaternions, void *scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Exact K-nearest-neighbour search (uniform grid).  Replaces pytorch3d.ops.knn_points as SuGaR
  * calls it: reset_neighbors (sugar_model.py:1013-1030, queries == points, K = 16) and
  * get_gaussians_closest_to_samples (sugar_model.py:1335-1343).

@@ -6,6 +6,8 @@ Follows, op for op in PyTorch on the CPU:
     get_field_values                                                 sugar_scene/sugar_model.py:1247-1316
     compute_density                                                  sugar_scene/sugar_model.py:1345-1368
     sample_points_in_gaussians                                       sugar_scene/sugar_model.py:885-928
+    get_smallest_axis / get_normals(estimate_from_points=False)      sugar_scene/sugar_model.py:930-968
+    "better normal" loss (inline in the trainers)                    sugar_trainers/coarse_sdf.py:688-716
 Third-party arithmetic that is NOT under /root/reference (pytorch3d 0.7.4, environment.yml:161) is
 restated from its published algorithm: quaternion_to_matrix / quaternion_apply (real-first) and
 knn_points (exact K-NN on squared distances; restated with cdist + topk).
@@ -13,6 +15,8 @@ knn_points (exact K-NN on squared distances; restated with cdist + topk).
 Parity pinning: tests/golden/field_*.npz were produced by running the reference's OWN
 SuGaR.get_field_values code (imported from /root/reference with the missing third-party modules
 stubbed, tests/golden/make_field_golden.py); tests/test_field_oracle.py checks this file against them.
+tests/golden/normal_*.npz likewise: normals from the reference's SuGaR.get_normals, loss from the
+trainer's own source lines executed as they stand (tests/golden/make_normal_golden.py).
 """
 import numpy as np
 import torch
@@ -63,6 +67,28 @@ def field_values_torch(x, nbr_idx, points, scaling, quaternions, strengths, dens
     return out
 
 
+def smallest_axis(scaling, quaternions):
+    """get_smallest_axis (sugar_model.py:930-945): the column of R(q) along the smallest scale."""
+    rot = quaternion_to_matrix(quaternions)
+    col = scaling.min(dim=-1)[1][..., None, None].expand(-1, 3, -1)
+    return rot.gather(2, col).squeeze(dim=2)
+
+
+def better_normal_loss_torch(x, gaussian_idx, nbr_idx, points, scaling, quaternions, nbr_opacity):
+    """Per-sample "better normal" loss, coarse_sdf.py:688-716 with the trainers' only setting
+    sdf_better_normal_gradient_through_normal_only=True (coarse_sdf.py:144): weights and signs are
+    detached, gradients reach the quaternions through the normals only.  Returns [N]."""
+    normals = smallest_axis(scaling, quaternions)
+    min_scaling = scaling.min(dim=-1)[0][nbr_idx].detach().view(len(x), -1)                       # :693
+    c_normals = normals[nbr_idx]                                                                 # :696
+    s_normals = normals[gaussian_idx]                                                            # :697
+    c_normals = c_normals * torch.sign((c_normals * s_normals[:, None]).sum(dim=-1, keepdim=True)).detach()  # :698-700
+    w = ((x[:, None] - points[nbr_idx]) * c_normals).sum(dim=-1).abs().detach()                  # :704-706
+    w = nbr_opacity.detach() * w / min_scaling.clamp(min=1e-6) ** 2                              # :707
+    w = w / w.sum(dim=-1).detach().unsqueeze(-1).clamp(min=1e-6)                                 # :710-711
+    return (s_normals - (w[..., None] * c_normals).sum(dim=-2)).pow(2).sum(dim=-1)               # :714-715
+
+
 def field_values(x, nbr_idx, points, scaling, quaternions, strengths, density_factor=1.0, density_threshold=1.0,
                  opacity_min_clamp=1e-16, **_):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
@@ -85,5 +111,5 @@ def make_case(P=1000, N=2000, K=16, seed=0, density_factor=1.0 / 16.0, density_t
     gi = torch.multinomial(areas / areas.sum(), N, replacement=True, generator=g)
     x = points[gi] + quaternion_apply(q[gi], 1.5 * scaling[gi] * torch.randn(N, 3, generator=g))
     f = lambda a: np.ascontiguousarray(a.numpy())
-    return dict(x=f(x.float()), nbr_idx=f(nn_idx[gi]), points=f(points), scaling=f(scaling), quaternions=f(q),
+    return dict(x=f(x.float()), nbr_idx=f(nn_idx[gi]), gaussian_idx=f(gi), points=f(points), scaling=f(scaling), quaternions=f(q),
                 strengths=f(strengths), density_factor=density_factor, density_threshold=density_threshold)

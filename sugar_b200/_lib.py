@@ -59,6 +59,9 @@ PROTOTYPES = {
     "sgr_backward_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_inspect_state": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 15),
     "sgr_field_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "sgr_normal_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "sgr_normal_loss_forward": (C.c_int, [C.c_int32] * 3 + [C.c_void_p] * 10),
+    "sgr_normal_loss_backward": (C.c_int, [C.c_int32] * 3 + [C.c_void_p] * 11),
     "sgr_field_forward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 12),
     "sgr_field_backward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 17),
     "sgr_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),

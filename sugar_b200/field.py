@@ -83,6 +83,58 @@ class _Field(torch.autograd.Function):
         return g_x, None, g_points, g_scaling, g_quat, g_str.view(s_shape), None, None, None
 
 
+class _NormalLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gaussian_idx, nbr_idx, points, scaling, quaternions, nbr_opacity):
+        if not x.is_cuda:
+            raise RuntimeError("sugar_b200.field needs CUDA tensors: there is no CPU fallback")
+        x, points, scaling, quaternions, nbr_opacity = (t.detach().contiguous().float()
+                                                        for t in (x, points, scaling, quaternions, nbr_opacity))
+        gaussian_idx, nbr_idx = gaussian_idx.contiguous().long(), nbr_idx.contiguous().long()
+        N, K, P = x.shape[0], nbr_idx.shape[1], points.shape[0]
+        dev = x.device
+        with torch.cuda.device(dev):
+            loss = torch.empty(N, device=dev)
+            scratch = torch.empty(lib.sgr_normal_scratch_bytes(P), dtype=torch.uint8, device=dev)
+            check(lib.sgr_normal_loss_forward(N, K, P, _ptr(x), _ptr(gaussian_idx), _ptr(nbr_idx), _ptr(points),
+                                              _ptr(scaling), _ptr(quaternions), _ptr(nbr_opacity), _ptr(loss),
+                                              _ptr(scratch), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(x, gaussian_idx, nbr_idx, points, scaling, quaternions, nbr_opacity)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        x, gaussian_idx, nbr_idx, points, scaling, quaternions, nbr_opacity = ctx.saved_tensors
+        N, K, P = x.shape[0], nbr_idx.shape[1], points.shape[0]
+        dev = x.device
+        with torch.cuda.device(dev):
+            g_quat = torch.empty_like(quaternions)
+            scratch = torch.empty(lib.sgr_normal_scratch_bytes(P), dtype=torch.uint8, device=dev)
+            check(lib.sgr_normal_loss_backward(N, K, P, _ptr(x), _ptr(gaussian_idx), _ptr(nbr_idx), _ptr(points),
+                                               _ptr(scaling), _ptr(quaternions), _ptr(nbr_opacity),
+                                               _ptr(g_loss.contiguous().float()), _ptr(g_quat), _ptr(scratch),
+                                               torch.cuda.current_stream(dev).cuda_stream))
+        return None, None, None, None, None, g_quat, None
+
+
+def better_normal_loss(x, gaussian_idx, closest_gaussians_idx, points, scaling, quaternions,
+                       closest_gaussian_opacities, gradient_through_normal_only=True):
+    """Per-sample "better normal" loss of the trainers (sugar_trainers/coarse_sdf.py:688-716): returns
+    `sdf_better_normal_loss` [N]; the caller adds `factor * loss.mean()` (coarse_sdf.py:716).
+
+    x = sdf_samples, gaussian_idx = sdf_gaussian_idx, closest_gaussians_idx = knn_idx[gaussian_idx],
+    closest_gaussian_opacities = fields['closest_gaussian_opacities'] (detached by the reference, :703).
+    Normals are SuGaR.get_normals(estimate_from_points=False) of an unbound model, i.e. the smallest
+    axis of each Gaussian (sugar_model.py:930-968).  Only the trainers' setting
+    sdf_better_normal_gradient_through_normal_only=True (coarse_sdf.py:144) is implemented: gradients
+    flow to `quaternions` alone."""
+    if not gradient_through_normal_only:
+        raise NotImplementedError("only sdf_better_normal_gradient_through_normal_only=True (the reference "
+                                  "trainers' fixed setting, coarse_sdf.py:144) is implemented")
+    return _NormalLoss.apply(x, gaussian_idx, closest_gaussians_idx, points, scaling, quaternions,
+                             closest_gaussian_opacities)
+
+
 def field_values(x, closest_gaussians_idx, points, scaling, quaternions, strengths, density_factor=1.,
                  density_threshold=1., opacity_min_clamp=1e-16, return_sdf=True,
                  return_closest_gaussian_opacities=False, return_beta=False):

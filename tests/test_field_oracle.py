@@ -66,3 +66,19 @@ def test_sampling_matches_reference_semantics():
     gi = torch.multinomial(areas / areas.sum(), N, replacement=True, generator=g2)
     ref = points[gi] + fo.quaternion_apply(q[gi], 1.5 * scaling[gi] * torch.randn(N, 3, generator=g2))
     assert torch.equal(idx, gi) and torch.allclose(x, ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["c1_1k_2k", "k8"])
+def test_normal_loss_oracle_matches_reference_code(name):
+    """oracle better_normal_loss_torch vs the trainer's own lines (tests/golden/make_normal_golden.py)."""
+    cfg = CASES[name]
+    gold = np.load(os.path.join(HERE, "golden", f"normal_{name}.npz"))
+    case = fo.make_case(density_threshold=1.0, **cfg)
+    t = lambda k: torch.from_numpy(case[k])
+    q = t("quaternions").clone().requires_grad_(True)
+    assert np.allclose(fo.smallest_axis(t("scaling"), q).detach().numpy(), gold["normals"], rtol=1e-6, atol=1e-7)
+    loss = fo.better_normal_loss_torch(t("x"), t("gaussian_idx"), t("nbr_idx"), t("points"), t("scaling"), q,
+                                       torch.from_numpy(gold["nbr_opacity"]))
+    assert np.allclose(loss.detach().numpy(), gold["loss"], rtol=1e-5, atol=1e-7)
+    loss.mean().backward()
+    assert np.allclose(q.grad.numpy(), gold["grad_quaternions"], rtol=1e-5, atol=1e-8)

@@ -74,3 +74,48 @@ def test_compute_density_and_empty():
     assert h.rel_err(nb.cpu().numpy(), ref["closest_gaussian_opacities"]) < 2e-5
     e = field.field_values(t["x"][:0], t["nbr_idx"][:0], t["points"], t["scaling"], t["quaternions"], t["strengths"])
     assert e["density"].numel() == 0 and e["sdf"].numel() == 0
+
+
+def _normal_ours(case, opac, dev="cuda"):
+    from sugar_b200 import field
+    t = lambda k: torch.from_numpy(case[k]).to(dev)
+    q = t("quaternions").requires_grad_(True)
+    loss = field.better_normal_loss(t("x"), t("gaussian_idx"), t("nbr_idx"), t("points"), t("scaling"), q,
+                                    torch.from_numpy(opac).to(dev))
+    loss.mean().backward()
+    return loss.detach().cpu().numpy(), q.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["c1_1k_2k", "k8"])
+def test_normal_loss_matches_reference_golden(name):
+    """fused better-normal loss vs the trainer's own source lines (tests/golden/make_normal_golden.py)."""
+    from make_field_golden import CASES
+    from oracle import field_oracle as fo
+    gold = np.load(os.path.join(HERE, "golden", f"normal_{name}.npz"))
+    case = fo.make_case(density_threshold=1.0, **CASES[name])
+    loss, gq = _normal_ours(case, gold["nbr_opacity"])
+    assert h.rel_err(loss, gold["loss"]) < 2e-5
+    assert h.rel_err(gq, gold["grad_quaternions"]) < 1e-4
+
+
+@pytest.mark.parametrize("P,N,K", [(5000, 20000, 16), (3000, 7001, 5), (2000, 4000, 32)])
+def test_normal_loss_matches_oracle(P, N, K):
+    from oracle import field_oracle as fo
+    case = fo.make_case(P=P, N=N, K=K, seed=P % 89, density_factor=1.0 / K)
+    opac = fo.field_values(**case)["closest_gaussian_opacities"]
+    loss, gq = _normal_ours(case, opac)
+    t = lambda k: torch.from_numpy(case[k])
+
+    def oracle(dt):
+        c = lambda k: t(k).to(dt)
+        q = c("quaternions").clone().requires_grad_(True)
+        ref = fo.better_normal_loss_torch(c("x"), t("gaussian_idx"), t("nbr_idx"), c("points"), c("scaling"), q,
+                                          torch.from_numpy(opac).to(dt))
+        ref.mean().backward()
+        return ref.detach().numpy(), q.grad.numpy()
+    l32, g32 = oracle(torch.float32)
+    l64, g64 = oracle(torch.float64)
+    # <x - mu, n> cancels for samples close to their Gaussian's plane: the fp32 op chain of the
+    # reference itself is only this close to the exact value, so allow 3x its own rounding noise
+    assert h.rel_err(loss, l64) < max(2e-5, 3 * h.rel_err(l32, l64))
+    assert h.rel_err(gq, g64) < max(1e-4, 3 * h.rel_err(g32, g64))
