@@ -21,8 +21,9 @@ KEEP = [
     "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
 ]
 STAGE = {"preprocess_kernel": "preprocess", "tile_scan_kernel": "tile_scan", "scatter_kernel": "scatter",
-         "tile_sort_merge_kernel": "tile_sort_smem", "tile_sort_kernel": "tile_sort_global",
-         "blend_forward_kernel": "blend_forward", "blend_backward_kernel": "blend_backward",
+         "tile_sort_merge_kernel": "tile_sort_smem", "tile_sort_bucket_kernel": "tile_sort_smem",
+         "tile_sort_kernel": "tile_sort_global", "blend_forward_kernel": "blend_forward",
+         "blend_backward_kernel": "blend_backward", "blend_backward_chunked_kernel": "blend_backward",
          "preprocess_backward_kernel": "preprocess_backward"}
 MULT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 

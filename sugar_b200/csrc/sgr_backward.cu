@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
         dp2 = dL_dpixels[2 * plane + pix];
     }
     const float bg_dot = fmaf(bg[2], dp2, fmaf(bg[1], dp1, bg[0] * dp0));
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     // Splats behind the deepest last contributor of the warp (of the tile) cannot touch any of its
     // pixels: the tile only walks list positions [0, tile_last), each warp only [0, warp_last).
@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
         __syncthreads();
         const int m = min(BWD_B, n - b0);
         const int jmin = n - b0 - warp_last;  // first batch slot whose list position is < warp_last
+        // list position of slot j is n-1-(b0+j); it precedes this pixel's last contributor iff j > jlim
+        const int jlim = n - 1 - b0 - last_contributor;
 #pragma unroll 1
         for (int c = 0; c * 32 < m; c++) {
             uint32_t touched = 0;
@@ -140,61 +142,60 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
             else if (cut > 0) mw &= ~((1u << cut) - 1u);
 #pragma unroll 1
             while (mw) {
-                const int jj = __ffs(mw) - 1;
-                mw &= mw - 1;
-                const int j = c * 32 + jj;
-                const int pos = n - 1 - (b0 + j);  // position in the front-to-back list
+                const uint32_t lowbit = mw & (0u - mw);
+                const int j = c * 32 + (__ffs(mw) - 1);
+                mw ^= lowbit;
                 const float4 A = lds128(sa + j * 16);
                 const float4 B = lds128(sb + j * 16);
                 const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                 const float power = splat_power(dx, dy, A.z, A.w, B.x);
-                bool valid = pos < last_contributor && !(power > 0.0f) && !(power < B.y);
+                bool valid = j > jlim && !(power > 0.0f) && !(power < B.y);
                 if (!__any_sync(0xffffffffu, valid)) continue;
-                // v[0..5] moments of S = dL/dG * G, v[6..7] + v8 colour gradients
-                float v[8], v8 = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = 0.f;
+                // S = dL/dG * G and the colour weight alpha*T of this pair; zero for lanes without one
+                float S = 0.f, dchannel = 0.f;
                 if (valid) {
                     const float G = expf(power);
                     const float alpha = fminf(0.99f, __fmul_rn(B.z, G));
                     valid = !(alpha < 1.0f / 255.0f);
                     if (valid) {
                         const float2 Cc = lds64(sc + j * 8);
-                        const float inv = __fdividef(1.0f, 1.0f - alpha);  // 1-alpha in [0.01, 1): MUFU.RCP suffices
+                        const float om = 1.0f - alpha;  // in [0.01, 1): a bare MUFU.RCP suffices
+                        float inv;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(om));
                         T = T * inv;
-                        const float dchannel = alpha * T;
-                        const float la = last_alpha, om_la = 1.0f - last_alpha;
-                        acc0 = fmaf(la, lc0, om_la * acc0);
-                        acc1 = fmaf(la, lc1, om_la * acc1);
-                        acc2 = fmaf(la, lc2, om_la * acc2);
-                        lc0 = B.w;
-                        lc1 = Cc.x;
-                        lc2 = Cc.y;
-                        float dL_dalpha = (lc0 - acc0) * dp0;
-                        dL_dalpha = fmaf(lc1 - acc1, dp1, dL_dalpha);
-                        dL_dalpha = fmaf(lc2 - acc2, dp2, dL_dalpha);
+                        dchannel = alpha * T;
+                        // acc holds the colour blended behind this splat (backward.cu:493-499 keeps
+                        // last_alpha / last_color and folds them in one iteration later; same
+                        // operations on the same values, evaluated eagerly below)
+                        float dL_dalpha = (B.w - acc0) * dp0;
+                        dL_dalpha = fmaf(Cc.x - acc1, dp1, dL_dalpha);
+                        dL_dalpha = fmaf(Cc.y - acc2, dp2, dL_dalpha);
                         dL_dalpha *= T;
-                        last_alpha = alpha;
                         dL_dalpha = fmaf(-T_final * inv, bg_dot, dL_dalpha);
-                        const float S = B.z * dL_dalpha * G;
-                        const float Sx = S * dx, Sy = S * dy;
-                        v[0] = S;
-                        v[1] = Sx;
-                        v[2] = Sy;
-                        v[3] = Sx * dx;
-                        v[4] = Sx * dy;
-                        v[5] = Sy * dy;
-                        v[6] = dchannel * dp0;
-                        v[7] = dchannel * dp1;
-                        v8 = dchannel * dp2;
+                        S = B.z * dL_dalpha * G;
+                        acc0 = fmaf(alpha, B.w, om * acc0);
+                        acc1 = fmaf(alpha, Cc.x, om * acc1);
+                        acc2 = fmaf(alpha, Cc.y, om * acc2);
                     }
                 }
                 if (!__any_sync(0xffffffffu, valid)) continue;
+                // v[0..5] moments of S, v[6..7] + v8 colour gradients
+                float v[8];
+                const float Sx = S * dx, Sy = S * dy;
+                v[0] = S;
+                v[1] = Sx;
+                v[2] = Sy;
+                v[3] = Sx * dx;
+                v[4] = Sx * dy;
+                v[5] = Sy * dy;
+                v[6] = dchannel * dp0;
+                v[7] = dchannel * dp1;
+                float v8 = dchannel * dp2;
                 const float r8 = warp_reduce8(v, lane);
                 v8 = warp_sum(v8);
                 if ((lane & 3u) == 0) s_acc[wid][j][lane >> 2] = r8;
                 if (lane == 1) s_acc[wid][j][8] = v8;
-                touched |= 1u << jj;
+                touched |= lowbit;
             }
             if (lane == 0) s_touched[wid][c] = touched;
         }
@@ -225,6 +226,245 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// blend backward, chunked reduction.  Same walk as blend_backward_kernel (strip membership, tail
+// skip, bit-identical recomputation of alpha / T), but
+//  * the 9 per-pair values are NOT reduced across the warp with shuffles.  Phase 1 (lane = pixel)
+//    parks S = dL/dG * G and the colour weight alpha*T of every contributing splat in a per-warp
+//    [pixel][slot] shared-memory tile; after CH splats the warp turns around (phase 2, lane = splat
+//    slot x strip row): each lane walks the 16 pixels of its row, rebuilds d = mean - pixel and
+//    accumulates the 6 moments + 3 colour sums of ITS splat in registers, the two rows are combined
+//    with one xor-16 shuffle per value and the result goes straight to the per-Gaussian
+//    accumulators with two red.v4 + one scalar reduction (chunks are 94 % full on the headline
+//    scene).  ~30 issued instructions per contributing (strip, splat) instead of ~67 for the
+//    butterfly; the per-warp partial-sum rows, touched masks and the per-batch fold disappear;
+//  * splat records are double-buffered: the ids of batch b+2 and the cp.async (LDGSTS) copies of
+//    batch b+1 are in flight while batch b is processed, so the CTA-wide barriers at the batch
+//    boundary no longer expose the plist -> record load chain (20 % of the stall samples before).
+// ------------------------------------------------------------------------------------------------
+constexpr int CH = 16;             // splats per chunk
+constexpr int CH_PITCH = CH + 1;   // float2 elements per pixel row: odd pitch = conflict-free transpose
+// per-warp chunk scratch (bytes from its base): pair[32][CH_PITCH] float2 | meta[CH] x 48 B | dp[32] float4
+//   meta: (x, y, conic a, conic b) (conic c, tau, opacity, r) (id, -, -, -)
+//   dp:   (dL/dpixel r g b, -T_final <bg, dL/dpixel>) of the strip's pixels
+constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 48, CB_BYTES = CB_DP + 32 * 16;
+// CTA shared-memory map (dynamic): records of two batches, membership words, chunk scratch
+constexpr uint32_t SM_A = 0, SM_B = SM_A + 2 * BWD_B * 16, SM_C = SM_B + 2 * BWD_B * 16, SM_ID = SM_C + 2 * BWD_B * 8,
+                   SM_MEMBER = SM_ID + 2 * BWD_B * 4, SM_LAST = SM_MEMBER + BWD_NW * (BWD_B / 32) * 4,
+                   SM_CHUNK = SM_LAST + 16, BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
+
+// phase 2: reduce the parked chunk (nf splats) over the strip's pixels and add it to the Gaussians'
+// accumulators.  Lane = (chunk slot, strip row).
+__device__ __forceinline__ void chunk_flush(uint32_t cb, int nf, float ddelx_dx, float ddely_dy, float *__restrict__ gacc)
+{
+    // blockDim.x == 16: lane = (threadIdx.y & 1) * 16 + threadIdx.x
+    const int slot = (int)(threadIdx.x & (CH - 1)), row = (int)(threadIdx.y & 1u);
+    const float tx0 = (float)(blockIdx.x * SGR_TILE), row_y = (float)(blockIdx.y * SGR_TILE + threadIdx.y);
+    __syncwarp();
+    const float4 M0 = lds128(cb + CB_META + slot * 48), M1 = lds128(cb + CB_META + slot * 48 + 16);
+    const uint32_t id = lds32(cb + CB_META + slot * 48 + 32);
+    const float dy = __fsub_rn(M0.y, row_y);
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    const uint32_t pa = cb + (row * 16 * CH_PITCH + slot) * 8, da = cb + CB_DP + row * 16 * 16;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float2 pr = lds64(pa + i * CH_PITCH * 8);
+        const float4 d = lds128(da + i * 16);
+        const float dx = __fsub_rn(M0.x, tx0 + (float)i);
+        const float Sx = pr.x * dx, Sy = pr.x * dy;
+        m0 += pr.x;
+        m1 += Sx;
+        m2 += Sy;
+        m3 = fmaf(Sx, dx, m3);
+        m4 = fmaf(Sx, dy, m4);
+        m5 = fmaf(Sy, dy, m5);
+        c0 = fmaf(pr.y, d.x, c0);
+        c1 = fmaf(pr.y, d.y, c1);
+        c2 = fmaf(pr.y, d.z, c2);
+    }
+    m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
+    m1 += __shfl_xor_sync(0xffffffffu, m1, 16);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 16);
+    m3 += __shfl_xor_sync(0xffffffffu, m3, 16);
+    m4 += __shfl_xor_sync(0xffffffffu, m4, 16);
+    m5 += __shfl_xor_sync(0xffffffffu, m5, 16);
+    c0 += __shfl_xor_sync(0xffffffffu, c0, 16);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
+    if (slot < nf) {
+        // moments -> gradients (backward.cu:537-554): dG/ddel = -G (Q d)
+        float *g = gacc + (size_t)id * 12;
+        if (row == 0) {
+            const float gmx = -(M0.z * m1 + M0.w * m2) * ddelx_dx;
+            const float gmy = -(M1.x * m2 + M0.w * m1) * ddely_dy;
+            red_add_v4(g, gmx, gmy, -0.5f * m3, -0.5f * m4);
+        } else {
+            red_add_v4(g + 4, -0.5f * m5, m0 / M1.z, c0, c1);
+            atomicAdd(g + 8, c2);
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
+    const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ plist, const float4 *__restrict__ rec, int W,
+    int H, int gx, const float *__restrict__ bg, const float *__restrict__ final_Ts,
+    const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dpixels, float *__restrict__ gacc)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int tid = threadIdx.y * SGR_TILE + threadIdx.x;
+    const unsigned lane = tid & 31, wid = tid >> 5;
+    const uint32_t pxi = blockIdx.x * SGR_TILE + threadIdx.x, pyi = blockIdx.y * SGR_TILE + threadIdx.y;
+    const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
+    const float tx0 = (float)(blockIdx.x * SGR_TILE), ty0 = (float)(blockIdx.y * SGR_TILE);
+    const uint32_t lo = tile_start[tile], hi = tile_start[tile + 1];
+    if (hi == lo) return;
+    const uint32_t sm = smem_addr_pinned(s_raw);
+    int *s_tile_last = (int *)(s_raw + SM_LAST);
+    uint32_t(*s_member)[BWD_B / 32] = (uint32_t(*)[BWD_B / 32])(s_raw + SM_MEMBER);
+    if (tid == 0) *s_tile_last = 0;
+
+    const size_t pix = (size_t)pyi * W + pxi, plane = (size_t)H * W;
+    float T = inside ? final_Ts[pix] : 0.0f;
+    const int last_contributor = inside ? (int)n_contrib[pix] : 0;
+    const uint32_t cb = sm + SM_CHUNK + wid * CB_BYTES;
+    {
+        float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+        if (inside) {
+            dp0 = dL_dpixels[pix];
+            dp1 = dL_dpixels[plane + pix];
+            dp2 = dL_dpixels[2 * plane + pix];
+        }
+        // (dL/dpixel, -T_final * <bg, dL/dpixel>) of this pixel: phase 2 reads the strip's table; the
+        // hit path of phase 1 reloads its own entry instead of pinning four registers across the loop
+        sts128(cb + CB_DP + lane * 16, dp0, dp1, dp2, -T * fmaf(bg[2], dp2, fmaf(bg[1], dp1, bg[0] * dp0)));
+    }
+    // the pixel centre, pinned: under register pressure nvcc otherwise re-derives pyf from
+    // S2R SR_TID.Y / SR_CTAID.Y inside the splat loop (long-latency special-register reads)
+    float pxf = (float)pxi, pyf = (float)pyi;
+    asm volatile("mov.f32 %0, %0;" : "+f"(pxf));
+    asm volatile("mov.f32 %0, %0;" : "+f"(pyf));
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    // Splats behind the deepest last contributor of the warp (of the tile) cannot touch any of its
+    // pixels: the tile only walks list positions [0, tile_last), each warp only [0, warp_last).
+    const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
+    __syncthreads();
+    if (lane == 0 && warp_last > 0) atomicMax(s_tile_last, warp_last);
+    __syncthreads();
+    const int n = *s_tile_last;
+    if (n == 0) return;
+    int nfill = 0;
+
+    // record pipeline (threads 0..BWD_B-1 own one slot of every batch): issue() starts the async
+    // copies of one splat record into buffer `buf`; ids are fetched one batch further ahead
+    const bool loader = tid < BWD_B;
+    auto fetch_id = [&](int b0) -> uint32_t {
+        return (loader && b0 + tid < n) ? plist[lo + (uint32_t)(n - 1 - (b0 + tid))] : 0xffffffffu;  // back to front
+    };
+    auto issue = [&](uint32_t id, int buf) {
+        if (id != 0xffffffffu) {
+            const float4 *r = rec + (size_t)id * 3;
+            const uint32_t e = buf * BWD_B + tid;
+            cp_async16_a(sm + SM_A + e * 16, r);
+            cp_async16_a(sm + SM_B + e * 16, r + 1);
+            cp_async8_a(sm + SM_C + e * 8, r + 2);
+            sts32(sm + SM_ID + e * 4, id);
+        }
+        cp_async_commit();
+    };
+    uint32_t id_cur = fetch_id(0);
+    issue(id_cur, 0);
+    uint32_t id_next = fetch_id(BWD_B);
+
+    for (int b0 = 0, buf = 0; b0 < n; b0 += BWD_B, buf ^= 1) {
+        cp_async_wait<0>();
+        __syncthreads();  // batch b0 has landed in `buf`; every warp is done with the other buffer
+        const uint32_t sa = sm + SM_A + buf * (BWD_B * 16), sb = sm + SM_B + buf * (BWD_B * 16),
+                       sc = sm + SM_C + buf * (BWD_B * 8), sid = sm + SM_ID + buf * (BWD_B * 4);
+        if (loader) {
+            uint32_t mask = 0;
+            if (id_cur != 0xffffffffu) {
+                const float4 r0 = lds128(sa + tid * 16), r1 = lds128(sb + tid * 16);
+                mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+            }
+#pragma unroll
+            for (int sidx = 0; sidx < BWD_NW; sidx++) {
+                const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
+                if (lane == 0) s_member[sidx][wid] = word;
+            }
+            // next batch's records start moving now; they are not needed before the next barrier
+            issue(id_next, buf ^ 1);
+            id_cur = id_next;
+            id_next = fetch_id(b0 + 2 * BWD_B);
+        }
+        __syncthreads();
+        const int m = min(BWD_B, n - b0);
+        const int jmin = n - b0 - warp_last;  // first batch slot whose list position is < warp_last
+        // list position of slot j is n-1-(b0+j); it precedes this pixel's last contributor iff j > jlim
+        const int jlim = n - 1 - b0 - last_contributor;
+#pragma unroll 1
+        for (int c = 0; c * 32 < m; c++) {
+            uint32_t mw = s_member[wid][c];
+            const int cut = jmin - c * 32;
+            if (cut >= 32) mw = 0;
+            else if (cut > 0) mw &= ~((1u << cut) - 1u);
+#pragma unroll 1
+            while (mw) {
+                const int j = c * 32 + (__ffs(mw) - 1);
+                mw &= mw - 1;
+                const float4 A = lds128(sa + j * 16);
+                const float4 B = lds128(sb + j * 16);
+                const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
+                const float power = splat_power(dx, dy, A.z, A.w, B.x);
+                bool valid = j > jlim && !(power > 0.0f) && !(power < B.y);
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                // S = dL/dG * G and the colour weight alpha*T of this pair; zero for lanes without one.
+                // (A candidate warp almost always keeps a contributing lane -- 8 554 776 of 8 554 918 on
+                // the headline scene -- so there is no second vote: an all-zero slot is harmless.)
+                float S = 0.f, dchannel = 0.f;
+                if (valid) {
+                    const float G = expf(power);
+                    const float alpha = fminf(0.99f, __fmul_rn(B.z, G));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float2 Cc = lds64(sc + j * 8);
+                        const float4 dp = lds128(cb + CB_DP + lane * 16);
+                        const float om = 1.0f - alpha;  // in [0.01, 1): a bare MUFU.RCP suffices
+                        float inv;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(om));
+                        T = T * inv;
+                        dchannel = alpha * T;
+                        // acc holds the colour blended behind this splat (backward.cu:493-499 keeps
+                        // last_alpha / last_color and folds them in one iteration later; same
+                        // operations on the same values, evaluated eagerly below)
+                        float dL_dalpha = (B.w - acc0) * dp.x;
+                        dL_dalpha = fmaf(Cc.x - acc1, dp.y, dL_dalpha);
+                        dL_dalpha = fmaf(Cc.y - acc2, dp.z, dL_dalpha);
+                        dL_dalpha *= T;
+                        dL_dalpha = fmaf(dp.w, inv, dL_dalpha);
+                        S = B.z * dL_dalpha * G;
+                        acc0 = fmaf(alpha, B.w, om * acc0);
+                        acc1 = fmaf(alpha, Cc.x, om * acc1);
+                        acc2 = fmaf(alpha, Cc.y, om * acc2);
+                    }
+                }
+                // park: every lane its pair; the record + id by all lanes alike (same address, same
+                // value: one wavefront, no branch)
+                sts64(cb + (lane * CH_PITCH + nfill) * 8, S, dchannel);
+                const uint32_t ma = cb + CB_META + nfill * 48;
+                sts128(ma, A.x, A.y, A.z, A.w);
+                sts128(ma + 16, B.x, B.y, B.z, B.w);
+                sts32(ma + 32, lds32(sid + j * 4));
+                if (++nfill == CH) {
+                    chunk_flush(cb, CH, 0.5f * W, 0.5f * H, gacc);
+                    nfill = 0;
+                }
+            }
+        }
+    }
+    if (nfill) chunk_flush(cb, nfill, 0.5f * W, 0.5f * H, gacc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -730,8 +970,29 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     float *gacc = (float *)align_up((size_t)grad_scratch);
     SGR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 48, st));
     if (num_rendered > 0) {
+#ifndef SGR_BWD_CHUNKED
+#define SGR_BWD_CHUNKED 1
+#endif
+#if SGR_BWD_CHUNKED
+#define SGR_BLEND_BWD_KERNEL blend_backward_chunked_kernel
+#define SGR_BLEND_BWD_SMEM BWD_SMEM_BYTES
+        {
+            // opt in to > 48 KB of dynamic shared memory once per device (the call is not free)
+            static bool attr_set[64] = {};
+            int dev = 0;
+            SGR_CUDA(cudaGetDevice(&dev));
+            if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+                SGR_CUDA(cudaFuncSetAttribute(blend_backward_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)BWD_SMEM_BYTES));
+                if (dev >= 0 && dev < 64) attr_set[dev] = true;
+            }
+        }
+#else
+#define SGR_BLEND_BWD_KERNEL blend_backward_kernel
+#define SGR_BLEND_BWD_SMEM 0
+#endif
         SGR_LAUNCH(K_BLEND_BWD, st,
-                   blend_backward_kernel<<<dim3(gx, gy), dim3(SGR_TILE, SGR_TILE), 0, st>>>(
+                   SGR_BLEND_BWD_KERNEL<<<dim3(gx, gy), dim3(SGR_TILE, SGR_TILE), SGR_BLEND_BWD_SMEM, st>>>(
                        img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T, img.n_contrib,
                        dL_dout_color, gacc));
     }

@@ -779,6 +779,12 @@ __global__ void __launch_bounds__(BK_T) tile_sort_bucket_kernel(const uint32_t *
 // ------------------------------------------------------------------------------------------------
 constexpr int BLEND_T = 256;
 
+// Double-buffered records (as in the backward) measured slower here: 0.708 vs 0.673 ms -- most tiles
+// saturate before their last batch, so the prefetched batch is wasted work.  Kept for A/B.
+#ifndef SGR_FWD_PIPELINED
+#define SGR_FWD_PIPELINED 0
+#endif
+
 __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *__restrict__ tile_start,
                                                                 const uint32_t *__restrict__ plist,
                                                                 const float4 *__restrict__ rec,
@@ -788,9 +794,14 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
                                                                 uint32_t *__restrict__ n_contrib,
                                                                 float *__restrict__ out_color)
 {
-    __shared__ float4 s_a[BLEND_T];  // x, y, conic a, conic b
-    __shared__ float4 s_b[BLEND_T];  // conic c, tau, opacity, r
-    __shared__ float2 s_c[BLEND_T];  // g, b
+#if SGR_FWD_PIPELINED
+    constexpr int NBUF = 2;  // records are double-buffered: batch b+1 is copied while batch b is blended
+#else
+    constexpr int NBUF = 1;
+#endif
+    __shared__ float4 s_a[NBUF * BLEND_T];  // x, y, conic a, conic b
+    __shared__ float4 s_b[NBUF * BLEND_T];  // conic c, tau, opacity, r
+    __shared__ float2 s_c[NBUF * BLEND_T];  // g, b
     __shared__ uint32_t s_member[8][BLEND_T / 32];
     if ((uint64_t)counters[0] > capacity) return;
     const int tile = blockIdx.y * gx + blockIdx.x;
@@ -801,13 +812,43 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
     const float pxf = (float)pxi, pyf = (float)pyi;
     const float tx0 = (float)(blockIdx.x * SGR_TILE), ty0 = (float)(blockIdx.y * SGR_TILE);
     const uint32_t lo = tile_start[tile], hi = tile_start[tile + 1];
-    bool done = !inside;
+    uint32_t done = inside ? 0u : 1u;  // 32-bit flag: a bool makes nvcc shuffle bytes (PRMT) in the hot loop
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0;
-    const uint32_t sa = smem_addr_pinned(s_a), sb = smem_addr_pinned(s_b), sc = smem_addr_pinned(s_c);
-    for (uint32_t b0 = lo; b0 < hi; b0 += BLEND_T) {
-        if (__syncthreads_count(done) == BLEND_T) break;
+    const uint32_t sa0 = smem_addr_pinned(s_a), sb0 = smem_addr_pinned(s_b), sc0 = smem_addr_pinned(s_c);
+#if SGR_FWD_PIPELINED
+    // record pipeline: every thread owns one slot of every batch; the id of batch b+2 and the
+    // cp.async (LDGSTS) copies of batch b+1 are in flight while batch b is blended, so the barriers
+    // at the batch boundary do not expose the plist -> record load chain.
+    auto fetch_id = [&](uint32_t b0) -> uint32_t { return (b0 + tid < hi) ? plist[b0 + tid] : 0xffffffffu; };
+    auto issue = [&](uint32_t id, uint32_t buf) {
+        if (id != 0xffffffffu) {
+            const float4 *r = rec + (size_t)id * 3;
+            const uint32_t e = buf * BLEND_T + tid;
+            cp_async16_a(sa0 + e * 16, r);
+            cp_async16_a(sb0 + e * 16, r + 1);
+            cp_async8_a(sc0 + e * 8, r + 2);
+        }
+        cp_async_commit();
+    };
+    uint32_t id_cur = fetch_id(lo);
+    issue(id_cur, 0);
+    uint32_t id_next = fetch_id(lo + BLEND_T);
+#endif
+    uint32_t buf = 0;
+    for (uint32_t b0 = lo; b0 < hi; b0 += BLEND_T, buf ^= (NBUF - 1)) {
+#if SGR_FWD_PIPELINED
+        cp_async_wait<0>();
+#endif
+        if (__syncthreads_count(done != 0u) == BLEND_T) break;
+        const uint32_t sa = sa0 + buf * (BLEND_T * 16), sb = sb0 + buf * (BLEND_T * 16), sc = sc0 + buf * (BLEND_T * 8);
         uint32_t mask = 0;
+#if SGR_FWD_PIPELINED
+        if (id_cur != 0xffffffffu) {
+            const float4 r0 = lds128(sa + tid * 16), r1 = lds128(sb + tid * 16);
+            mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+        }
+#else
         if (b0 + tid < hi) {
             const uint32_t id = plist[b0 + tid];
             const float4 *r = rec + (size_t)id * 3;
@@ -817,14 +858,20 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
             s_c[tid] = make_float2(r2.x, r2.y);
             mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
         }
+#endif
 #pragma unroll
         for (int sidx = 0; sidx < 8; sidx++) {
             const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
             if (lane == 0) s_member[sidx][wid] = word;
         }
+#if SGR_FWD_PIPELINED
+        issue(id_next, buf ^ 1u);  // the other buffer was released by the barrier above
+        id_cur = id_next;
+        id_next = fetch_id(b0 + 2 * BLEND_T);
+#endif
         __syncthreads();
         const uint32_t base_pos = b0 - lo;
-        if (!__all_sync(0xffffffffu, done)) {
+        if (!__all_sync(0xffffffffu, done != 0u)) {
 #pragma unroll 1
             for (int k = 0; k < BLEND_T / 32; k++) {
                 uint32_t mw = s_member[wid][k];
@@ -842,7 +889,7 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
                     if (alpha < 1.0f / 255.0f) continue;
                     const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
                     if (test_T < 0.0001f) {
-                        done = true;
+                        done = 1u;
                         continue;
                     }
                     const float2 Cc = lds64(sc + j * 8);
@@ -852,7 +899,7 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
                     T = test_T;
                     last = base_pos + (uint32_t)j + 1u;
                 }
-                if (__all_sync(0xffffffffu, done)) break;
+                if (__all_sync(0xffffffffu, done != 0u)) break;
             }
         }
     }
