@@ -92,15 +92,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, load=None, timed=None):
+        """`load` = (t0, t1) of the window in which the GPU ran the benchmark's steps back to back (pre-roll +
+        timed region + post-roll); only rows stamped inside it count.  `timed` = the timed region itself."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        sm, mx, reasons, inside = [], [], set(), 0
+        for stamp, r in self.rows:
+            if load is not None and not (load[0] + 0.05 <= stamp <= load[1]):
+                continue
+            if timed is not None and timed[0] <= stamp <= timed[1]:
+                inside += 1
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -112,7 +117,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": inside,
+                "window": "steps run back to back from pre-roll through the timed region to post-roll"}
 
 
 def load_peaks():
@@ -288,6 +294,14 @@ def main():
         radii = step_device()
     torch.cuda.synchronize()
     V_vis = int((radii > 0).sum())
+    # nvidia-smi needs a few hundred ms to deliver its first row and the timed region is short: run the
+    # same step back to back before (pre-roll) and after (post-roll) the timed region, a fixed number of
+    # times on every rank, and keep the clock samples of that whole loaded window.
+    PRE_ROLL, POST_ROLL = 150, 40
+    clocks = ClockSampler(local)
+    t_load0 = time.perf_counter()
+    for _ in range(PRE_ROLL):
+        step_device()
 
     if not use_ref:
         _lib.profile(True)   # allocates the event pool
@@ -295,14 +309,18 @@ def main():
         torch.cuda.synchronize()
         _lib.profile_read()
     launches0 = 0 if use_ref else _lib.lib.sgr_launch_count()
-    clocks = ClockSampler(local)
+    t_timed0 = time.perf_counter()
     ms = timed(step_device, args.steps)
+    t_timed1 = time.perf_counter()
     prof = {}
     if not use_ref:
         prof = _lib.profile_read()
         _lib.profile(False)
     launches = 0 if use_ref else int(_lib.lib.sgr_launch_count() - launches0)
-    clk = clocks.stop()
+    for _ in range(POST_ROLL):
+        step_device()
+    torch.cuda.synchronize()
+    clk = clocks.stop(load=(t_load0, time.perf_counter()), timed=(t_timed0, t_timed1))
 
     for _ in range(3):
         step_e2e()
