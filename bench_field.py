@@ -111,6 +111,20 @@ def main():
         fo.better_normal_loss_torch(x, gi, nbr, points, scaling, ql, opac).mean().backward()
         ql.grad = None
     nl_ms, nl_ref_ms = timeit(normal_ours, a.steps), timeit(normal_ref, max(3, a.steps // 4))
+    # level-set ray sampling (sugar_model.py:1970-2081): N rays x 21 samples, 3 levels + normals
+    try:
+        from sugar_b200 import levelset
+        cam = torch.tensor([0.0, 0.0, -8.0], device=dev)
+
+        def ls():
+            return levelset.level_surface_points(x, cam, nbr, points, scaling, quats, strengths, density_factor=1.0,
+                                                 return_normals=True)
+        ls_ms = timeit(ls, max(3, a.steps // 4))
+        ls_out = ls()
+        levelset_res = {"ms": ls_ms, "rays": N, "samples_per_ray": 21, "rays_per_s": N / (ls_ms * 1e-3),
+                        "valid_at_0.3": int(ls_out[0.3]["valid"].sum())}
+    except Exception as e:  # keep the line printable
+        levelset_res = {"error": repr(e)[:200]}
     fwd_bytes = N * (12 + 8 * K + 48 * K)
     stages = {k: {"ms": round(v[0] / v[1], 4)} for k, v in prof.items()}
     if "field_forward" in stages:
@@ -123,6 +137,7 @@ def main():
                          "sample": f"{ns} samples of the workload, PyTorch op chain of sugar_model.py:1247-1316"},
         "knn_reset_neighbors": {"ms": knn_ms, "points_per_s": P / (knn_ms * 1e-3), "K": K,
                                 "note": "exact K-NN of the cloud against itself (uniform grid), replaces pytorch3d.knn_points"},
+        "level_set_sampling": levelset_res,
         "better_normal_loss": {"ms_fwd_bwd": nl_ms, "torch_same_gpu_ms": nl_ref_ms, "samples_per_s": N / (nl_ms * 1e-3)},
         "stages": stages}))
 

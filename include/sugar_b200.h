@@ -164,6 +164,8 @@ typedef struct SgrFieldParams {
     float density_factor;
     float density_threshold;
     float opacity_min_clamp; /* 1e-16 in the reference */
+    int32_t samples_per_idx_row; /* 0/1: nbr_idx is i64[N,K]; g > 1: i64[ceil(N/g),K], row n/g serves sample n
+                                  * (ray samples that share their pixel's neighbours, sugar_model.py:1980) */
 } SgrFieldParams;
 
 /* `scratch` must hold sgr_field_scratch_bytes(P) (packed per-Gaussian records; device memory). */

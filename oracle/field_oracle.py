@@ -8,6 +8,7 @@ Follows, op for op in PyTorch on the CPU:
     sample_points_in_gaussians                                       sugar_scene/sugar_model.py:885-928
     get_smallest_axis / get_normals(estimate_from_points=False)      sugar_scene/sugar_model.py:930-968
     "better normal" loss (inline in the trainers)                    sugar_trainers/coarse_sdf.py:688-716
+    level-set points along camera rays (per-ray part)                sugar_scene/sugar_model.py:1970-2081
 Third-party arithmetic that is NOT under /root/reference (pytorch3d 0.7.4, environment.yml:161) is
 restated from its published algorithm: quaternion_to_matrix / quaternion_apply (real-first) and
 knn_points (exact K-NN on squared distances; restated with cdist + topk).
@@ -16,7 +17,9 @@ Parity pinning: tests/golden/field_*.npz were produced by running the reference'
 SuGaR.get_field_values code (imported from /root/reference with the missing third-party modules
 stubbed, tests/golden/make_field_golden.py); tests/test_field_oracle.py checks this file against them.
 tests/golden/normal_*.npz likewise: normals from the reference's SuGaR.get_normals, loss from the
-trainer's own source lines executed as they stand (tests/golden/make_normal_golden.py).
+trainer's own source lines executed as they stand (tests/golden/make_normal_golden.py);
+tests/golden/levelset_*.npz from lines 1970-2081 of compute_level_surface_points_from_camera_fast executed
+as they stand (tests/golden/make_levelset_golden.py).
 """
 import numpy as np
 import torch
@@ -87,6 +90,53 @@ def better_normal_loss_torch(x, gaussian_idx, nbr_idx, points, scaling, quaterni
     w = nbr_opacity.detach() * w / min_scaling.clamp(min=1e-6) ** 2                              # :707
     w = w / w.sum(dim=-1).detach().unsqueeze(-1).clamp(min=1e-6)                                 # :710-711
     return (s_normals - (w[..., None] * c_normals).sum(dim=-2)).pow(2).sum(dim=-1)               # :714-715
+
+
+def level_surface_points_torch(world_points, camera_center, closest_gaussians_idx, points, scaling, quaternions,
+                               strengths, surface_levels=(0.1, 0.3, 0.5), n_points_in_range=21, range_size=3.0,
+                               density_factor=1.0, return_normals=True):
+    """Per-ray part of compute_level_surface_points_from_camera_fast (sugar_model.py:1970-2081), default flags
+    (compute_intersection_for_flat_gaussian=False, compute_flat_normals=False, just_use_depth_as_level=False)."""
+    cam = camera_center.reshape(1, 3)
+    to_cam = torch.nn.functional.normalize(cam - points, dim=-1)                                            # :1971
+    q_inv = quaternions * quaternions.new_tensor([1.0, -1.0, -1.0, -1.0])
+    stds = (scaling * quaternion_apply(q_inv, to_cam)).norm(dim=-1)                                         # :1972
+    points_stds = stds[closest_gaussians_idx[..., 0]]
+    rng = torch.linspace(-range_size, range_size, n_points_in_range).to(points).view(1, -1, 1)              # :1976
+    rng = rng * points_stds[..., None, None].expand(-1, n_points_in_range, 1)
+    cam_to_samples = torch.nn.functional.normalize(world_points - cam, dim=-1)
+    samples = (world_points[:, None, :] + rng * cam_to_samples[:, None, :]).view(-1, 3)
+    K = closest_gaussians_idx.shape[1]
+    s_idx = closest_gaussians_idx[:, None, :].expand(-1, n_points_in_range, -1).reshape(-1, K)
+    isr = quaternion_to_matrix(quaternions) * (1.0 / scaling.clamp(min=1e-8))[:, None]                      # :1986
+    str_ = strengths.view(-1, 1)
+
+    def opac(x, idx):
+        shift = x[:, None] - points[idx]
+        warped = isr[idx].transpose(-1, -2) @ shift[..., None]
+        o = (warped[..., 0] * warped[..., 0]).sum(dim=-1).clamp(min=0.0, max=1e8)
+        return density_factor * str_[idx][..., 0] * torch.exp(-1.0 / 2 * o), warped
+    dens = opac(samples, s_idx)[0].sum(dim=-1)
+    m = dens >= 1.0
+    dens = torch.where(m, dens / (dens + 1e-12), dens).reshape(-1, n_points_in_range)                       # :2007-2011
+    out = {}
+    for level in surface_levels:
+        under, above = dens - level < 0, dens - level > 0
+        _, first = above.max(dim=-1, keepdim=True)
+        empty = ~under[..., 0] + (first[..., 0] == 0)
+        vd, vr, fa = dens[~empty], rng[~empty][..., 0], first[~empty]
+        v1, v0 = vd.gather(-1, fa).view(-1), vd.gather(-1, fa - 1).view(-1)
+        t1, t0 = vr.gather(-1, fa).view(-1), vr.gather(-1, fa - 1).view(-1)
+        t = (level - v0) / (v1 - v0) * (t1 - t0) + t0
+        inter = world_points[~empty] + t[:, None] * cam_to_samples[~empty]
+        res = {"intersection_points": inter, "valid": ~empty}
+        if return_normals:
+            idx = closest_gaussians_idx[~empty]
+            o, warped = opac(inter, idx)
+            grad = (o[..., None] * (isr[idx] @ warped)[..., 0]).sum(dim=-2)                                 # :2065
+            res["normals"] = -torch.nn.functional.normalize(grad, dim=-1)                                  # :2075
+        out[level] = res
+    return out
 
 
 def field_values(x, nbr_idx, points, scaling, quaternions, strengths, density_factor=1.0, density_threshold=1.0,

@@ -36,7 +36,7 @@ class SgrGaussians(C.Structure):
 
 class SgrFieldParams(C.Structure):
     _fields_ = [("N", C.c_int32), ("K", C.c_int32), ("P", C.c_int32), ("density_factor", C.c_float),
-                ("density_threshold", C.c_float), ("opacity_min_clamp", C.c_float)]
+                ("density_threshold", C.c_float), ("opacity_min_clamp", C.c_float), ("samples_per_idx_row", C.c_int32)]
 
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)

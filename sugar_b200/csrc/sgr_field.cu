@@ -61,7 +61,7 @@ __device__ __forceinline__ float group_sum(float v)
 }
 
 struct FieldArgs {
-    int N, K, P;
+    int N, K, P, group;
     float density_factor, sdf_offset, opacity_min_clamp;
     const float *x;
     const int64_t *idx;
@@ -93,11 +93,12 @@ __global__ void __launch_bounds__(256) field_forward_kernel(const FieldArgs a, f
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const int n = blockIdx.x * SPB + g;
     const bool live = n < a.N;
+    const int nrow = a.group > 1 ? n / a.group : n;  // neighbour row shared by `group` consecutive samples
     float dens = 0.f, bsum = 0.f;
     if (live) {
         const float x0 = a.x[3 * n], x1 = a.x[3 * n + 1], x2 = a.x[3 * n + 2];
         for (int k = l; k < a.K; k += G) {
-            const int64_t id = a.idx[(size_t)n * a.K + k];
+            const int64_t id = a.idx[(size_t)nrow * a.K + k];
             const float4 r0 = __ldg(a.rec + id * 3), r1 = __ldg(a.rec + id * 3 + 1), r2 = __ldg(a.rec + id * 3 + 2);
             const Rot R = quat_to_rot(r1);
             const float sh0 = x0 - r0.x, sh1 = x1 - r0.y, sh2 = x2 - r0.z;
@@ -142,13 +143,14 @@ __global__ void __launch_bounds__(256) field_backward_kernel(const FieldArgs a, 
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const int n = blockIdx.x * SPB + g;
     const bool live = n < a.N;
+    const int nrow = a.group > 1 ? n / a.group : n;
     float x0 = 0, x1 = 0, x2 = 0;
     if (live) x0 = a.x[3 * n], x1 = a.x[3 * n + 1], x2 = a.x[3 * n + 2];
     // pass 1: recompute density and beta for the sample (needed for d sdf / d density)
     float dens = 0.f, bsum = 0.f;
     if (live)
         for (int k = l; k < a.K; k += G) {
-            const int64_t id = a.idx[(size_t)n * a.K + k];
+            const int64_t id = a.idx[(size_t)nrow * a.K + k];
             const float4 r0 = __ldg(a.rec + id * 3), r1 = __ldg(a.rec + id * 3 + 1), r2 = __ldg(a.rec + id * 3 + 2);
             const Rot R = quat_to_rot(r1);
             const float sh0 = x0 - r0.x, sh1 = x1 - r0.y, sh2 = x2 - r0.z;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(256) field_backward_kernel(const FieldArgs a, 
     float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f;
     if (live)
         for (int k = l; k < a.K; k += G) {
-            const int64_t id = a.idx[(size_t)n * a.K + k];
+            const int64_t id = a.idx[(size_t)nrow * a.K + k];
             const float4 r0 = __ldg(a.rec + id * 3), r1 = __ldg(a.rec + id * 3 + 1), r2 = __ldg(a.rec + id * 3 + 2);
             const Rot R = quat_to_rot(r1);
             const float sh[3] = {x0 - r0.x, x1 - r0.y, x2 - r0.z};
@@ -298,6 +300,7 @@ static FieldArgs make_args(const SgrFieldParams *p, const float *x, const int64_
     a.N = p->N;
     a.K = p->K;
     a.P = p->P;
+    a.group = p->samples_per_idx_row > 1 ? p->samples_per_idx_row : 1;
     a.density_factor = p->density_factor;
     // np.sqrt(-2. * np.log(min(density_threshold, 1.)))   (sugar_model.py:1305), evaluated in double like numpy
     const double thr = p->density_threshold < 1.0f ? (double)p->density_threshold : 1.0;

@@ -21,8 +21,9 @@ import torch
 from ._lib import SgrFieldParams, check, lib
 
 
-def _params(N, K, P, density_factor, density_threshold, opacity_min_clamp):
+def _params(N, K, P, density_factor, density_threshold, opacity_min_clamp, group=1):
     p = SgrFieldParams()
+    p.samples_per_idx_row = int(group)
     p.N, p.K, p.P = int(N), int(K), int(P)
     p.density_factor = float(density_factor)
     p.density_threshold = float(density_threshold)
@@ -37,37 +38,43 @@ def _ptr(t):
 class _Field(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, nbr_idx, points, scaling, quaternions, strengths, density_factor, density_threshold,
-                opacity_min_clamp):
+                opacity_min_clamp, group=1, outputs=7):
+        """outputs: bit 0 nbr_opacity, bit 1 beta, bit 2 sdf -- unrequested ones are neither allocated nor
+        written (they come back as empty tensors)."""
         if not x.is_cuda:
             raise RuntimeError("sugar_b200.field needs CUDA tensors: there is no CPU fallback")
         x, points, scaling, quaternions = (t.contiguous().float() for t in (x, points, scaling, quaternions))
         strengths = strengths.contiguous().float()
         nbr_idx = nbr_idx.contiguous().long()
         N, K, P = x.shape[0], nbr_idx.shape[1], points.shape[0]
+        if nbr_idx.shape[0] * group < N:
+            raise RuntimeError("closest_gaussians_idx has too few rows for the samples")
         dev = x.device
         with torch.cuda.device(dev):
             density = torch.empty(N, device=dev)
-            nbr = torch.empty((N, K), device=dev)
-            beta = torch.empty(N, device=dev)
-            sdf = torch.empty(N, device=dev)
+            nbr = torch.empty((N, K) if outputs & 1 else (0, K), device=dev)
+            beta = torch.empty(N if outputs & 2 else 0, device=dev)
+            sdf = torch.empty(N if outputs & 4 else 0, device=dev)
             scratch = torch.empty(lib.sgr_field_scratch_bytes(P), dtype=torch.uint8, device=dev)
-            p = _params(N, K, P, density_factor, density_threshold, opacity_min_clamp)
+            p = _params(N, K, P, density_factor, density_threshold, opacity_min_clamp, group)
             check(lib.sgr_field_forward(C.byref(p), _ptr(x), _ptr(nbr_idx), _ptr(points), _ptr(scaling),
-                                        _ptr(quaternions), _ptr(strengths), _ptr(density), _ptr(nbr), _ptr(beta),
-                                        _ptr(sdf), _ptr(scratch), torch.cuda.current_stream(dev).cuda_stream))
+                                        _ptr(quaternions), _ptr(strengths), _ptr(density),
+                                        _ptr(nbr) if outputs & 1 else None, _ptr(beta) if outputs & 2 else None,
+                                        _ptr(sdf) if outputs & 4 else None, _ptr(scratch), torch.cuda.current_stream(dev).cuda_stream))
         ctx.save_for_backward(x, nbr_idx, points, scaling, quaternions, strengths)
-        ctx.cfg = (density_factor, density_threshold, opacity_min_clamp, strengths.shape)
+        ctx.cfg = (density_factor, density_threshold, opacity_min_clamp, strengths.shape, group, outputs)
         ctx.mark_non_differentiable(nbr_idx)
         return density, nbr, beta, sdf
 
     @staticmethod
     def backward(ctx, g_density, g_nbr, g_beta, g_sdf):
         x, nbr_idx, points, scaling, quaternions, strengths = ctx.saved_tensors
-        density_factor, density_threshold, opacity_min_clamp, s_shape = ctx.cfg
+        density_factor, density_threshold, opacity_min_clamp, s_shape, group, outputs = ctx.cfg
         N, K, P = x.shape[0], nbr_idx.shape[1], points.shape[0]
         dev = x.device
         c = lambda g: None if g is None else g.contiguous().float()
-        g_density, g_nbr, g_beta, g_sdf = map(c, (g_density, g_nbr, g_beta, g_sdf))
+        g_density, g_nbr, g_beta, g_sdf = map(c, (g_density, g_nbr if outputs & 1 else None,
+                                                  g_beta if outputs & 2 else None, g_sdf if outputs & 4 else None))
         with torch.cuda.device(dev):
             g_x = torch.empty_like(x)
             g_points = torch.empty_like(points)
@@ -75,12 +82,12 @@ class _Field(torch.autograd.Function):
             g_quat = torch.empty_like(quaternions)
             g_str = torch.empty(P, device=dev)
             scratch = torch.empty(lib.sgr_field_scratch_bytes(P), dtype=torch.uint8, device=dev)
-            p = _params(N, K, P, density_factor, density_threshold, opacity_min_clamp)
+            p = _params(N, K, P, density_factor, density_threshold, opacity_min_clamp, group)
             check(lib.sgr_field_backward(C.byref(p), _ptr(x), _ptr(nbr_idx), _ptr(points), _ptr(scaling),
                                          _ptr(quaternions), _ptr(strengths), _ptr(g_density), _ptr(g_nbr), _ptr(g_beta),
                                          _ptr(g_sdf), _ptr(g_x), _ptr(g_points), _ptr(g_scaling), _ptr(g_quat),
                                          _ptr(g_str), _ptr(scratch), torch.cuda.current_stream(dev).cuda_stream))
-        return g_x, None, g_points, g_scaling, g_quat, g_str.view(s_shape), None, None, None
+        return g_x, None, g_points, g_scaling, g_quat, g_str.view(s_shape), None, None, None, None, None
 
 
 class _NormalLoss(torch.autograd.Function):
@@ -152,10 +159,13 @@ def field_values(x, closest_gaussians_idx, points, scaling, quaternions, strengt
 
 
 def compute_density(x, closest_gaussians_idx, points, scaling, quaternions, strengths, density_factor=1.,
-                    return_closest_gaussian_opacities=False):
-    """SuGaR.compute_density (sugar_model.py:1345-1368) for given neighbour indices."""
+                    return_closest_gaussian_opacities=False, samples_per_idx_row=1):
+    """SuGaR.compute_density (sugar_model.py:1345-1368) for given neighbour indices.  With
+    `samples_per_idx_row` = g > 1, row n // g of `closest_gaussians_idx` serves sample n (consecutive ray
+    samples sharing their pixel's neighbours) so the index table need not be replicated."""
     density, nbr, _, _ = _Field.apply(x, closest_gaussians_idx, points, scaling, quaternions, strengths,
-                                      density_factor, 1.0, 1e-16)
+                                      density_factor, 1.0, 1e-16, samples_per_idx_row,
+                                      1 if return_closest_gaussian_opacities else 0)
     return (density, nbr) if return_closest_gaussian_opacities else density
 
 

@@ -82,3 +82,21 @@ def test_normal_loss_oracle_matches_reference_code(name):
     assert np.allclose(loss.detach().numpy(), gold["loss"], rtol=1e-5, atol=1e-7)
     loss.mean().backward()
     assert np.allclose(q.grad.numpy(), gold["grad_quaternions"], rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["k16", "k8"])
+def test_levelset_oracle_matches_reference_code(name):
+    """oracle level_surface_points_torch vs sugar_model.py:1970-2081 executed as it stands
+    (tests/golden/make_levelset_golden.py)."""
+    from make_levelset_golden import CASES as LCASES, LEVELS, make_inputs
+    gold = np.load(os.path.join(HERE, "golden", f"levelset_{name}.npz"))
+    case, cam = make_inputs(LCASES[name])
+    t = lambda k: torch.from_numpy(case[k])
+    out = fo.level_surface_points_torch(t("x"), torch.from_numpy(cam), t("nbr_idx"), t("points"), t("scaling"),
+                                        t("quaternions"), t("strengths"), surface_levels=LEVELS,
+                                        density_factor=LCASES[name]["density_factor"])
+    for lv in LEVELS:
+        o = out[lv]
+        assert np.array_equal(t("gaussian_idx")[o["valid"]].numpy(), gold[f"gaussian_idx_{lv}"])
+        assert np.allclose(o["intersection_points"].numpy(), gold[f"points_{lv}"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(o["normals"].numpy(), gold[f"normals_{lv}"], rtol=1e-4, atol=1e-5)
