@@ -147,7 +147,7 @@ def field_values(x, closest_gaussians_idx, points, scaling, quaternions, strengt
                  return_closest_gaussian_opacities=False, return_beta=False):
     """SuGaR.get_field_values for explicit neighbour indices (closest_gaussians_idx = knn_idx[gaussian_idx])."""
     density, nbr, beta, sdf = _Field.apply(x, closest_gaussians_idx, points, scaling, quaternions, strengths,
-                                           density_factor, density_threshold, opacity_min_clamp)
+                                           density_factor, density_threshold, opacity_min_clamp, 1, 7)
     fields = {"density": density}
     if return_closest_gaussian_opacities:
         fields["closest_gaussian_opacities"] = nbr
