@@ -134,3 +134,34 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     d = np.abs(a - b).max() if a.size else 0.0
     return d / max(np.abs(b).max() if b.size else 0.0, 1e-30)
+
+
+def grad_sensitivity(sc, bg, dL, eps=1e-6, **opts):
+    """Conditioning probe for the per-Gaussian backward chain (CPU oracle): relative change (|.|_inf / |g|_inf)
+    of each returned gradient when the blend accumulators dL_dmeans2D / dL_dconic are perturbed by `eps`
+    relative noise, i.e. by what fp32 summation order alone does to them.  For surface-aligned Gaussians
+    with a 1e-6 axis, eps = 1e-6 moves dL_drotations by ~1e-4: there a fixed 1e-4 bar measures the
+    conditioning of the reference's formula, not the implementation."""
+    import ctypes as C
+    from oracle import raster_oracle as ro
+    fw, bw = run_oracle(sc, np.asarray(bg, np.float32), dL, **opts)
+    L, i, _p = ro.lib(), fw["_in"], ro._p
+    P, W, H, M, D = fw["P"], fw["W"], fw["H"], fw["M"], fw["D"]
+    cov3Ds = i["cov3D_precomp"] if i["cov3D_precomp"] is not None else fw["cov3D"]
+
+    def chain(dm2d, dconic):
+        g = dict(means3D=np.zeros((P, 3), np.float32), cov3D_precomp=np.zeros((P, 6), np.float32),
+                 shs=np.zeros((P, max(M, 1), 3), np.float32), scales=np.zeros((P, 3), np.float32),
+                 rotations=np.zeros((P, 4), np.float32))
+        L.oracle_preprocess_backward(
+            C.c_int(P), C.c_int(D), C.c_int(M), _p(i["means3D"]), _p(fw["radii"]), _p(i["shs"]), _p(fw["clamped"]),
+            _p(i["scales"]), _p(i["rotations"]), C.c_float(i["scale_modifier"]), _p(cov3Ds), _p(i["viewmatrix"]),
+            _p(i["projmatrix"]), C.c_int(W), C.c_int(H), C.c_float(i["tanfovx"]), C.c_float(i["tanfovy"]),
+            _p(i["campos"]), _p(dm2d), _p(dconic), _p(bw["dL_dcolors"].copy()), _p(g["means3D"]), _p(g["cov3D_precomp"]),
+            _p(g["shs"]), _p(g["scales"]), _p(g["rotations"]))
+        return g
+    base = chain(bw["dL_dmeans2D"].copy(), bw["dL_dconic"].copy())
+    rng = np.random.default_rng(0)
+    noisy = lambda a: (a * (1 + eps * rng.standard_normal(a.shape))).astype(np.float32)
+    pert = chain(noisy(bw["dL_dmeans2D"]), noisy(bw["dL_dconic"]))
+    return {k: float(np.abs(pert[k] - base[k]).max() / max(np.abs(base[k]).max(), 1e-30)) for k in base}
