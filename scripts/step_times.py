@@ -1,3 +1,5 @@
+"""Per-step wall times of the bench workload and allocator statistics (how the allocator-cycle fix in
+sugar_b200/_C.py was found): python scripts/step_times.py"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

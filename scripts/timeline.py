@@ -1,3 +1,5 @@
+"""Kernel timeline of one fwd+bwd step from the library's own CUDA-event log (sgr_profile_timeline):
+python scripts/timeline.py"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
