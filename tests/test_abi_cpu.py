@@ -53,3 +53,29 @@ def test_dropin_module_surface():
         "means3D", "means2D", "sh", "colors_precomp", "opacities", "scales", "rotations", "cov3Ds_precomp",
         "raster_settings"]
     assert hasattr(m.GaussianRasterizer, "markVisible")
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    """Factor-mode rebuild, normal loss, K-NN and field entry points reject bad sizes / null pointers before
+    touching CUDA (status -1 + message), and their workspace queries are monotone."""
+    from sugar_b200 import _lib
+    L = _lib.lib
+    assert L.sgr_sh_grad_from_factors(10, 0, 0, 1, None, None, None, None, None) == -1      # M must be > 0
+    assert L.sgr_sh_grad_from_factors(10, 16, 4, 1, None, None, None, None, None) == -1     # degree > 3
+    assert L.sgr_sh_grad_from_factors(10, 16, 3, 1, None, None, None, None, None) == -1     # null pointers
+    assert b"sgr_sh_grad_from_factors" in L.sgr_last_error()
+    assert L.sgr_sh_grad_from_factors(0, 16, 3, 1, None, None, None, None, None) == 0       # P == 0: nothing to do
+    assert L.sgr_normal_loss_forward(5, 0, 10, *([None] * 10)) == -1                        # K must be > 0
+    assert L.sgr_normal_loss_forward(5, 16, 10, *([None] * 10)) == -1                       # null pointers
+    assert L.sgr_normal_loss_backward(5, 16, 10, *([None] * 11)) == -1
+    p = _lib.SgrFieldParams()
+    p.N, p.K, p.P = 4, 0, 10
+    assert L.sgr_field_forward(ctypes.byref(p), *([None] * 12)) == -1
+    for fn in (L.sgr_field_scratch_bytes, L.sgr_normal_scratch_bytes, L.sgr_knn_workspace_bytes):
+        assert 0 < fn(1000) <= fn(100000)
+    # the staged backward shares the plain one's validation
+    v = _lib.SgrView(); g = _lib.SgrGaussians()
+    v.image_width, v.image_height, g.P = 0, 0, 5
+    hook = _lib.STAGE_HOOK(lambda ctx, stage: None)
+    assert L.sgr_rasterize_backward_staged(ctypes.byref(v), ctypes.byref(g), *([None] * 4), 0, *([None] * 11),
+                                           hook, None) == -1
