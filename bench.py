@@ -240,11 +240,14 @@ def main():
     # e2e: every step copies ITS view's camera + upstream image gradient from pinned host memory
     # and reads the scalar loss back.  Like any input pipeline, the copy of step k+1 is issued on
     # a side stream while step k computes (double buffered); it is still one H2D per step inside
-    # the timed region.
+    # the timed region.  The loss of every step is copied device -> host into pinned memory on the
+    # compute stream (asynchronously, like a training loop that logs without stalling); all reads
+    # complete before the timed region closes and are checked afterwards.
     copy_stream = torch.cuda.Stream(device=dev)
     slots = [None, None]
     slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"i": 0}
+    loss_ring = torch.full((4096,), float("nan")).pin_memory()
 
     def prefetch(k):
         with torch.cuda.stream(copy_stream):
@@ -256,9 +259,12 @@ def main():
         e2e_state["i"] += 1
         if slots[k] is None:
             prefetch(k)
-        torch.cuda.current_stream(dev).wait_event(slot_ready[k])
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(slot_ready[k])
         vm, pm, cp, b, g = slots[k]
-        prefetch(k ^ 1)  # next step's inputs; slot k^1 was consumed by the previous (synchronised) step
+        for x in slots[k]:
+            x.record_stream(cur)  # allocated on the copy stream, consumed on this one
+        prefetch(k ^ 1)  # next step's inputs (fresh tensors: nothing in flight is overwritten)
         rast = mod.GaussianRasterizer(settings(vm, pm, cp, b))
         color, radii = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
                             shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
@@ -266,9 +272,9 @@ def main():
         loss.backward()
         if arena is not None:
             arena.all_reduce_from(params, campos=campos_all, sh_degree=D)
-        val = loss.item()  # device -> host read of the step's result
+        # device -> host read of the step's result
+        loss_ring[(e2e_state["i"] - 1) % loss_ring.numel()].copy_(loss.detach(), non_blocking=True)
         zero_grads()
-        return val
 
     def barrier():
         if dist is not None:
@@ -294,10 +300,21 @@ def main():
         radii = step_device()
     torch.cuda.synchronize()
     V_vis = int((radii > 0).sum())
-    # nvidia-smi needs a few hundred ms to deliver its first row and the timed region is short: run the
-    # same step back to back before (pre-roll) and after (post-roll) the timed region, a fixed number of
-    # times on every rank, and keep the clock samples of that whole loaded window.
-    PRE_ROLL, POST_ROLL = 150, 40
+    # nvidia-smi needs up to a second to deliver its first row and the timed region is short: run the
+    # same step back to back before (pre-roll, ~1.2 s) and after (post-roll, ~0.3 s) the timed region, the
+    # same number of times on every rank, and keep the clock samples of that whole loaded window.
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    probe_ms = max(e0.elapsed_time(e1) / 5, 0.05)
+    rolls = torch.tensor([min(max(int(1200.0 / probe_ms), 50), 2000), min(max(int(300.0 / probe_ms), 10), 500)],
+                         device=dev)
+    if dist is not None:
+        dist.broadcast(rolls, src=0)  # collectives inside the step: every rank must run the same count
+    PRE_ROLL, POST_ROLL = (int(v) for v in rolls.tolist())
     clocks = ClockSampler(local)
     t_load0 = time.perf_counter()
     for _ in range(PRE_ROLL):
@@ -324,7 +341,11 @@ def main():
 
     for _ in range(3):
         step_e2e()
+    e2e_first = e2e_state["i"]
     ms_e2e = timed(step_e2e, args.steps)
+    e2e_losses = loss_ring[[(e2e_first + k) % loss_ring.numel() for k in range(args.steps)]]
+    if not bool(torch.isfinite(e2e_losses).all()):
+        raise RuntimeError("e2e: a step's loss did not reach the host")
 
     out = {"metric": METRIC, "value": world / (ms * 1e-3) if not use_ref else 1.0 / (ms * 1e-3), "unit": "views/s",
            "n_gpus": 1 if use_ref else world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -338,7 +359,9 @@ def main():
     n_e2e = 1 if use_ref else world
     out["e2e"] = {"value": n_e2e / (ms_e2e * 1e-3), "unit": "views/s",
                   "h2d_bytes_per_step": int(dL_h.numel() * 4 + (16 + 16 + 3 + 3) * 4), "d2h_bytes_per_step": 4,
-                  "ms_per_step": ms_e2e}
+                  "ms_per_step": ms_e2e,
+                  "d2h": "the step's loss, copied asynchronously into pinned host memory every step; all reads "
+                         "complete inside the timed region (checked finite afterwards)"}
     out["gpu_launches"] = launches
     if use_ref:
         out["impl"] = "reference"
