@@ -251,9 +251,17 @@ constexpr int CH_PITCH = CH + 1;   // float2 elements per pixel row: odd pitch =
 //   dp:   (dL/dpixel r g b, -T_final <bg, dL/dpixel>) of the strip's pixels
 constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 48, CB_BYTES = CB_DP + 32 * 16;
 // CTA shared-memory map (dynamic): records of two batches, membership words, chunk scratch
+// SGR_BWD_ONE_BARRIER (experimental, off): the membership words of batch b+1 are built by the loader threads at the
+// end of batch b from their own landed records, into a second set of words, so ONE CTA barrier per batch publishes
+// records and words together (the default needs two and leaves the non-loader warps idle in between).
+#ifndef SGR_BWD_ONE_BARRIER
+#define SGR_BWD_ONE_BARRIER 0
+#endif
+constexpr uint32_t SM_MEMBER_SETS = SGR_BWD_ONE_BARRIER ? 2 : 1;
 constexpr uint32_t SM_A = 0, SM_B = SM_A + 2 * BWD_B * 16, SM_C = SM_B + 2 * BWD_B * 16, SM_ID = SM_C + 2 * BWD_B * 8,
-                   SM_MEMBER = SM_ID + 2 * BWD_B * 4, SM_LAST = SM_MEMBER + BWD_NW * (BWD_B / 32) * 4,
-                   SM_CHUNK = SM_LAST + 16, BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
+                   SM_MEMBER = SM_ID + 2 * BWD_B * 4,
+                   SM_LAST = SM_MEMBER + SM_MEMBER_SETS * BWD_NW * (BWD_B / 32) * 4, SM_CHUNK = SM_LAST + 16,
+                   BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
 
 // phase 2: reduce the parked chunk (nf splats) over the strip's pixels and add it to the Gaussians'
 // accumulators.  Lane = (chunk slot, strip row).
@@ -378,12 +386,42 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
     uint32_t id_cur = fetch_id(0);
     issue(id_cur, 0);
     uint32_t id_next = fetch_id(BWD_B);
+#if SGR_BWD_ONE_BARRIER
+    // loader threads: membership words of the batch in `buf`, each from its own landed record
+    auto make_masks = [&](uint32_t id, int buf) {
+        uint32_t mask = 0;
+        if (id != 0xffffffffu) {
+            const uint32_t e = buf * BWD_B + tid;
+            const float4 r0 = lds128(sm + SM_A + e * 16), r1 = lds128(sm + SM_B + e * 16);
+            mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+        }
+#pragma unroll
+        for (int sidx = 0; sidx < BWD_NW; sidx++) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
+            if (lane == 0) s_member[buf * BWD_NW + sidx][wid] = word;
+        }
+    };
+    if (loader) {
+        cp_async_wait<0>();
+        make_masks(id_cur, 0);
+    }
+#endif
 
     for (int b0 = 0, buf = 0; b0 < n; b0 += BWD_B, buf ^= 1) {
-        cp_async_wait<0>();
-        __syncthreads();  // batch b0 has landed in `buf`; every warp is done with the other buffer
         const uint32_t sa = sm + SM_A + buf * (BWD_B * 16), sb = sm + SM_B + buf * (BWD_B * 16),
                        sc = sm + SM_C + buf * (BWD_B * 8), sid = sm + SM_ID + buf * (BWD_B * 4);
+#if SGR_BWD_ONE_BARRIER
+        __syncthreads();  // records + membership words of batch b0 are published; every warp is done with b0 - BWD_B
+        const uint32_t(*member)[BWD_B / 32] = s_member + buf * BWD_NW;
+        if (loader) {
+            issue(id_next, buf ^ 1);
+            id_cur = id_next;
+            id_next = fetch_id(b0 + 2 * BWD_B);
+        }
+#else
+        cp_async_wait<0>();
+        __syncthreads();  // batch b0 has landed in `buf`; every warp is done with the other buffer
+        const uint32_t(*member)[BWD_B / 32] = s_member;
         if (loader) {
             uint32_t mask = 0;
             if (id_cur != 0xffffffffu) {
@@ -401,13 +439,14 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
             id_next = fetch_id(b0 + 2 * BWD_B);
         }
         __syncthreads();
+#endif
         const int m = min(BWD_B, n - b0);
         const int jmin = n - b0 - warp_last;  // first batch slot whose list position is < warp_last
         // list position of slot j is n-1-(b0+j); it precedes this pixel's last contributor iff j > jlim
         const int jlim = n - 1 - b0 - last_contributor;
 #pragma unroll 1
         for (int c = 0; c * 32 < m; c++) {
-            uint32_t mw = s_member[wid][c];
+            uint32_t mw = member[wid][c];
             const int cut = jmin - c * 32;
             if (cut >= 32) mw = 0;
             else if (cut > 0) mw &= ~((1u << cut) - 1u);
@@ -463,6 +502,12 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
                 }
             }
         }
+#if SGR_BWD_ONE_BARRIER
+        if (loader) {  // next batch: own record has landed -> its membership bits, published by the next barrier
+            cp_async_wait<0>();
+            make_masks(id_cur, buf ^ 1);
+        }
+#endif
     }
     if (nfill) chunk_flush(cb, nfill, 0.5f * W, 0.5f * H, gacc);
 }
