@@ -257,6 +257,11 @@ constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 48, CB_BY
 #ifndef SGR_BWD_ONE_BARRIER
 #define SGR_BWD_ONE_BARRIER 0
 #endif
+// SGR_BWD_BALANCED_LOADERS (experimental, off): every warp stages 16 records of a batch (lanes 0-15) instead of
+// warps 0-3 staging 32 each, so no warp carries more staging work than another.
+#ifndef SGR_BWD_BALANCED_LOADERS
+#define SGR_BWD_BALANCED_LOADERS 0
+#endif
 constexpr uint32_t SM_MEMBER_SETS = SGR_BWD_ONE_BARRIER ? 2 : 1;
 constexpr uint32_t SM_A = 0, SM_B = SM_A + 2 * BWD_B * 16, SM_C = SM_B + 2 * BWD_B * 16, SM_ID = SM_C + 2 * BWD_B * 8,
                    SM_MEMBER = SM_ID + 2 * BWD_B * 4,
@@ -368,14 +373,31 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
 
     // record pipeline (threads 0..BWD_B-1 own one slot of every batch): issue() starts the async
     // copies of one splat record into buffer `buf`; ids are fetched one batch further ahead
+#if SGR_BWD_BALANCED_LOADERS
+    static_assert(BWD_B == 16 * BWD_NW, "16 records per warp");
+    const bool loader = lane < 16;             // every warp takes part in the ballots below
+    const int ls = (int)(wid * 16 + lane);     // this thread's record slot within a batch
+#else
     const bool loader = tid < BWD_B;
+    const int ls = tid;
+#endif
+    // warps that execute the staging code (whole warps: it contains ballots); within them only `loader` lanes own a record
+    const bool staging_warp = SGR_BWD_BALANCED_LOADERS ? true : loader;
     auto fetch_id = [&](int b0) -> uint32_t {
-        return (loader && b0 + tid < n) ? plist[lo + (uint32_t)(n - 1 - (b0 + tid))] : 0xffffffffu;  // back to front
+        return (loader && b0 + ls < n) ? plist[lo + (uint32_t)(n - 1 - (b0 + ls))] : 0xffffffffu;  // back to front
+    };
+    // membership words: bit j of word c <-> record c*32+j of the batch
+    auto put_member = [&](uint32_t(*set)[BWD_B / 32], int sidx, uint32_t word) {
+#if SGR_BWD_BALANCED_LOADERS
+        if (lane == 0) ((uint16_t *)set[sidx])[wid] = (uint16_t)word;  // this warp's 16 records
+#else
+        if (lane == 0) set[sidx][wid] = word;
+#endif
     };
     auto issue = [&](uint32_t id, int buf) {
         if (id != 0xffffffffu) {
             const float4 *r = rec + (size_t)id * 3;
-            const uint32_t e = buf * BWD_B + tid;
+            const uint32_t e = buf * BWD_B + ls;
             cp_async16_a(sm + SM_A + e * 16, r);
             cp_async16_a(sm + SM_B + e * 16, r + 1);
             cp_async8_a(sm + SM_C + e * 8, r + 2);
@@ -391,17 +413,17 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
     auto make_masks = [&](uint32_t id, int buf) {
         uint32_t mask = 0;
         if (id != 0xffffffffu) {
-            const uint32_t e = buf * BWD_B + tid;
+            const uint32_t e = buf * BWD_B + ls;
             const float4 r0 = lds128(sm + SM_A + e * 16), r1 = lds128(sm + SM_B + e * 16);
             mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
         }
 #pragma unroll
         for (int sidx = 0; sidx < BWD_NW; sidx++) {
             const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
-            if (lane == 0) s_member[buf * BWD_NW + sidx][wid] = word;
+            put_member(s_member + buf * BWD_NW, sidx, word);
         }
     };
-    if (loader) {
+    if (staging_warp) {
         cp_async_wait<0>();
         make_masks(id_cur, 0);
     }
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
 #if SGR_BWD_ONE_BARRIER
         __syncthreads();  // records + membership words of batch b0 are published; every warp is done with b0 - BWD_B
         const uint32_t(*member)[BWD_B / 32] = s_member + buf * BWD_NW;
-        if (loader) {
+        if (staging_warp) {
             issue(id_next, buf ^ 1);
             id_cur = id_next;
             id_next = fetch_id(b0 + 2 * BWD_B);
@@ -422,16 +444,16 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
         cp_async_wait<0>();
         __syncthreads();  // batch b0 has landed in `buf`; every warp is done with the other buffer
         const uint32_t(*member)[BWD_B / 32] = s_member;
-        if (loader) {
+        if (staging_warp) {
             uint32_t mask = 0;
             if (id_cur != 0xffffffffu) {
-                const float4 r0 = lds128(sa + tid * 16), r1 = lds128(sb + tid * 16);
+                const float4 r0 = lds128(sa + ls * 16), r1 = lds128(sb + ls * 16);
                 mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
             }
 #pragma unroll
             for (int sidx = 0; sidx < BWD_NW; sidx++) {
                 const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
-                if (lane == 0) s_member[sidx][wid] = word;
+                put_member(s_member, sidx, word);
             }
             // next batch's records start moving now; they are not needed before the next barrier
             issue(id_next, buf ^ 1);
@@ -503,7 +525,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
             }
         }
 #if SGR_BWD_ONE_BARRIER
-        if (loader) {  // next batch: own record has landed -> its membership bits, published by the next barrier
+        if (staging_warp) {  // next batch: own record has landed -> its membership bits, published by the next barrier
             cp_async_wait<0>();
             make_masks(id_cur, buf ^ 1);
         }
