@@ -104,7 +104,16 @@ class GradArena:
         for f in self.fields:
             self.offsets[f] = (off, widths[f] * P)
             off += widths[f] * P
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.numel = off
+        self.device = device
+        self._flat = None
+
+    @property
+    def flat(self) -> torch.Tensor:
+        """Staging buffer of the packing fallback; allocated on first use (the in-place path never needs it)."""
+        if self._flat is None:
+            self._flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        return self._flat
 
     def view(self, name: str) -> torch.Tensor:
         o, n = self.offsets[name]
@@ -135,7 +144,7 @@ class GradArena:
                 return None
         whole = torch.empty(0, dtype=torch.float32, device=g0.device).set_(store)
         self._base = whole[s0:]
-        return self._base[:self.flat.numel()]
+        return self._base[:self.numel]
 
     def _all_reduce_factored(self, params, buf, campos, sh_degree):
         """SH factor mode: all-reduce everything but the sh slot, all-gather the factors, rebuild dL_dsh.
@@ -145,7 +154,7 @@ class GradArena:
         o_sh, n_sh = self.offsets["shs"]
         M = n_sh // (3 * P)
         # dL_dcolors sits behind [arena | dL_dmeans2D 3P] in the backward's buffer (sugar_b200/_C.py)
-        o_col = self.flat.numel() + 3 * P
+        o_col = self.numel + 3 * P
         dRGB = self._base[o_col:o_col + 3 * P]
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         pending = []
@@ -203,7 +212,7 @@ class GradArena:
 
     def unpack_to(self, params: Dict[str, torch.Tensor]) -> None:
         """Write the reduced gradients back as .grad of the (replicated) parameters."""
-        src = getattr(self, "reduced", self.flat)
+        src = self.reduced if hasattr(self, "reduced") else self.flat
         for f in self.fields:
             o, n = self.offsets[f]
             if params[f].grad is None or params[f].grad.data_ptr() != src.data_ptr() + o * 4:
