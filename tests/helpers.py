@@ -165,3 +165,30 @@ def grad_sensitivity(sc, bg, dL, eps=1e-6, **opts):
     noisy = lambda a: (a * (1 + eps * rng.standard_normal(a.shape))).astype(np.float32)
     pert = chain(noisy(bw["dL_dmeans2D"]), noisy(bw["dL_dconic"]))
     return {k: float(np.abs(pert[k] - base[k]).max() / max(np.abs(base[k]).max(), 1e-30)) for k in base}
+
+
+def check_linear_properties(run, W, H, tol_img=1e-5, tol_grad=1e-4):
+    """Size-independent invariants of the rasterizer, for any implementation behind
+    run(bg, dL) -> (color f32[3,H,W], radii, {name: grad} or None), all numpy:
+      * the background enters as  image(bg) = image(0) + final_T * bg  with one final_T for the three channels
+        (forward.cu:361-367), and radii do not depend on it;
+      * the backward is linear in the upstream image gradient.
+    The CPU suite runs it on the oracle (small), the GPU suite on the CUDA path at the headline size."""
+    from sugar_b200 import scenes
+    c0, r0, _ = run((0.0, 0.0, 0.0), None)
+    c1, r1, _ = run((1.0, 1.0, 1.0), None)
+    T = c1 - c0
+    assert np.abs(T[0] - T[1]).max() <= tol_img and np.abs(T[0] - T[2]).max() <= tol_img
+    assert T.min() >= -tol_img and T.max() <= 1.0 + tol_img
+    bg2 = np.array([0.25, 0.5, 1.0], np.float32)
+    c2, r2, _ = run(tuple(float(v) for v in bg2), None)
+    assert np.abs(c2 - (c0 + T[0][None] * bg2[:, None, None])).max() <= 2 * tol_img
+    assert np.array_equal(r0, r1) and np.array_equal(r0, r2)
+    d1, d2 = scenes.upstream_grad(W, H, seed=1), scenes.upstream_grad(W, H, seed=2)
+    a, b = 0.75, -1.5
+    g1, g2 = run((0.0, 0.0, 0.0), d1)[2], run((0.0, 0.0, 0.0), d2)[2]
+    g12 = run((0.0, 0.0, 0.0), (a * d1 + b * d2).astype(np.float32))[2]
+    assert set(g1) == set(g12) and len(g12) >= 5
+    for k in g12:
+        err = rel_err(g12[k], a * g1[k] + b * g2[k])
+        assert err <= tol_grad, f"backward not linear in dL for {k}: {err:.2e}"

@@ -291,3 +291,18 @@ def test_debug_flag_and_argument_errors():
         st2 = st._replace(bg=torch.zeros(3), viewmatrix=cpu["viewmatrix"], projmatrix=cpu["projmatrix"], campos=cpu["campos"])
         ours.GaussianRasterizer(st2)(means3D=cpu["means3D"], means2D=cpu["means3D"], opacities=cpu["opacities"],
                                      shs=cpu["shs"], scales=cpu["scales"], rotations=cpu["rotations"])
+
+
+def test_headline_size_linear_properties():
+    """3M Gaussians / 1920x1080 (the bench workload): background linearity through final_T and linearity of
+    the backward in the upstream gradient -- properties that need no element-wise reference
+    (helpers.check_linear_properties; the same checker runs on the CPU oracle in test_oracle_properties.py)."""
+    from sugar_b200 import diff_gaussian_rasterization as ours, scenes
+    P, W, H = 3_000_000, 1920, 1080
+    sc = scenes.make_scene(P, W, H, seed=0)
+
+    def run(bg, dL):
+        o = h.run_module(ours, sc, bg, dL, use_sh=True, sh_degree=3)
+        grads = None if dL is None else {k: v.cpu().numpy() for k, v in o["grads"].items()}
+        return o["color"].cpu().numpy(), o["radii"].cpu().numpy(), grads
+    h.check_linear_properties(run, W, H, tol_img=1e-5, tol_grad=1e-4)

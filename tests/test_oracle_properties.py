@@ -68,3 +68,15 @@ def test_culled_gaussians_have_zero_radius_and_zero_gradients():
     culled = fw["radii"] == 0
     for k in ("dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dscales", "dL_drotations"):
         assert not np.any(bw[k][culled]), k
+
+
+def test_linear_properties_checker_on_the_oracle():
+    """helpers.check_linear_properties (the checker the GPU suite runs at the headline size) on the CPU oracle."""
+    sc = _scene(P=1200, W=80, H=48, seed=17)
+
+    def run(bg, dL):
+        fw, bw = h.run_oracle(sc, np.asarray(bg, np.float32), dL)
+        grads = None if bw is None else {k: bw[k] for k in ("dL_dmeans3D", "dL_dmeans2D", "dL_dopacity", "dL_dsh",
+                                                            "dL_dscales", "dL_drotations")}
+        return fw["color"], fw["radii"], grads
+    h.check_linear_properties(run, sc.width, sc.height, tol_img=1e-6, tol_grad=2e-5)
