@@ -37,6 +37,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "forward+backward views/sec @3M Gaussians 1920x1080"
 
 
+def load_scenes():
+    """sugar_b200/scenes.py by path (numpy only).  `import sugar_b200` would map libsugar_b200.so into the
+    process, which the reference arm must not do."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sgr_scenes", os.path.join(ROOT, "sugar_b200", "scenes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -57,7 +67,25 @@ def parse():
 # algorithmic bytes per kernel launch (DESIGN.md "Algorithmic bytes")
 # P Gaussians, V visible, R instances, T tiles, M stored / D active SH, W x H pixels
 # ---------------------------------------------------------------------------------------------
-def algorithmic_bytes(P, V, R, W, H, M, D):
+# which resource bounds each kernel: the blend kernels do ~256 pair evaluations
+# per 40 bytes and are bound by FP32 instruction issue, not by HBM
+KERNEL_BOUND = {"preprocess": "hbm", "preprocess_backward": "hbm", "scatter": "l2-atomics", "tile_scan": "latency",
+                "tile_sort_smem": "shared-memory", "tile_sort_global": "l2", "blend_forward": "fp32-issue",
+                "blend_backward": "fp32-issue", "field_forward": "hbm", "field_backward": "l2-atomics"}
+
+
+def load_ncu_facts():
+    """Per-kernel facts from the committed ncu capture (profiles/ncu_kernels.json, written by
+    scripts/summarize_ncu.py): DRAM bytes and warp-instructions per launch at the headline workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_kernels.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def algorithmic_bytes(P, V, R, W, H, M, D, sh_written=True):
+    """`sh_written`: False in SH factor mode (N > 1), where the per-Gaussian backward does not write dL_dsh."""
     T = ((W + 15) // 16) * ((H + 15) // 16)
     sh = 12 * (D + 1) ** 2
     return {
@@ -68,7 +96,7 @@ def algorithmic_bytes(P, V, R, W, H, M, D):
         "tile_sort_global": R * 12,
         "blend_forward": R * 40 + W * H * 20,
         "blend_backward": R * 40 + W * H * 20 + V * 36 * 2,
-        "preprocess_backward": V * (36 + 44 + sh) + P * (92 + 12 * M),
+        "preprocess_backward": V * (36 + 44 + sh) + P * (92 + (12 * M if sh_written else 0)),
     }
 
 
@@ -129,22 +157,72 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(args):
-    """Scalar C oracle (port of the reference algorithm) on a bounded sample: a 1/64-area scene of
-    the same splat density (P/64 Gaussians at W/8 x H/8), forward+backward, timed on one host core."""
-    from oracle import raster_oracle as ro
-    from sugar_b200 import scenes
+def _cpu_sample(job):
+    """One worker of cpu_baseline(): forward+backward of the C oracle on one 1/64-area sample."""
+    seed, P, W, H, D = job
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers as h
-    f = 8
-    P, W, H = args.gaussians // (f * f), args.width // f, args.height // f
-    sc = scenes.make_scene(P, W, H, seed=0)
+    scenes = load_scenes()
+    sc = scenes.make_scene(P, W, H, seed=seed)
     dL = scenes.upstream_grad(W, H)
     t0 = time.perf_counter()
-    fw, bw = h.run_oracle(sc, np.zeros(3, np.float32), dL, use_sh=True, sh_degree=args.sh_degree)
-    dt = time.perf_counter() - t0
-    return {"value": 1.0 / (dt * f * f), "unit": "views/s", "cores": 1, "kind": "port",
-            "sample": f"1/{f*f}-area sample of the workload ({P} Gaussians @ {W}x{H}, same splat density), "
-                      f"fwd+bwd {dt:.2f} s on 1 core, scaled x{f*f}", "host_cores": os.cpu_count()}
+    h.run_oracle(sc, np.zeros(3, np.float32), dL, use_sh=True, sh_degree=D)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(args):
+    """The C oracle (port of the reference algorithm; the reference has no CPU rasterizer) on a bounded
+    sample, on all host cores: the view is cut into 64 pieces of 1/64 of its area with the same splat
+    density (P/64 Gaussians at W/8 x H/8 each); min(cores, 64) of them run concurrently, one per core,
+    forward+backward.  views/s = pieces done / 64 / wall time."""
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    f = 8
+    P, W, H = args.gaussians // (f * f), args.width // f, args.height // f
+    cores = os.cpu_count() or 1
+    n = max(1, min(cores, f * f))
+    jobs = [(s, P, W, H, args.sh_degree) for s in range(n)]
+    with cf.ProcessPoolExecutor(max_workers=n, mp_context=mp.get_context("spawn")) as ex:
+        list(ex.map(_cpu_sample, jobs[:n]))  # start the workers / load the library
+        t0 = time.perf_counter()
+        per = list(ex.map(_cpu_sample, jobs))
+        dt = time.perf_counter() - t0
+    return {"value": n / (f * f) / dt, "unit": "views/s", "cores": n, "kind": "port",
+            "sample": f"{n} of the 64 1/64-area pieces of the workload ({P} Gaussians @ {W}x{H} each, same splat "
+                      f"density), one per core, fwd+bwd; {dt:.2f} s wall, {sum(per):.1f} core-seconds",
+            "host_cores": cores}
+
+
+def cpu_baseline_density(args):
+    """north_star: the reference's pure-PyTorch density / SDF path (oracle/field_oracle.py restates
+    sugar_model.py:730-750, 1247-1316 op for op) timed on the box's host cores, bounded sample."""
+    import torch
+    from oracle import field_oracle as fo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from scipy.spatial import cKDTree
+    Pg, N, K = 200_000, 100_000, 16
+    g = torch.Generator().manual_seed(0)
+    points = torch.randn(Pg, 3, generator=g)
+    scaling = torch.exp(torch.randn(Pg, 3, generator=g) * 0.5 - 3.5)
+    quats = torch.nn.functional.normalize(torch.randn(Pg, 4, generator=g), dim=-1)
+    strengths = torch.sigmoid(torch.randn(Pg, generator=g) * 2.0)
+    knn = torch.from_numpy(cKDTree(points.numpy()).query(points.numpy(), k=K, workers=-1)[1].astype(np.int64))
+    gi = torch.randint(0, Pg, (N,), generator=g)
+    x = points[gi] + fo.quaternion_apply(quats[gi], 1.5 * scaling[gi] * torch.randn(N, 3, generator=g))
+    f = lambda a: np.ascontiguousarray(a.numpy())
+    case = dict(x=f(x), nbr_idx=f(knn[gi]), gaussian_idx=f(gi), points=f(points), scaling=f(scaling),
+                quaternions=f(quats), strengths=f(strengths), density_factor=1.0 / 16.0, density_threshold=1.0)
+    fo.field_values(**case)  # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        fo.field_values(**case)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": N / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"density+SDF forward of {N} samples, K={K} neighbours, {Pg} Gaussians, PyTorch CPU "
+                      f"({cores} threads), {dt*1e3:.0f} ms per call"}
 
 
 def main():
@@ -165,7 +243,7 @@ def main():
     dev = torch.device("cuda", local)
     P, W, H, D = args.gaussians, args.width, args.height, args.sh_degree
 
-    from sugar_b200 import scenes
+    scenes = load_scenes()
     use_ref = False
     if args.impl == "reference":
         import helpers as h
@@ -178,7 +256,9 @@ def main():
             print(json.dumps({"metric": METRIC, "value": cb["value"], "unit": "views/s", "n_gpus": 1,
                               "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
                               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                              "impl": "reference", "config": {"workload": f"{P} Gaussians {W}x{H} SH{D}"},
+                              "impl": "reference",
+                              "config": {"workload": f"{P} Gaussians (SH deg {D}, M=16) {W}x{H}, 1 view per GPU per step, "
+                                                     "fwd+bwd"},
                               "cpu_baseline": cb, "gpu_launches": 0,
                               "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0,
                                       "d2h_bytes_per_step": 0}}))
@@ -347,55 +427,73 @@ def main():
     if not bool(torch.isfinite(e2e_losses).all()):
         raise RuntimeError("e2e: a step's loss did not reach the host")
 
+    # `config` is identical in both arms (the driver compares them); arm-specific facts live elsewhere
     out = {"metric": METRIC, "value": world / (ms * 1e-3) if not use_ref else 1.0 / (ms * 1e-3), "unit": "views/s",
            "n_gpus": 1 if use_ref else world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{P} Gaussians (SH deg {D}, M=16) {W}x{H}, 1 view per GPU per step, fwd+bwd",
-                      "visible": V_vis, "l2_policy": "inputs (708 MB of Gaussian parameters) larger than L2; no flush",
-                      "parallelism": f"view-dp{world}" if world > 1 else "single",
-                      "exchange": ("none" if world == 1 else "all-reduce 236 B/Gaussian" if args.no_sh_factors else
-                                   "all-reduce 44 B/Gaussian + all-gather 12 B/Gaussian/view SH factors")},
+                      "visible": V_vis, "l2_policy": "inputs (708 MB of Gaussian parameters) larger than L2; no flush"},
+           "parallelism": {"mode": f"view-dp{world}" if world > 1 else "single",
+                           "exchange": ("none" if world == 1 else "all-reduce 236 B/Gaussian" if args.no_sh_factors else
+                                        "all-reduce 44 B/Gaussian + all-gather 12 B/Gaussian/view SH factors")},
            "clocks": clk}
     n_e2e = 1 if use_ref else world
     out["e2e"] = {"value": n_e2e / (ms_e2e * 1e-3), "unit": "views/s",
                   "h2d_bytes_per_step": int(dL_h.numel() * 4 + (16 + 16 + 3 + 3) * 4), "d2h_bytes_per_step": 4,
                   "ms_per_step": ms_e2e,
+                  "resident": "the Gaussian parameters (708 MB: the trainer's nn.Parameters) stay device-resident in "
+                              "both arms, as in the reference's training loop; per-step H2D = this view's camera "
+                              "(38 floats) + upstream image gradient (24.9 MB, pinned, prefetched one step ahead)",
                   "d2h": "the step's loss, copied asynchronously into pinned host memory every step; all reads "
                          "complete inside the timed region (checked finite afterwards)"}
     out["gpu_launches"] = launches
     if use_ref:
         out["impl"] = "reference"
-        out["config"]["reference"] = "unmodified diff-gaussian-rasterization CUDA sources compiled for sm_100a (oracle/_ref)"
+        out["impl_note"] = "unmodified diff-gaussian-rasterization CUDA sources compiled for sm_100a (oracle/_ref)"
         out["gpu_launches"] = 0
     if rank == 0 and not use_ref:
         # R of this view for the byte model
-        rast = mod.GaussianRasterizer(settings(viewmatrix, projmatrix, campos, bg))
         with torch.no_grad():
             from sugar_b200 import _C
             R = _C.rasterize_gaussians(bg, params["means3D"], torch.Tensor([]), params["opacities"], params["scales"],
                                        params["rotations"], 1.0, torch.Tensor([]), viewmatrix, projmatrix, sc.tanfovx,
                                        sc.tanfovy, H, W, params["shs"], D, campos, False, False)[0]
-        alg = algorithmic_bytes(P, V_vis, R, W, H, 16, D)
+        alg = algorithmic_bytes(P, V_vis, R, W, H, 16, D, sh_written=(world == 1 or args.no_sh_factors))
         peak, peak_src = load_peaks()
+        ncu = load_ncu_facts()
+        sm_clock = (clk.get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = 148 * 4 * sm_clock  # warp-instructions / s the chip can issue at the measured clock
         stages = {}
         for name, (tot, cnt) in prof.items():
             avg_ms = tot / cnt
             b = alg.get(name)
-            stages[name] = {"ms": round(avg_ms, 4), "launches_per_step": cnt / args.steps,
-                            "gbs": round(b / (avg_ms * 1e-3) / 1e9, 1) if b else None}
+            st = {"ms": round(avg_ms, 4), "launches_per_step": cnt / args.steps,
+                  "gbs": round(b / (avg_ms * 1e-3) / 1e9, 1) if b else None,
+                  "hbm_frac": round(b / (avg_ms * 1e-3) / 1e9 / peak, 4) if b else None,
+                  "bound": KERNEL_BOUND.get(name, "latency")}
+            inst = (ncu.get(name) or {}).get("warp_instructions")
+            if inst:
+                st["issue_frac"] = round(inst / (avg_ms * 1e-3) / issue_peak, 4)
+            stages[name] = st
         dom = max(stages, key=lambda k: stages[k]["ms"] * stages[k]["launches_per_step"]) if stages else None
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get(dom)
-        except Exception:
-            pass
         if dom:
-            out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                               "frac": round(stages[dom]["gbs"] / peak, 4) if stages[dom]["gbs"] else None,
-                               "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": alg.get(dom)}
+            facts = ncu.get(dom) or {}
+            out["roofline"] = {"kernel": dom, "bound": KERNEL_BOUND.get(dom, "hbm"), "achieved": stages[dom]["gbs"],
+                               "peak": peak, "unit": "GB/s",
+                               "frac": stages[dom]["hbm_frac"], "traffic": facts.get("dram_bytes"),
+                               "peak_source": peak_src, "algorithmic_bytes": alg.get(dom)}
+            if facts.get("warp_instructions"):
+                # the blend kernels are FP32-issue bound (~256 pair evaluations per 40 bytes): their roofline
+                # is the issue rate, warp-instructions (ncu smsp__inst_executed.sum) / duration vs SMs x 4 x clock
+                out["roofline"]["issue"] = {
+                    "achieved": round(facts["warp_instructions"] / (stages[dom]["ms"] * 1e-3) / 1e9, 1),
+                    "peak": round(issue_peak / 1e9, 1), "unit": "G warp-inst/s", "frac": stages[dom].get("issue_frac"),
+                    "warp_instructions": facts["warp_instructions"], "source": facts.get("source")}
+            # the HBM-bound stages BASELINE.md holds to >= 60 % of peak
+            out["roofline"]["hbm_stages"] = {k: v["hbm_frac"] for k, v in stages.items()
+                                             if v["bound"] == "hbm" and v["hbm_frac"] is not None}
         out["stages"] = stages
-        out["config"]["num_rendered"] = R
+        out["workload_stats"] = {"num_rendered": R, "visible": V_vis}
         total_alg = sum(alg[k] for k in alg if k in stages)
         out["hbm_gbs_whole_step"] = round(total_alg / (ms * 1e-3) / 1e9, 1)
         if not args.no_cpu_baseline:
@@ -403,6 +501,10 @@ def main():
                 out["cpu_baseline"] = cpu_baseline(args)
             except Exception as ex:  # the oracle is a checker; never let it break the bench line
                 out["cpu_baseline"] = {"error": repr(ex)}
+            try:
+                out["cpu_baseline_density"] = cpu_baseline_density(args)
+            except Exception as ex:
+                out["cpu_baseline_density"] = {"error": repr(ex)}
     if use_ref:
         out["cpu_baseline"] = {"value": out["value"], "unit": "views/s", "cores": 0, "kind": "reference",
                                "sample": "full workload on the GPU: the reference path has no CPU implementation"}

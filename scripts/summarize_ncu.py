@@ -1,7 +1,8 @@
 """Turn an `ncu --set full` report into the committed summaries under profiles/:
    python scripts/summarize_ncu.py gpurun_out/prof_X.ncu-rep r01
  -> profiles/r01_ncu_summary.csv  (one row per captured launch, key metrics)
- -> profiles/ncu_traffic.json     (dram bytes read+written per launch, keyed by bench.py stage name)"""
+ -> profiles/ncu_kernels.json     (per bench.py stage: dram bytes read+written and warp-instructions per
+                                   launch, summed over the launches of one step; bench.py reads it)"""
 import csv
 import io
 import json
@@ -34,7 +35,7 @@ def main(rep, tag):
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
     out = os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.csv")
-    traffic = {}
+    traffic, insts = {}, {}
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         cols = [c for c in KEEP if c in ix]
@@ -47,9 +48,12 @@ def main(rep, tag):
             if key:
                 b = sum(float(r[ix[c]]) * MULT.get(units[ix[c]], 1) for c in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
                 traffic[key] = traffic.get(key, 0) + int(b)
-    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
-        json.dump(traffic, f, indent=1)
-    print("wrote", out, traffic)
+                insts[key] = insts.get(key, 0) + int(float(r[ix["smsp__inst_executed.sum"]]))
+    facts = {k: {"dram_bytes": traffic[k], "warp_instructions": insts[k], "source": f"profiles/{tag}_ncu_summary.csv"}
+             for k in traffic}
+    with open(os.path.join(ROOT, "profiles", "ncu_kernels.json"), "w") as f:
+        json.dump(facts, f, indent=1)
+    print("wrote", out, facts)
 
 
 if __name__ == "__main__":

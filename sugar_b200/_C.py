@@ -5,8 +5,10 @@ signatures and return tuples, implemented over the C ABI of libsugar_b200.so.
 torch is used only for device memory (caching allocator), the current stream and the device
 guard; all arithmetic happens in the hand-written sm_100a kernels.
 """
+import contextlib
 import ctypes as C
 import os
+import threading
 from typing import Tuple
 
 import torch
@@ -14,11 +16,51 @@ import torch
 from . import _lib
 from ._lib import SgrGaussians, SgrView, check, lib
 
-# Instance-capacity hint per device: after the first forward the binning buffer is sized from the
-# previous view's instance count (x1.25 + slack) so the whole forward is enqueued without
-# waiting for the device; the C side re-runs binning on overflow (include/sugar_b200.h).
-_capacity_hint = {}
 _USE_HINT = os.environ.get("SGR_NO_CAPACITY_HINT", "0") != "1"
+
+
+class Context:
+    """Mutable state of the op that outlives one call.  Nothing here is process-global: a model (or a
+    thread, or a view-parallel exchange) can own its context and select it with `use_context`;
+    calls made outside any `use_context` block share `default_context()`.
+
+    capacity_hint  (device, H, W) -> instance capacity.  After the first forward the binning buffer is
+                   sized from the previous view's instance count (x1.25 + slack) so the whole forward is
+                   enqueued without waiting for the device; the C side re-runs binning on overflow
+                   (include/sugar_b200.h).
+    exchange       None, or the view-parallel exchange (sugar_b200.parallel.ViewParallel) that the
+                   backward hands its per-Gaussian gradients to before returning them to autograd.
+
+    The forward stores the context it ran under in the autograd node, so the backward -- which autograd
+    runs on its own engine thread -- uses the same one."""
+
+    def __init__(self):
+        self.capacity_hint = {}
+        self.exchange = None
+        self.lock = threading.Lock()
+
+
+_default_context = Context()
+_tls = threading.local()
+
+
+def default_context() -> Context:
+    return _default_context
+
+
+def current_context() -> Context:
+    return getattr(_tls, "ctx", None) or _default_context
+
+
+@contextlib.contextmanager
+def use_context(ctx: Context):
+    """Calls made by this thread inside the block use `ctx` (nestable)."""
+    prev = getattr(_tls, "ctx", None)
+    _tls.ctx = ctx
+    try:
+        yield ctx
+    finally:
+        _tls.ctx = prev
 
 
 def _ptr(t: torch.Tensor, name: str):
@@ -142,9 +184,12 @@ def _c(t):
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
-                                                     torch.Tensor]:
-    """RasterizeGaussiansCUDA (rasterize_points.cu:36-115)."""
+                        prefiltered, debug, *, context: Context = None) -> Tuple[int, torch.Tensor, torch.Tensor,
+                                                                                   torch.Tensor, torch.Tensor,
+                                                                                   torch.Tensor]:
+    """RasterizeGaussiansCUDA (rasterize_points.cu:36-115).  `context` (keyword-only, not part of the
+    reference signature) selects whose capacity hint is used; default: the calling thread's current one."""
+    context = context or current_context()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -156,7 +201,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         key = (dev.index, H, W)
-        hint = _capacity_hint.get(key, 0) if _USE_HINT else 0
+        hint = context.capacity_hint.get(key, 0) if _USE_HINT else 0
         reserve = lib.sgr_geometry_bytes(P) + lib.sgr_image_bytes(W, H) + 1024
         if hint:
             reserve += lib.sgr_binning_bytes(hint)
@@ -175,7 +220,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         R = int(rendered.value)
         if P:
             # next view's optimistic capacity: 25% headroom, rounded to 1M instances (stable sizes)
-            _capacity_hint[key] = _round_up(int(R * 1.25) + 65536, 1 << 20)
+            context.capacity_hint[key] = _round_up(int(R * 1.25) + 65536, 1 << 20)
     geom_t, binning_t, img_t = arena.get("geom"), arena.get("binning"), arena.get("img")
     arena.release()
     return R, out_color, radii, geom_t, binning_t, img_t
@@ -193,8 +238,10 @@ FACTOR_HOOK = None
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh,
-                                 degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
+                                 degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, *,
+                                 context: Context = None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:118-196)."""
+    context = context or current_context()
     dev = means3D.device
     P, H, W = means3D.size(0), dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0

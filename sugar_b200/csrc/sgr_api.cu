@@ -178,6 +178,11 @@ __global__ void inspect_bin_kernel(int T, const uint32_t *__restrict__ tile_star
 __global__ void mark_visible_kernel(int P, const float *__restrict__ means, const float *__restrict__ vm,
                                     uint8_t *__restrict__ present);  // sgr_forward.cu
 
+#ifdef SGR_BLEND_STATS
+int read_fwd_stats(unsigned long long *out, int reset);  // sgr_forward.cu
+int read_bwd_stats(unsigned long long *out, int reset);  // sgr_backward.cu
+#endif
+
 }  // namespace sgr
 
 using namespace sgr;
@@ -240,6 +245,14 @@ int sgr_profile_read(float *total_ms, int *counts)
     g_prof_n = 0;
     return SGR_OK;
 }
+#ifdef SGR_BLEND_STATS
+SGR_API int sgr_debug_blend_stats(unsigned long long *out16, int reset)
+{
+    int rc = sgr::read_fwd_stats(out16, reset);
+    if (rc) return rc;
+    return sgr::read_bwd_stats(out16 + 8, reset);
+}
+#endif
 const char *sgr_version(void) { return "sugar_b200 0.1 (sm_100a)"; }
 
 size_t sgr_geometry_bytes(int32_t P) { return GeomState::bytes((size_t)(P < 0 ? 0 : P)); }

@@ -14,7 +14,13 @@
 // Gaussian folds the (at most 8) warp rows and issues two 16-byte vector reductions
 // (red.global.add.v4.f32 -> SASS REDG.E.ADD.F32x4) plus one scalar: 3 L2 operations per
 // (tile, Gaussian) instead of 9 per (pixel, Gaussian).
+#include <mutex>
+
 #include "sgr_internal.cuh"
+
+#ifndef SGR_BWD_CHUNKED
+#define SGR_BWD_CHUNKED 1
+#endif
 
 namespace sgr {
 
@@ -244,6 +250,19 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__r
 //    batch b+1 are in flight while batch b is processed, so the CTA-wide barriers at the batch
 //    boundary no longer expose the plist -> record load chain (20 % of the stall samples before).
 // ------------------------------------------------------------------------------------------------
+#ifdef SGR_BLEND_STATS
+__device__ unsigned long long g_bwd_stats[8];
+#define BWD_STAT(k, v) atomicAdd(&g_bwd_stats[k], (unsigned long long)(v))
+int read_bwd_stats(unsigned long long *out, int reset)
+{
+    SGR_CUDA(cudaMemcpyFromSymbol(out, g_bwd_stats, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {};
+        SGR_CUDA(cudaMemcpyToSymbol(g_bwd_stats, z, sizeof(z)));
+    }
+    return SGR_OK;
+}
+#endif
 constexpr int CH = 16;             // splats per chunk
 constexpr int CH_PITCH = CH + 1;   // float2 elements per pixel row: odd pitch = conflict-free transpose
 // per-warp chunk scratch (bytes from its base): pair[32][CH_PITCH] float2 | meta[CH] x 48 B | dp[32] float4
@@ -463,6 +482,9 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
         __syncthreads();
 #endif
         const int m = min(BWD_B, n - b0);
+#ifdef SGR_BLEND_STATS
+        if (tid == 0) BWD_STAT(6, m);
+#endif
         const int jmin = n - b0 - warp_last;  // first batch slot whose list position is < warp_last
         // list position of slot j is n-1-(b0+j); it precedes this pixel's last contributor iff j > jlim
         const int jlim = n - 1 - b0 - last_contributor;
@@ -481,6 +503,21 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
                 const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                 const float power = splat_power(dx, dy, A.z, A.w, B.x);
                 bool valid = j > jlim && !(power > 0.0f) && !(power < B.y);
+#ifdef SGR_BLEND_STATS
+                {
+                    const bool hit = valid && !(fminf(0.99f, __fmul_rn(B.z, expf(power))) < 1.0f / 255.0f);
+                    const unsigned mc = __ballot_sync(0xffffffffu, valid), mh = __ballot_sync(0xffffffffu, hit);
+                    const unsigned ml = __ballot_sync(0xffffffffu, j > jlim);
+                    if (lane == 0) {
+                        BWD_STAT(0, 1);
+                        BWD_STAT(1, mc != 0);
+                        BWD_STAT(2, mh != 0);
+                        BWD_STAT(3, __popc(mc));
+                        BWD_STAT(4, __popc(mh));
+                        BWD_STAT(5, __popc(ml));
+                    }
+                }
+#endif
                 if (!__any_sync(0xffffffffu, valid)) continue;
                 // S = dL/dG * G and the colour weight alpha*T of this pair; zero for lanes without one.
                 // (A candidate warp almost always keeps a contributing lane -- 8 554 776 of 8 554 918 on
@@ -1035,6 +1072,24 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     ImageState img = ImageState::carve((void *)image_buffer, W, H);
     BinState bin = BinState::carve((void *)binning_buffer, (size_t)num_rendered);
     float *gacc = (float *)align_up((size_t)grad_scratch);
+    {
+        // opt in to > 48 KB of dynamic shared memory once per device (the call is not free); calls
+        // may come from several threads (autograd engine threads of different devices)
+        static std::mutex mu;
+        static bool attr_set[64] = {};
+        int dev = 0;
+        SGR_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+#if SGR_BWD_CHUNKED
+            SGR_CUDA(cudaFuncSetAttribute(blend_backward_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)BWD_SMEM_BYTES));
+#endif
+            SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+    }
     SGR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 48, st));
     if (num_rendered > 0) {
 #ifndef SGR_BWD_CHUNKED
@@ -1043,17 +1098,6 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
 #if SGR_BWD_CHUNKED
 #define SGR_BLEND_BWD_KERNEL blend_backward_chunked_kernel
 #define SGR_BLEND_BWD_SMEM BWD_SMEM_BYTES
-        {
-            // opt in to > 48 KB of dynamic shared memory once per device (the call is not free)
-            static bool attr_set[64] = {};
-            int dev = 0;
-            SGR_CUDA(cudaGetDevice(&dev));
-            if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-                SGR_CUDA(cudaFuncSetAttribute(blend_backward_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)BWD_SMEM_BYTES));
-                if (dev >= 0 && dev < 64) attr_set[dev] = true;
-            }
-        }
 #else
 #define SGR_BLEND_BWD_KERNEL blend_backward_kernel
 #define SGR_BLEND_BWD_SMEM 0
@@ -1103,13 +1147,6 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     a.dsh = dL_dsh;
     a.dscales = dL_dscales;
     a.drots = dL_drotations;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    SGR_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set[dev] = true;
-    }
     auto al16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
     a.bulk_ok = al16(gacc) && al16(g->means3D) && (!g->scales || al16(g->scales)) && (!g->rotations || al16(g->rotations)) &&
                 (!g->cov3D_precomp || al16(g->cov3D_precomp));

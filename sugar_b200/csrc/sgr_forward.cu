@@ -18,6 +18,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <mutex>
+#include <vector>
+
 #include "sgr_internal.cuh"
 
 namespace sgr {
@@ -779,6 +782,12 @@ __global__ void __launch_bounds__(BK_T) tile_sort_bucket_kernel(const uint32_t *
 // ------------------------------------------------------------------------------------------------
 constexpr int BLEND_T = 256;
 
+// -DSGR_BLEND_STATS: count what the blend loops do (scripts/blend_stats.py); never in the shipped build
+#ifdef SGR_BLEND_STATS
+__device__ unsigned long long g_fwd_stats[8];
+#define FWD_STAT(k, v) atomicAdd(&g_fwd_stats[k], (unsigned long long)(v))
+#endif
+
 // Double-buffered records (as in the backward) measured slower here: 0.708 vs 0.673 ms -- most tiles
 // saturate before their last batch, so the prefetched batch is wasted work.  Kept for A/B.
 #ifndef SGR_FWD_PIPELINED
@@ -871,6 +880,9 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
 #endif
         __syncthreads();
         const uint32_t base_pos = b0 - lo;
+#ifdef SGR_BLEND_STATS
+        if (tid == 0) FWD_STAT(6, min((uint32_t)BLEND_T, hi - b0));  // records staged
+#endif
         if (!__all_sync(0xffffffffu, done != 0u)) {
 #pragma unroll 1
             for (int k = 0; k < BLEND_T / 32; k++) {
@@ -879,6 +891,25 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
                 while (mw) {
                     const int j = (k << 5) + __ffs(mw) - 1;
                     mw &= mw - 1;
+#ifdef SGR_BLEND_STATS
+                    {
+                        const float4 A = lds128(sa + j * 16);
+                        const float4 B = lds128(sb + j * 16);
+                        const float power = splat_power(__fsub_rn(A.x, pxf), __fsub_rn(A.y, pyf), A.z, A.w, B.x);
+                        const bool cand = !done && !(power > 0.0f || power < B.y);
+                        const bool hit = cand && !(fminf(0.99f, __fmul_rn(B.z, expf(power))) < 1.0f / 255.0f);
+                        const unsigned mc = __ballot_sync(0xffffffffu, cand), mh = __ballot_sync(0xffffffffu, hit);
+                        const unsigned ml = __ballot_sync(0xffffffffu, !done);
+                        if (lane == 0) {
+                            FWD_STAT(0, 1);            // strip-splat visits
+                            FWD_STAT(1, mc != 0);      // ... with a lane that passes the power test
+                            FWD_STAT(2, mh != 0);      // ... with a lane that contributes
+                            FWD_STAT(3, __popc(mc));   // lanes passing the power test
+                            FWD_STAT(4, __popc(mh));   // contributing (pixel, splat) pairs
+                            FWD_STAT(5, __popc(ml));   // live lanes over all visits
+                        }
+                    }
+#endif
                     if (done) continue;
                     const float4 A = lds128(sa + j * 16);
                     const float4 B = lds128(sb + j * 16);
@@ -913,6 +944,18 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
     }
 }
 
+#ifdef SGR_BLEND_STATS
+int read_fwd_stats(unsigned long long *out, int reset)
+{
+    SGR_CUDA(cudaMemcpyFromSymbol(out, g_fwd_stats, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {};
+        SGR_CUDA(cudaMemcpyToSymbol(g_fwd_stats, z, sizeof(z)));
+    }
+    return SGR_OK;
+}
+#endif
+
 __global__ void mark_visible_kernel(int P, const float *__restrict__ means, const float *__restrict__ vm,
                                     uint8_t *__restrict__ present)
 {
@@ -925,14 +968,22 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means, cons
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-struct DeviceSlot {
+// Host-side per-call state: one pinned word (the instance count's read-back) and one event.  Calls
+// may overlap on one device (two streams / two threads), so every call takes its own slot from a small
+// per-device pool and returns it when it is done; the one-time function attributes are set under the
+// same lock.
+struct CallSlot {
     uint32_t *pinned = nullptr;
     cudaEvent_t ev = nullptr;
+};
+struct DevicePool {
+    std::mutex mu;
+    std::vector<CallSlot> free_slots;
     bool attrs_set = false;
 };
-static DeviceSlot g_slots[64];
+static DevicePool g_pools[64];
 
-static int get_slot(DeviceSlot **out)
+static int current_pool(DevicePool **out)
 {
     int dev = 0;
     SGR_CUDA(cudaGetDevice(&dev));
@@ -940,20 +991,40 @@ static int get_slot(DeviceSlot **out)
         set_error("device ordinal %d out of range", dev);
         return SGR_EINVAL;
     }
-    DeviceSlot &s = g_slots[dev];
-    if (!s.pinned) {
-        SGR_CUDA(cudaHostAlloc((void **)&s.pinned, 4096, cudaHostAllocDefault));
-        SGR_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
-    }
-    if (!s.attrs_set) {
+    *out = &g_pools[dev];
+    return SGR_OK;
+}
+
+static int acquire_slot(DevicePool *pool, CallSlot *slot)
+{
+    std::lock_guard<std::mutex> lock(pool->mu);
+    if (!pool->attrs_set) {
         SGR_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SGR_CUDA(cudaFuncSetAttribute(tile_sort_merge_kernel<8192, 2048>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-        s.attrs_set = true;
+        pool->attrs_set = true;
     }
-    *out = &s;
+    if (!pool->free_slots.empty()) {
+        *slot = pool->free_slots.back();
+        pool->free_slots.pop_back();
+        return SGR_OK;
+    }
+    SGR_CUDA(cudaHostAlloc((void **)&slot->pinned, 64, cudaHostAllocDefault));
+    SGR_CUDA(cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming));
     return SGR_OK;
 }
+
+struct SlotLease {  // returns the slot to its pool on every exit path
+    DevicePool *pool = nullptr;
+    CallSlot slot;
+    ~SlotLease()
+    {
+        if (pool && slot.pinned) {
+            std::lock_guard<std::mutex> lock(pool->mu);
+            pool->free_slots.push_back(slot);
+        }
+    }
+};
 
 static inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
@@ -994,9 +1065,12 @@ int launch_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc geom_all
                    int32_t *radii, int64_t capacity_hint, int64_t *num_rendered, cudaStream_t st)
 {
     const int P = g->P, W = view->image_width, H = view->image_height;
-    DeviceSlot *slot;
-    int rc = get_slot(&slot);
+    SlotLease lease;
+    int rc = current_pool(&lease.pool);
     if (rc) return rc;
+    rc = acquire_slot(lease.pool, &lease.slot);
+    if (rc) return rc;
+    CallSlot *slot = &lease.slot;
 
     ViewConsts v;
     v.viewmatrix = view->viewmatrix;

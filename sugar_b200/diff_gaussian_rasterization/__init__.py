@@ -41,12 +41,12 @@ def _snapshot(args):
     return tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
 
 
-def _call_with_dump(fn, args, debug, dump_name, what):
+def _call_with_dump(fn, args, debug, dump_name, what, **kw):
     if not debug:
-        return fn(*args)
+        return fn(*args, **kw)
     saved = _snapshot(args)
     try:
-        return fn(*args)
+        return fn(*args, **kw)
     except Exception:
         torch.save(saved, dump_name)
         print(f"\nAn error occured in {what}. Please forward {dump_name} for debugging.")
@@ -64,8 +64,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
                 rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        # the op's cross-call state (capacity hint, view-parallel exchange) travels with the autograd
+        # node: the backward runs on autograd's engine thread, where thread-local selection is not visible
+        ctx.sgr_context = _C.current_context()
         num_rendered, color, radii, geom, binning, img = _call_with_dump(
-            _C.rasterize_gaussians, args, rs.debug, "snapshot_fw.dump", "forward")
+            _C.rasterize_gaussians, args, rs.debug, "snapshot_fw.dump", "forward", context=ctx.sgr_context)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning,
@@ -81,7 +84,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, sh, rs.sh_degree, rs.campos,
                 geom, ctx.num_rendered, binning, img, rs.debug)
         (g_means2D, g_colors, g_opacities, g_means3D, g_cov3D, g_sh, g_scales, g_rotations) = _call_with_dump(
-            _C.rasterize_gaussians_backward, args, rs.debug, "snapshot_bw.dump", "backward")
+            _C.rasterize_gaussians_backward, args, rs.debug, "snapshot_bw.dump", "backward", context=ctx.sgr_context)
         return (g_means3D, g_means2D, g_sh, g_colors, g_opacities, g_scales, g_rotations, g_cov3D, None)
 
 

@@ -48,3 +48,26 @@ def test_load_peaks_returns_a_positive_hbm_peak():
     import bench
     peak, src = bench.load_peaks()
     assert peak > 1000 and isinstance(src, str)
+
+
+def test_reference_arm_helpers_do_not_map_the_product_library():
+    """bench.py --impl reference must not import sugar_b200 (which maps libsugar_b200.so): the scene generator is
+    loaded by path and tests/helpers.py stays import-free of the package at module level."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests'); import bench, helpers; "
+            "sc = bench.load_scenes().make_scene(100, 32, 16, seed=0); assert sc.means3D.shape == (100, 3); "
+            "assert not any(m == 'sugar_b200' or m.startswith('sugar_b200.') for m in sys.modules), "
+            "[m for m in sys.modules if 'sugar' in m]; "
+            "maps = open('/proc/self/maps').read(); assert 'libsugar_b200' not in maps") % (ROOT, ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True, timeout=120)
+
+
+def test_cpu_sample_worker_and_factor_mode_bytes():
+    import bench
+    dt = bench._cpu_sample((0, 300, 48, 32, 3))
+    assert 0 < dt < 30
+    P, V, R, W, H = 1000, 800, 3000, 64, 64
+    full = bench.algorithmic_bytes(P, V, R, W, H, 16, 3)["preprocess_backward"]
+    fac = bench.algorithmic_bytes(P, V, R, W, H, 16, 3, sh_written=False)["preprocess_backward"]
+    assert full - fac == P * 192
+    assert bench.KERNEL_BOUND["blend_backward"] == "fp32-issue" and bench.KERNEL_BOUND["preprocess"] == "hbm"

@@ -1,0 +1,141 @@
+"""Element-wise parity with the UNMODIFIED reference CUDA build (oracle/_ref) at every rasterizer
+configuration BASELINE.json names, through the public module on the same tensors in the same process:
+
+    C2        100k Gaussians,   800x800,  SH degree 2
+    C3          1M Gaussians, 1920x1080,  SH degree 3      (also tests/test_gpu_parity.py::test_full_size_properties)
+    headline    3M Gaussians, 1920x1080,  SH degree 3      (the workload bench.py times)
+    C4          3M mesh-bound (flat first axis, refine.py), 1600x1200, SH degree 3
+    C5          6M Gaussians, 3840x2160,  SH degree 3      (one view of the 8-view batch)
+
+Bars: num_rendered, radii, n_contrib equal; image and final_T bit-identical; every gradient
+|a-b|_inf / |b|_inf <= 1e-4 (BASELINE.json).  Mesh-bound Gaussians (a 1e-6 axis) are the documented
+exception for dL_dscales / dL_drotations: there the reference's own per-Gaussian chain amplifies the fp32
+summation-order noise of the blend accumulators by ~1e3, so those two tensors are held to 5x the larger
+of (the reference's own run-to-run difference, the chain's measured sensitivity to 1e-6 accumulator noise
+on a 1/64-area sample of the same distribution -- helpers.grad_sensitivity, CPU oracle).
+
+Also here: the capacity-overflow re-run of the forward (rasterizer_impl.cu:281-317 sizes the binning
+buffers after a host wait; ours guesses and must re-run binning when the guess was too small) and two
+forwards in flight on two streams.
+"""
+import numpy as np
+import pytest
+
+import helpers as h
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 1e-4
+
+CONFIGS = [
+    # id, P, W, H, sh_degree, mesh_bound
+    ("c2_100k_800x800_sh2", 100_000, 800, 800, 2, False),
+    ("c3_1m_1080p_sh3", 1_000_000, 1920, 1080, 3, False),
+    ("headline_3m_1080p_sh3", 3_000_000, 1920, 1080, 3, False),
+    ("c4_3m_meshbound_1600x1200_sh3", 3_000_000, 1600, 1200, 3, True),
+    ("c5_6m_4k_sh3", 6_000_000, 3840, 2160, 3, False),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_baseline_config_matches_reference_build(cfg):
+    import torch
+    if not h.have_ref():
+        pytest.skip("oracle/_ref not built")
+    name, P, W, H, deg, mesh = cfg
+    from sugar_b200 import _C, diff_gaussian_rasterization as ours, scenes
+    ref = h.load_ref_module()
+    sc = scenes.make_scene(P, W, H, seed=0, mesh_bound=mesh)
+    dL = scenes.upstream_grad(W, H)
+    bg = (0.0, 0.0, 0.0)
+    a = h.run_module(ours, sc, bg, dL, use_sh=True, sh_degree=deg)
+    b = h.run_module(ref, sc, bg, dL, use_sh=True, sh_degree=deg)
+    assert a["num_rendered"] == b["num_rendered"]
+    assert torch.equal(a["radii"], b["radii"]), "radii differ"
+    assert torch.equal(a["color"].view(torch.int32), b["color"].view(torch.int32)), "image not bit-exact"
+    st = _C.inspect_state(P, W, H, a["num_rendered"], a["geom"], a["binning"], a["img"])
+    rs = h.decode_ref_state(b, P, W, H)
+    assert torch.equal(st["n_contrib"], rs["n_contrib"]), "n_contrib differs"
+    assert torch.equal(st["final_T"].view(torch.int32), rs["final_T"].view(torch.int32)), "final_T not bit-exact"
+    assert torch.equal(st["point_list"], rs["point_list"]), "sorted Gaussian ids differ"
+    assert torch.equal(st["keys"], rs["keys"]), "sorted 64-bit keys differ"
+    assert torch.equal(st["ranges"], rs["ranges"]), "tile ranges differ"
+    del st, rs
+    assert set(a["grads"]) == set(b["grads"])
+    errs = {k: h.rel_err(a["grads"][k].cpu().numpy(), b["grads"][k].cpu().numpy()) for k in b["grads"]}
+    bad = {k: e for k, e in errs.items() if e > GRAD_RTOL}
+    if bad and mesh:
+        b2 = h.run_module(ref, sc, bg, dL, use_sh=True, sh_degree=deg)
+        noise = {k: h.rel_err(b2["grads"][k].cpu().numpy(), b["grads"][k].cpu().numpy()) for k in bad}
+        small = scenes.make_scene(P // 64, W // 8, H // 8, seed=0, mesh_bound=True)
+        sens = h.grad_sensitivity(small, bg, scenes.upstream_grad(W // 8, H // 8), use_sh=True, sh_degree=deg)
+        bad = {k: e for k, e in bad.items()
+               if k not in ("scales", "rotations") or e > 5.0 * max(noise[k], sens.get(k, 0.0))}
+    assert not bad, f"{name}: gradient rel err over the bar: {bad} (all: {errs})"
+
+
+def _forward_state(mod, sc, ctx=None):
+    from sugar_b200 import _C
+    if ctx is None:
+        return h.run_module(mod, sc, (0.1, 0.2, 0.3), None, use_sh=True, sh_degree=3)
+    with _C.use_context(ctx):
+        return h.run_module(mod, sc, (0.1, 0.2, 0.3), None, use_sh=True, sh_degree=3)
+
+
+def test_capacity_overflow_reruns_binning():
+    """A capacity hint far below the true instance count: the guarded first attempt must be a no-op and the
+    re-run (exact size) must give the same keys / ids / ranges / image as a run without any hint."""
+    import torch
+    from sugar_b200 import _C, diff_gaussian_rasterization as ours, scenes
+    P, W, H = 200_000, 640, 360
+    sc = scenes.make_scene(P, W, H, seed=11, camera="posed")
+    dL = scenes.upstream_grad(W, H)
+    cold = _C.Context()                       # no hint: waits for the count like the reference
+    a = _forward_state(ours, sc, cold)
+    R = a["num_rendered"]
+    assert R > (1 << 16)
+    key = (torch.cuda.current_device(), H, W)
+    assert cold.capacity_hint[key] >= R       # the next view's optimistic capacity
+    tiny = _C.Context()
+    tiny.capacity_hint[key] = 1 << 12         # forces the overflow path
+    with _C.use_context(tiny):
+        b = h.run_module(ours, sc, (0.1, 0.2, 0.3), dL, use_sh=True, sh_degree=3)
+    assert b["num_rendered"] == R and tiny.capacity_hint[key] >= R
+    sa = _C.inspect_state(P, W, H, R, a["geom"], a["binning"], a["img"])
+    sb = _C.inspect_state(P, W, H, R, b["geom"], b["binning"], b["img"])
+    for k in ("keys", "point_list", "ranges", "n_contrib", "tiles_touched"):
+        assert torch.equal(sa[k], sb[k]), k
+    assert torch.equal(a["color"], b["color"]) and torch.equal(a["radii"], b["radii"])
+    # backward after a re-run forward reads the right ranges: compare with a hinted (no overflow) run
+    with _C.use_context(cold):
+        c = h.run_module(ours, sc, (0.1, 0.2, 0.3), dL, use_sh=True, sh_degree=3)
+    for k in c["grads"]:
+        assert h.rel_err(b["grads"][k].cpu().numpy(), c["grads"][k].cpu().numpy()) <= GRAD_RTOL, k
+    # a hint that is too small by ONE instance overflows too; one that is exact does not change anything
+    for cap in (R - 1, R):
+        ctx = _C.Context()
+        ctx.capacity_hint[key] = cap
+        d = _forward_state(ours, sc, ctx)
+        assert d["num_rendered"] == R and torch.equal(d["color"], a["color"]), cap
+
+
+def test_two_forwards_in_flight_on_two_streams():
+    """Two different views enqueued back to back on two streams (per-call pinned slot + event on the C
+    side): each must report its own instance count and image."""
+    import torch
+    from sugar_b200 import _C, diff_gaussian_rasterization as ours, scenes
+    sc1 = scenes.make_scene(150_000, 640, 360, seed=21, camera="posed")
+    sc2 = scenes.make_scene(60_000, 640, 360, seed=22, camera="posed", px_sigma=3.0)
+    want1, want2 = _forward_state(ours, sc1, _C.Context()), _forward_state(ours, sc2, _C.Context())
+    assert want1["num_rendered"] != want2["num_rendered"]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    c1, c2 = _C.Context(), _C.Context()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            g1 = _forward_state(ours, sc1, c1)
+        with torch.cuda.stream(s2):
+            g2 = _forward_state(ours, sc2, c2)
+        torch.cuda.synchronize()
+        assert g1["num_rendered"] == want1["num_rendered"] and g2["num_rendered"] == want2["num_rendered"]
+        assert torch.equal(g1["color"], want1["color"]) and torch.equal(g2["color"], want2["color"])

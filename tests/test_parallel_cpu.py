@@ -26,9 +26,14 @@ def _worker(rank, world, port, q):
     arena = parallel.GradArena(P, M, "cpu")
     arena.all_reduce_from(params, 1.0 / world)
     arena.unpack_to(params)
-    q.put((rank, {k: v for k, v in local.items()}, {k: p.grad.clone() for k, p in params.items()},
-           parallel.shard_views(8, rank, world)))
+    # numpy, not torch tensors: a tensor travels as a file descriptor that the parent must still be able
+    # to open after this process has exited (ConnectionResetError when the worker wins the race)
+    q.put((rank, {k: v.numpy().copy() for k, v in local.items()},
+           {k: p.grad.detach().numpy().copy() for k, p in params.items()}, parallel.shard_views(8, rank, world)))
+    dist.barrier()
     dist.destroy_process_group()
+    q.close()
+    q.join_thread()  # the feeder thread has written everything before the process exits
 
 
 def test_arena_allreduce_gloo_world2():
@@ -50,7 +55,7 @@ def test_arena_allreduce_gloo_world2():
     for k in res[0][1]:
         mean = (res[0][1][k] + res[1][1][k]) / world
         for r in res:
-            assert torch.allclose(r[2][k], mean, atol=1e-7), k
+            assert torch.allclose(torch.from_numpy(r[2][k]), torch.from_numpy(mean), atol=1e-7), k
     assert res[0][3] == [0, 2, 4, 6] and res[1][3] == [1, 3, 5, 7]
     assert 59 * 50 == sum(n for _, n in __import__("sugar_b200.parallel", fromlist=["x"]).GradArena(50, 16, "cpu").offsets.values())
 
