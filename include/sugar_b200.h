@@ -141,12 +141,15 @@ SGR_API size_t sgr_backward_scratch_bytes(int32_t P);
  * (GeometryState / BinningState / ImageState, rasterizer_impl.h:30-63).  Any output may be NULL.
  *   depths f32[P], means2D f32[P,2], conic_opacity f32[P,4], rgb f32[P,3], clamped u8[P,3],
  *   tiles_touched u32[P]; keys u64[R] = (tile<<32 | depth bits) in sorted order,
- *   point_list u32[R]; ranges u32[T,2]; final_T f32[H,W]; n_contrib u32[H,W]. */
+ *   point_list u32[R]; ranges u32[T,2]; final_T f32[H,W]; n_contrib u32[H,W];
+ *   footprint u8[R]: per sorted instance, which of its tile's eight 8x4-pixel blocks (bit = band*2 + half)
+ *   the splat can reach with alpha >= 1/255 -- this library's own culling state, not a reference array
+ *   (0xff when the list carries no masks, i.e. P > 2^24). */
 SGR_API int sgr_inspect_state(int32_t P, int32_t width, int32_t height, int64_t num_rendered,
                       const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
                       float *depths, float *means2D, float *conic_opacity, float *rgb, uint8_t *clamped,
                       uint32_t *tiles_touched, uint64_t *keys, uint32_t *point_list, uint32_t *ranges,
-                      float *final_T, uint32_t *n_contrib, void *stream);
+                      float *final_T, uint32_t *n_contrib, uint8_t *footprint, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * SuGaR surface-regularisation field: fused K-neighbour gather + anisotropic density / SDF.

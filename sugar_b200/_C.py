@@ -323,14 +323,17 @@ def inspect_state(P, W, H, R, geomBuffer, binningBuffer, imageBuffer):
                keys=torch.zeros(max(R, 1), dtype=torch.int64, device=dev),
                point_list=torch.zeros(max(R, 1), dtype=torch.int32, device=dev),
                ranges=torch.zeros((T, 2), dtype=torch.int32, device=dev),
-               final_T=f(H, W), n_contrib=torch.zeros((H, W), dtype=torch.int32, device=dev))
+               final_T=f(H, W), n_contrib=torch.zeros((H, W), dtype=torch.int32, device=dev),
+               footprint=torch.zeros(max(R, 1), dtype=torch.uint8, device=dev))
     with torch.cuda.device(dev):
         check(lib.sgr_inspect_state(P, W, H, R, geomBuffer.data_ptr(), binningBuffer.data_ptr(), imageBuffer.data_ptr(),
                                     out["depths"].data_ptr(), out["means2D"].data_ptr(),
                                     out["conic_opacity"].data_ptr(), out["rgb"].data_ptr(), out["clamped"].data_ptr(),
                                     out["tiles_touched"].data_ptr(), out["keys"].data_ptr(),
                                     out["point_list"].data_ptr(), out["ranges"].data_ptr(), out["final_T"].data_ptr(),
-                                    out["n_contrib"].data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+                                    out["n_contrib"].data_ptr(), out["footprint"].data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream))
     out["keys"] = out["keys"][:R]
     out["point_list"] = out["point_list"][:R]
+    out["footprint"] = out["footprint"][:R]
     return out

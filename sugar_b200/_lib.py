@@ -57,7 +57,7 @@ PROTOTYPES = {
     "sgr_binning_bytes": (C.c_size_t, [C.c_int64]),
     "sgr_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "sgr_backward_scratch_bytes": (C.c_size_t, [C.c_int32]),
-    "sgr_inspect_state": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 15),
+    "sgr_inspect_state": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 16),
     "sgr_field_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_normal_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_normal_loss_forward": (C.c_int, [C.c_int32] * 3 + [C.c_void_p] * 10),

@@ -69,6 +69,15 @@ void prof_end(cudaStream_t st)
     g_prof_n++;
 }
 
+bool ids_packed(int P)
+{
+    static const bool force_unpacked = [] {
+        const char *e = getenv("SGR_FORCE_UNPACKED_IDS");
+        return e && e[0] == '1';
+    }();
+    return !force_unpacked && P <= SGR_PACKED_MAX_P;
+}
+
 static int validate(const SgrView *view, const SgrGaussians *g, bool forward)
 {
     if (!view || !g) {
@@ -158,8 +167,9 @@ __global__ void inspect_geom_kernel(int P, GeomState g, const int32_t *radii_unu
     }
 }
 
-__global__ void inspect_bin_kernel(int T, const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ plist,
-                                   const float *__restrict__ depth, uint64_t *keys, uint32_t *point_list, uint32_t *ranges)
+__global__ void inspect_bin_kernel(int T, int packed, const uint32_t *__restrict__ tile_start,
+                                   const uint32_t *__restrict__ plist, const float *__restrict__ depth, uint64_t *keys,
+                                   uint32_t *point_list, uint32_t *ranges, uint8_t *footprint)
 {
     const int t = blockIdx.x;
     const uint32_t lo = tile_start[t], hi = tile_start[t + 1];
@@ -169,8 +179,9 @@ __global__ void inspect_bin_kernel(int T, const uint32_t *__restrict__ tile_star
         ranges[2 * t + 1] = hi > lo ? hi : 0u;
     }
     for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
-        const uint32_t id = plist[k];
+        const uint32_t w = plist[k], id = packed ? (w >> 8) : w;
         if (point_list) point_list[k] = id;
+        if (footprint) footprint[k] = packed ? (uint8_t)(w & 0xffu) : (uint8_t)0xffu;
         if (keys) keys[k] = ((uint64_t)t << 32) | __float_as_uint(depth[id]);
     }
 }
@@ -332,7 +343,8 @@ int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, c
 int sgr_inspect_state(int32_t P, int32_t width, int32_t height, int64_t num_rendered, const void *geom_buffer,
                       const void *binning_buffer, const void *image_buffer, float *depths, float *means2D,
                       float *conic_opacity, float *rgb, uint8_t *clamped, uint32_t *tiles_touched, uint64_t *keys,
-                      uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib, void *stream)
+                      uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib, uint8_t *footprint,
+                      void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (P <= 0 || !geom_buffer || !image_buffer) {
@@ -344,9 +356,10 @@ int sgr_inspect_state(int32_t P, int32_t width, int32_t height, int64_t num_rend
     const int T = ((width + 15) / 16) * ((height + 15) / 16);
     inspect_geom_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, geom, nullptr, depths, means2D, conic_opacity, rgb, clamped,
                                                          tiles_touched);
-    if (binning_buffer && (keys || point_list || ranges)) {
+    if (binning_buffer && (keys || point_list || ranges || footprint)) {
         BinState bin = BinState::carve((void *)binning_buffer, (size_t)num_rendered);
-        inspect_bin_kernel<<<T, 128, 0, st>>>(T, img.tile_start, bin.plist, geom.depth, keys, point_list, ranges);
+        inspect_bin_kernel<<<T, 128, 0, st>>>(T, ids_packed(P) ? 1 : 0, img.tile_start, bin.plist, geom.depth, keys,
+                                              point_list, ranges, footprint);
     }
     const size_t npix = (size_t)width * height;
     if (final_T) SGR_CUDA(cudaMemcpyAsync(final_T, img.final_T, npix * 4, cudaMemcpyDeviceToDevice, st));

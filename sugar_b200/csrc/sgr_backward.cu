@@ -9,18 +9,13 @@
 //                              only the 48 B/Gaussian accumulator record is memset.
 //
 // The reference issues 9 global atomicAdd per contributing (pixel, Gaussian) pair, up to 256-way
-// contended.  Here every warp reduces its 32 pixels with a 14-shuffle multi-value butterfly,
-// parks the 9 partial sums in its private shared-memory row, and after each batch one thread per
-// Gaussian folds the (at most 8) warp rows and issues two 16-byte vector reductions
-// (red.global.add.v4.f32 -> SASS REDG.E.ADD.F32x4) plus one scalar: 3 L2 operations per
-// (tile, Gaussian) instead of 9 per (pixel, Gaussian).
+// contended.  Here a warp parks the two per-pair scalars of its 32 pixels in shared memory, reduces 16
+// splats at a time in a transposed pass and issues two 16-byte vector reductions
+// (red.global.add.v4.f32 -> SASS REDG.E.ADD.F32x4) plus one scalar per (8x4 block, Gaussian): 3 L2
+// operations instead of 9 per (pixel, Gaussian).
 #include <mutex>
 
 #include "sgr_internal.cuh"
-
-#ifndef SGR_BWD_CHUNKED
-#define SGR_BWD_CHUNKED 1
-#endif
 
 namespace sgr {
 
@@ -34,221 +29,25 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Sum 8 values across the warp with 9 shuffles (recursive halving), result k lands in lane 4k.
-__device__ __forceinline__ float warp_reduce8(const float (&v)[8], unsigned lane)
-{
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    float w[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const float send = b4 ? v[k] : v[k + 4];
-        const float keep = b4 ? v[k + 4] : v[k];
-        w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    float u[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const float send = b3 ? w[k] : w[k + 2];
-        const float keep = b3 ? w[k + 2] : w[k];
-        u[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    float t;
-    {
-        const float send = b2 ? u[0] : u[1];
-        const float keep = b2 ? u[1] : u[0];
-        t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    return t;  // lane L holds value index (b4?4:0)+(b3?2:0)+(b2?1:0)
-}
-
-__global__ void __launch_bounds__(256) blend_backward_kernel(const uint32_t *__restrict__ tile_start,
-                                                             const uint32_t *__restrict__ plist,
-                                                             const float4 *__restrict__ rec, int W, int H, int gx,
-                                                             const float *__restrict__ bg,
-                                                             const float *__restrict__ final_Ts,
-                                                             const uint32_t *__restrict__ n_contrib,
-                                                             const float *__restrict__ dL_dpixels, float *__restrict__ gacc)
-{
-    __shared__ float4 s_a[BWD_B];
-    __shared__ float4 s_b[BWD_B];
-    __shared__ float2 s_c[BWD_B];
-    __shared__ uint32_t s_id[BWD_B];
-    __shared__ float s_acc[BWD_NW][BWD_B][9];
-    __shared__ uint32_t s_member[BWD_NW][BWD_B / 32];  // splats whose footprint reaches strip w
-    __shared__ uint32_t s_touched[BWD_NW][BWD_B / 32]; // splats warp w produced partial sums for
-
-    const int tile = blockIdx.y * gx + blockIdx.x;
-    const int tid = threadIdx.y * SGR_TILE + threadIdx.x;
-    const unsigned lane = tid & 31, wid = tid >> 5;
-    const uint32_t pxi = blockIdx.x * SGR_TILE + threadIdx.x, pyi = blockIdx.y * SGR_TILE + threadIdx.y;
-    const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
-    const float pxf = (float)pxi, pyf = (float)pyi;
-    const float tx0 = (float)(blockIdx.x * SGR_TILE), ty0 = (float)(blockIdx.y * SGR_TILE);
-    const uint32_t lo = tile_start[tile], hi = tile_start[tile + 1];
-    if (hi == lo) return;
-    __shared__ int s_tile_last;
-    if (tid == 0) s_tile_last = 0;
-
-    const size_t pix = (size_t)pyi * W + pxi, plane = (size_t)H * W;
-    const float T_final = inside ? final_Ts[pix] : 0.0f;
-    float T = T_final;
-    const int last_contributor = inside ? (int)n_contrib[pix] : 0;
-    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
-    if (inside) {
-        dp0 = dL_dpixels[pix];
-        dp1 = dL_dpixels[plane + pix];
-        dp2 = dL_dpixels[2 * plane + pix];
-    }
-    const float bg_dot = fmaf(bg[2], dp2, fmaf(bg[1], dp1, bg[0] * dp0));
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-    // Splats behind the deepest last contributor of the warp (of the tile) cannot touch any of its
-    // pixels: the tile only walks list positions [0, tile_last), each warp only [0, warp_last).
-    const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
-    __syncthreads();
-    if (lane == 0 && warp_last > 0) atomicMax(&s_tile_last, warp_last);
-    __syncthreads();
-    const int n = s_tile_last;
-    if (n == 0) return;
-    const uint32_t sa = smem_addr_pinned(s_a), sb = smem_addr_pinned(s_b), sc = smem_addr_pinned(s_c);
-
-    for (int b0 = 0; b0 < n; b0 += BWD_B) {
-        __syncthreads();
-        uint32_t mask = 0;
-        if (tid < BWD_B) {
-            if (b0 + tid < n) {
-                const uint32_t id = plist[lo + (uint32_t)(n - 1 - (b0 + tid))];  // back to front
-                const float4 *r = rec + (size_t)id * 3;
-                const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-                s_id[tid] = id;
-                s_a[tid] = r0;
-                s_b[tid] = r1;
-                s_c[tid] = make_float2(r2.x, r2.y);
-                mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
-            }
-#pragma unroll
-            for (int sidx = 0; sidx < BWD_NW; sidx++) {
-                const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
-                if (lane == 0) s_member[sidx][wid] = word;
-            }
-        }
-        __syncthreads();
-        const int m = min(BWD_B, n - b0);
-        const int jmin = n - b0 - warp_last;  // first batch slot whose list position is < warp_last
-        // list position of slot j is n-1-(b0+j); it precedes this pixel's last contributor iff j > jlim
-        const int jlim = n - 1 - b0 - last_contributor;
-#pragma unroll 1
-        for (int c = 0; c * 32 < m; c++) {
-            uint32_t touched = 0;
-            uint32_t mw = s_member[wid][c];
-            const int cut = jmin - c * 32;
-            if (cut >= 32) mw = 0;
-            else if (cut > 0) mw &= ~((1u << cut) - 1u);
-#pragma unroll 1
-            while (mw) {
-                const uint32_t lowbit = mw & (0u - mw);
-                const int j = c * 32 + (__ffs(mw) - 1);
-                mw ^= lowbit;
-                const float4 A = lds128(sa + j * 16);
-                const float4 B = lds128(sb + j * 16);
-                const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
-                const float power = splat_power(dx, dy, A.z, A.w, B.x);
-                bool valid = j > jlim && !(power > 0.0f) && !(power < B.y);
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                // S = dL/dG * G and the colour weight alpha*T of this pair; zero for lanes without one
-                float S = 0.f, dchannel = 0.f;
-                if (valid) {
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, __fmul_rn(B.z, G));
-                    valid = !(alpha < 1.0f / 255.0f);
-                    if (valid) {
-                        const float2 Cc = lds64(sc + j * 8);
-                        const float om = 1.0f - alpha;  // in [0.01, 1): a bare MUFU.RCP suffices
-                        float inv;
-                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(om));
-                        T = T * inv;
-                        dchannel = alpha * T;
-                        // acc holds the colour blended behind this splat (backward.cu:493-499 keeps
-                        // last_alpha / last_color and folds them in one iteration later; same
-                        // operations on the same values, evaluated eagerly below)
-                        float dL_dalpha = (B.w - acc0) * dp0;
-                        dL_dalpha = fmaf(Cc.x - acc1, dp1, dL_dalpha);
-                        dL_dalpha = fmaf(Cc.y - acc2, dp2, dL_dalpha);
-                        dL_dalpha *= T;
-                        dL_dalpha = fmaf(-T_final * inv, bg_dot, dL_dalpha);
-                        S = B.z * dL_dalpha * G;
-                        acc0 = fmaf(alpha, B.w, om * acc0);
-                        acc1 = fmaf(alpha, Cc.x, om * acc1);
-                        acc2 = fmaf(alpha, Cc.y, om * acc2);
-                    }
-                }
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                // v[0..5] moments of S, v[6..7] + v8 colour gradients
-                float v[8];
-                const float Sx = S * dx, Sy = S * dy;
-                v[0] = S;
-                v[1] = Sx;
-                v[2] = Sy;
-                v[3] = Sx * dx;
-                v[4] = Sx * dy;
-                v[5] = Sy * dy;
-                v[6] = dchannel * dp0;
-                v[7] = dchannel * dp1;
-                float v8 = dchannel * dp2;
-                const float r8 = warp_reduce8(v, lane);
-                v8 = warp_sum(v8);
-                if ((lane & 3u) == 0) s_acc[wid][j][lane >> 2] = r8;
-                if (lane == 1) s_acc[wid][j][8] = v8;
-                touched |= lowbit;
-            }
-            if (lane == 0) s_touched[wid][c] = touched;
-        }
-        __syncthreads();
-        if (tid < m) {
-            float s[9];
-#pragma unroll
-            for (int k = 0; k < 9; k++) s[k] = 0.f;
-            bool any = false;
-#pragma unroll
-            for (int w = 0; w < BWD_NW; w++) {
-                if ((s_touched[w][tid >> 5] >> (tid & 31)) & 1u) {
-                    any = true;
-#pragma unroll
-                    for (int k = 0; k < 9; k++) s[k] += s_acc[w][tid][k];
-                }
-            }
-            if (any) {
-                // moments -> gradients (backward.cu:537-554): dG/ddel = -G (Q d)
-                const float4 A = s_a[tid];
-                const float4 B = s_b[tid];
-                const float gmx = -(A.z * s[1] + A.w * s[2]) * ddelx_dx;
-                const float gmy = -(B.x * s[2] + A.w * s[1]) * ddely_dy;
-                float *g = gacc + (size_t)s_id[tid] * 12;
-                red_add_v4(g, gmx, gmy, -0.5f * s[3], -0.5f * s[4]);
-                red_add_v4(g + 4, -0.5f * s[5], s[0] / B.z, s[6], s[7]);
-                atomicAdd(g + 8, s[8]);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// blend backward, chunked reduction.  Same walk as blend_backward_kernel (strip membership, tail
-// skip, bit-identical recomputation of alpha / T), but
-//  * the 9 per-pair values are NOT reduced across the warp with shuffles.  Phase 1 (lane = pixel)
-//    parks S = dL/dG * G and the colour weight alpha*T of every contributing splat in a per-warp
-//    [pixel][slot] shared-memory tile; after CH splats the warp turns around (phase 2, lane = splat
-//    slot x strip row): each lane walks the 16 pixels of its row, rebuilds d = mean - pixel and
-//    accumulates the 6 moments + 3 colour sums of ITS splat in registers, the two rows are combined
-//    with one xor-16 shuffle per value and the result goes straight to the per-Gaussian
-//    accumulators with two red.v4 + one scalar reduction (chunks are 94 % full on the headline
-//    scene).  ~30 issued instructions per contributing (strip, splat) instead of ~67 for the
-//    butterfly; the per-warp partial-sum rows, touched masks and the per-batch fold disappear;
-//  * splat records are double-buffered: the ids of batch b+2 and the cp.async (LDGSTS) copies of
-//    batch b+1 are in flight while batch b is processed, so the CTA-wide barriers at the batch
-//    boundary no longer expose the plist -> record load chain (20 % of the stall samples before).
+// blend backward.  One CTA per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block (the
+// forward's geometry); the tile's list is walked back to front over its first max(n_contrib)
+// positions only, a batch of BWD_B records at a time, with the footprint masks deciding which warp
+// visits which splat (sgr_internal.cuh).  Splat records are double-buffered: the ids of batch b+2 and
+// the cp.async (LDGSTS) copies of batch b+1 are in flight while batch b is processed.
+//
+// Reduction.  The 9 per-pair values are NOT reduced across the warp with shuffles.  Phase 1 (lane =
+// pixel) parks S = dL/dG * G and the colour weight alpha*T of every contributing splat in a per-warp
+// [pixel][slot] shared-memory tile; after CH splats the warp turns around (phase 2, lane = slot x half
+// block): each lane walks the 16 pixels of its half, accumulates RAW moments of S about the half's
+// centre -- the pixel offsets are compile-time constants, so a pixel costs 3 FMAs for the moments and 3
+// for the colours -- shifts them to the splat's centre once, combines the two halves with one xor-16
+// shuffle per value and adds the result to the per-Gaussian accumulators with two red.v4 + one scalar
+// reduction (chunks are ~94 % full on the headline scene).
+//
+// alpha is recomputed as in the forward; G = exp(power) comes from ex2.approx (MUFU.EX2) instead of
+// libdevice's expf -- 2 instructions instead of 8 -- except within 1e-5 (relative) of the 1/255 threshold,
+// where the exact expf decides, so the set of contributing pairs is the forward's.
 // ------------------------------------------------------------------------------------------------
 #ifdef SGR_BLEND_STATS
 __device__ unsigned long long g_bwd_stats[8];
@@ -267,55 +66,59 @@ constexpr int CH = 16;             // splats per chunk
 constexpr int CH_PITCH = CH + 1;   // float2 elements per pixel row: odd pitch = conflict-free transpose
 // per-warp chunk scratch (bytes from its base): pair[32][CH_PITCH] float2 | meta[CH] x 48 B | dp[32] float4
 //   meta: (x, y, conic a, conic b) (conic c, tau, opacity, r) (id, -, -, -)
-//   dp:   (dL/dpixel r g b, -T_final <bg, dL/dpixel>) of the strip's pixels
+//   dp:   (dL/dpixel r g b, -T_final <bg, dL/dpixel>) of the block's pixels
 constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 48, CB_BYTES = CB_DP + 32 * 16;
 // CTA shared-memory map (dynamic): records of two batches, membership words, chunk scratch
-// SGR_BWD_ONE_BARRIER (experimental, off): the membership words of batch b+1 are built by the loader threads at the
-// end of batch b from their own landed records, into a second set of words, so ONE CTA barrier per batch publishes
-// records and words together (the default needs two and leaves the non-loader warps idle in between).
-#ifndef SGR_BWD_ONE_BARRIER
-#define SGR_BWD_ONE_BARRIER 0
-#endif
-// SGR_BWD_BALANCED_LOADERS (experimental, off): every warp stages 16 records of a batch (lanes 0-15) instead of
-// warps 0-3 staging 32 each, so no warp carries more staging work than another.
-#ifndef SGR_BWD_BALANCED_LOADERS
-#define SGR_BWD_BALANCED_LOADERS 0
-#endif
-constexpr uint32_t SM_MEMBER_SETS = SGR_BWD_ONE_BARRIER ? 2 : 1;
 constexpr uint32_t SM_A = 0, SM_B = SM_A + 2 * BWD_B * 16, SM_C = SM_B + 2 * BWD_B * 16, SM_ID = SM_C + 2 * BWD_B * 8,
-                   SM_MEMBER = SM_ID + 2 * BWD_B * 4,
-                   SM_LAST = SM_MEMBER + SM_MEMBER_SETS * BWD_NW * (BWD_B / 32) * 4, SM_CHUNK = SM_LAST + 16,
-                   BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
+                   SM_MEMBER = SM_ID + 2 * BWD_B * 4, SM_LAST = SM_MEMBER + BWD_NW * (BWD_B / 32) * 4,
+                   SM_CHUNK = SM_LAST + 16, BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
 
-// phase 2: reduce the parked chunk (nf splats) over the strip's pixels and add it to the Gaussians'
-// accumulators.  Lane = (chunk slot, strip row).
-__device__ __forceinline__ void chunk_flush(uint32_t cb, int nf, float ddelx_dx, float ddely_dy, float *__restrict__ gacc)
+__device__ __forceinline__ float ex2_approx(float x)
 {
-    // blockDim.x == 16: lane = (threadIdx.y & 1) * 16 + threadIdx.x
-    const int slot = (int)(threadIdx.x & (CH - 1)), row = (int)(threadIdx.y & 1u);
-    const float tx0 = (float)(blockIdx.x * SGR_TILE), row_y = (float)(blockIdx.y * SGR_TILE + threadIdx.y);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// phase 2: reduce the parked chunk (nf splats) over the block's pixels and add it to the Gaussians'
+// accumulators.  Lane = (chunk slot, half): half h holds block rows 2h, 2h+1 = phase-1 lanes 16h..16h+15.
+__device__ __forceinline__ void chunk_flush(uint32_t cb, int nf, float blk_x0, float blk_y0, float ddelx_dx,
+                                            float ddely_dy, float *__restrict__ gacc)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int slot = (int)(lane & (CH - 1)), half = (int)(lane >> 4);
     __syncwarp();
     const float4 M0 = lds128(cb + CB_META + slot * 48), M1 = lds128(cb + CB_META + slot * 48 + 16);
     const uint32_t id = lds32(cb + CB_META + slot * 48 + 32);
-    const float dy = __fsub_rn(M0.y, row_y);
-    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    const uint32_t pa = cb + (row * 16 * CH_PITCH + slot) * 8, da = cb + CB_DP + row * 16 * 16;
+    // d = mean - pixel = (ax - cx_i, ay - cy_i) with the half's centre as origin: cx_i = (i & 7) - 3.5,
+    // cy_i = (i >> 3) - 0.5
+    const float ax = M0.x - (blk_x0 + 3.5f), ay = M0.y - (blk_y0 + 2.0f * (float)half + 0.5f);
+    float s_lo = 0.f, s_hi = 0.f, t_lo = 0.f, t_hi = 0.f, u = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    const uint32_t pa = cb + (half * 16 * CH_PITCH + slot) * 8, da = cb + CB_DP + half * 16 * 16;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const float2 pr = lds64(pa + i * CH_PITCH * 8);
         const float4 d = lds128(da + i * 16);
-        const float dx = __fsub_rn(M0.x, tx0 + (float)i);
-        const float Sx = pr.x * dx, Sy = pr.x * dy;
-        m0 += pr.x;
-        m1 += Sx;
-        m2 += Sy;
-        m3 = fmaf(Sx, dx, m3);
-        m4 = fmaf(Sx, dy, m4);
-        m5 = fmaf(Sy, dy, m5);
+        const float cx = (float)(i & 7) - 3.5f;
+        if (i < 8) {
+            s_lo += pr.x;
+            t_lo = fmaf(pr.x, cx, t_lo);
+        } else {
+            s_hi += pr.x;
+            t_hi = fmaf(pr.x, cx, t_hi);
+        }
+        u = fmaf(pr.x, cx * cx, u);
         c0 = fmaf(pr.y, d.x, c0);
         c1 = fmaf(pr.y, d.y, c1);
         c2 = fmaf(pr.y, d.z, c2);
     }
+    const float s0 = s_lo + s_hi, sx = t_lo + t_hi, sy = 0.5f * (s_hi - s_lo), sxy = 0.5f * (t_hi - t_lo);
+    float m0 = s0;
+    float m1 = fmaf(ax, s0, -sx);                                    // sum S dx
+    float m2 = fmaf(ay, s0, -sy);                                    // sum S dy
+    float m3 = fmaf(ax, fmaf(ax, s0, -2.0f * sx), u);                // sum S dx^2
+    float m4 = fmaf(ax, m2, fmaf(-ay, sx, sxy));                     // sum S dx dy
+    float m5 = fmaf(ay, fmaf(ay, s0, -2.0f * sy), 0.25f * s0);       // sum S dy^2
     m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
     m1 += __shfl_xor_sync(0xffffffffu, m1, 16);
     m2 += __shfl_xor_sync(0xffffffffu, m2, 16);
@@ -328,32 +131,36 @@ __device__ __forceinline__ void chunk_flush(uint32_t cb, int nf, float ddelx_dx,
     if (slot < nf) {
         // moments -> gradients (backward.cu:537-554): dG/ddel = -G (Q d)
         float *g = gacc + (size_t)id * 12;
-        if (row == 0) {
+        if (half == 0) {
             const float gmx = -(M0.z * m1 + M0.w * m2) * ddelx_dx;
             const float gmy = -(M1.x * m2 + M0.w * m1) * ddely_dy;
             red_add_v4(g, gmx, gmy, -0.5f * m3, -0.5f * m4);
         } else {
-            red_add_v4(g + 4, -0.5f * m5, m0 / M1.z, c0, c1);
+            red_add_v4(g + 4, -0.5f * m5, __fdividef(m0, M1.z), c0, c1);
             atomicAdd(g + 8, c2);
         }
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
-    const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ plist, const float4 *__restrict__ rec, int W,
-    int H, int gx, const float *__restrict__ bg, const float *__restrict__ final_Ts,
-    const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dpixels, float *__restrict__ gacc)
+template <bool packed>
+__global__ void __launch_bounds__(256, 4) blend_backward_kernel(
+    const uint32_t *__restrict__ tile_order, const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ plist,
+    const float4 *__restrict__ rec, int W, int H, int gx, const float *__restrict__ bg,
+    const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dpixels,
+    float *__restrict__ gacc)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const int tile = blockIdx.y * gx + blockIdx.x;
-    const int tid = threadIdx.y * SGR_TILE + threadIdx.x;
-    const unsigned lane = tid & 31, wid = tid >> 5;
-    const uint32_t pxi = blockIdx.x * SGR_TILE + threadIdx.x, pyi = blockIdx.y * SGR_TILE + threadIdx.y;
-    const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
-    const float tx0 = (float)(blockIdx.x * SGR_TILE), ty0 = (float)(blockIdx.y * SGR_TILE);
+    const int tile = (int)tile_order[blockIdx.x];
     const uint32_t lo = tile_start[tile], hi = tile_start[tile + 1];
     if (hi == lo) return;
+    const int tile_y = tile / gx, tile_x = tile - tile_y * gx;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31, wid = tid >> 5;
+    const int tx0 = tile_x * SGR_TILE, ty0 = tile_y * SGR_TILE;
+    const int bx0 = tx0 + (int)(wid & 1u) * 8, by0 = ty0 + (int)(wid >> 1) * 4;
+    const uint32_t pxi = bx0 + (lane & 7u), pyi = by0 + (lane >> 3);
+    const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
     const uint32_t sm = smem_addr_pinned(s_raw);
     int *s_tile_last = (int *)(s_raw + SM_LAST);
     uint32_t(*s_member)[BWD_B / 32] = (uint32_t(*)[BWD_B / 32])(s_raw + SM_MEMBER);
@@ -370,12 +177,12 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
             dp1 = dL_dpixels[plane + pix];
             dp2 = dL_dpixels[2 * plane + pix];
         }
-        // (dL/dpixel, -T_final * <bg, dL/dpixel>) of this pixel: phase 2 reads the strip's table; the
+        // (dL/dpixel, -T_final * <bg, dL/dpixel>) of this pixel: phase 2 reads the block's table; the
         // hit path of phase 1 reloads its own entry instead of pinning four registers across the loop
         sts128(cb + CB_DP + lane * 16, dp0, dp1, dp2, -T * fmaf(bg[2], dp2, fmaf(bg[1], dp1, bg[0] * dp0)));
     }
-    // the pixel centre, pinned: under register pressure nvcc otherwise re-derives pyf from
-    // S2R SR_TID.Y / SR_CTAID.Y inside the splat loop (long-latency special-register reads)
+    // the pixel centre, pinned: under register pressure nvcc otherwise re-derives it from special
+    // registers inside the splat loop
     float pxf = (float)pxi, pyf = (float)pyi;
     asm volatile("mov.f32 %0, %0;" : "+f"(pxf));
     asm volatile("mov.f32 %0, %0;" : "+f"(pyf));
@@ -389,34 +196,22 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
     const int n = *s_tile_last;
     if (n == 0) return;
     int nfill = 0;
+    const float blk_x0 = (float)bx0, blk_y0 = (float)by0;
 
     // record pipeline (threads 0..BWD_B-1 own one slot of every batch): issue() starts the async
-    // copies of one splat record into buffer `buf`; ids are fetched one batch further ahead
-#if SGR_BWD_BALANCED_LOADERS
-    static_assert(BWD_B == 16 * BWD_NW, "16 records per warp");
-    const bool loader = lane < 16;             // every warp takes part in the ballots below
-    const int ls = (int)(wid * 16 + lane);     // this thread's record slot within a batch
-#else
+    // copies of one splat record into buffer `buf`; list words are fetched one batch further ahead
     const bool loader = tid < BWD_B;
-    const int ls = tid;
-#endif
-    // warps that execute the staging code (whole warps: it contains ballots); within them only `loader` lanes own a record
-    const bool staging_warp = SGR_BWD_BALANCED_LOADERS ? true : loader;
-    auto fetch_id = [&](int b0) -> uint32_t {
-        return (loader && b0 + ls < n) ? plist[lo + (uint32_t)(n - 1 - (b0 + ls))] : 0xffffffffu;  // back to front
+    auto fetch = [&](int b0) -> uint32_t {
+        // back to front; dead instances (packed list, empty footprint) are dropped here: 0xffffffff
+        if (!(loader && b0 + tid < n)) return 0xffffffffu;
+        const uint32_t w = plist[lo + (uint32_t)(n - 1 - (b0 + tid))];
+        return (packed && (w & 0xffu) == 0u) ? 0xffffffffu : w;
     };
-    // membership words: bit j of word c <-> record c*32+j of the batch
-    auto put_member = [&](uint32_t(*set)[BWD_B / 32], int sidx, uint32_t word) {
-#if SGR_BWD_BALANCED_LOADERS
-        if (lane == 0) ((uint16_t *)set[sidx])[wid] = (uint16_t)word;  // this warp's 16 records
-#else
-        if (lane == 0) set[sidx][wid] = word;
-#endif
-    };
-    auto issue = [&](uint32_t id, int buf) {
-        if (id != 0xffffffffu) {
+    auto issue = [&](uint32_t w, int buf) {
+        if (w != 0xffffffffu) {
+            const uint32_t id = packed ? (w >> 8) : w;
             const float4 *r = rec + (size_t)id * 3;
-            const uint32_t e = buf * BWD_B + ls;
+            const uint32_t e = buf * BWD_B + tid;
             cp_async16_a(sm + SM_A + e * 16, r);
             cp_async16_a(sm + SM_B + e * 16, r + 1);
             cp_async8_a(sm + SM_C + e * 8, r + 2);
@@ -424,63 +219,36 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
         }
         cp_async_commit();
     };
-    uint32_t id_cur = fetch_id(0);
-    issue(id_cur, 0);
-    uint32_t id_next = fetch_id(BWD_B);
-#if SGR_BWD_ONE_BARRIER
-    // loader threads: membership words of the batch in `buf`, each from its own landed record
-    auto make_masks = [&](uint32_t id, int buf) {
-        uint32_t mask = 0;
-        if (id != 0xffffffffu) {
-            const uint32_t e = buf * BWD_B + ls;
-            const float4 r0 = lds128(sm + SM_A + e * 16), r1 = lds128(sm + SM_B + e * 16);
-            mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
-        }
-#pragma unroll
-        for (int sidx = 0; sidx < BWD_NW; sidx++) {
-            const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
-            put_member(s_member + buf * BWD_NW, sidx, word);
-        }
-    };
-    if (staging_warp) {
-        cp_async_wait<0>();
-        make_masks(id_cur, 0);
-    }
-#endif
+    uint32_t w_cur = fetch(0);
+    issue(w_cur, 0);
+    uint32_t w_next = fetch(BWD_B);
 
     for (int b0 = 0, buf = 0; b0 < n; b0 += BWD_B, buf ^= 1) {
         const uint32_t sa = sm + SM_A + buf * (BWD_B * 16), sb = sm + SM_B + buf * (BWD_B * 16),
                        sc = sm + SM_C + buf * (BWD_B * 8), sid = sm + SM_ID + buf * (BWD_B * 4);
-#if SGR_BWD_ONE_BARRIER
-        __syncthreads();  // records + membership words of batch b0 are published; every warp is done with b0 - BWD_B
-        const uint32_t(*member)[BWD_B / 32] = s_member + buf * BWD_NW;
-        if (staging_warp) {
-            issue(id_next, buf ^ 1);
-            id_cur = id_next;
-            id_next = fetch_id(b0 + 2 * BWD_B);
-        }
-#else
         cp_async_wait<0>();
         __syncthreads();  // batch b0 has landed in `buf`; every warp is done with the other buffer
-        const uint32_t(*member)[BWD_B / 32] = s_member;
-        if (staging_warp) {
+        if (loader) {
             uint32_t mask = 0;
-            if (id_cur != 0xffffffffu) {
-                const float4 r0 = lds128(sa + ls * 16), r1 = lds128(sb + ls * 16);
-                mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+            if (w_cur != 0xffffffffu) {
+                if (packed) {
+                    mask = w_cur & 0xffu;
+                } else {
+                    const float4 r0 = lds128(sa + tid * 16), r1 = lds128(sb + tid * 16);
+                    mask = block_mask_of_record(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+                }
             }
 #pragma unroll
-            for (int sidx = 0; sidx < BWD_NW; sidx++) {
-                const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
-                put_member(s_member, sidx, word);
+            for (int blk = 0; blk < BWD_NW; blk++) {
+                const uint32_t word = __ballot_sync(0xffffffffu, (mask >> blk) & 1u);
+                if (lane == 0) s_member[blk][wid] = word;
             }
             // next batch's records start moving now; they are not needed before the next barrier
-            issue(id_next, buf ^ 1);
-            id_cur = id_next;
-            id_next = fetch_id(b0 + 2 * BWD_B);
+            issue(w_next, buf ^ 1);
+            w_cur = w_next;
+            w_next = fetch(b0 + 2 * BWD_B);
         }
         __syncthreads();
-#endif
         const int m = min(BWD_B, n - b0);
 #ifdef SGR_BLEND_STATS
         if (tid == 0) BWD_STAT(6, m);
@@ -490,7 +258,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
         const int jlim = n - 1 - b0 - last_contributor;
 #pragma unroll 1
         for (int c = 0; c * 32 < m; c++) {
-            uint32_t mw = member[wid][c];
+            uint32_t mw = s_member[wid][c];
             const int cut = jmin - c * 32;
             if (cut >= 32) mw = 0;
             else if (cut > 0) mw &= ~((1u << cut) - 1u);
@@ -502,7 +270,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
                 const float4 B = lds128(sb + j * 16);
                 const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
                 const float power = splat_power(dx, dy, A.z, A.w, B.x);
-                bool valid = j > jlim && !(power > 0.0f) && !(power < B.y);
+                const bool valid = j > jlim && !(power > 0.0f) && !(power < B.y);
 #ifdef SGR_BLEND_STATS
                 {
                     const bool hit = valid && !(fminf(0.99f, __fmul_rn(B.z, expf(power))) < 1.0f / 255.0f);
@@ -520,12 +288,16 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
 #endif
                 if (!__any_sync(0xffffffffu, valid)) continue;
                 // S = dL/dG * G and the colour weight alpha*T of this pair; zero for lanes without one.
-                // (A candidate warp almost always keeps a contributing lane -- 8 554 776 of 8 554 918 on
-                // the headline scene -- so there is no second vote: an all-zero slot is harmless.)
+                // (A candidate warp almost always keeps a contributing lane, so there is no second vote:
+                // an all-zero slot is harmless.)
                 float S = 0.f, dchannel = 0.f;
                 if (valid) {
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, __fmul_rn(B.z, G));
+                    float G = ex2_approx(power * 1.4426950408889634f);
+                    float alpha = fminf(0.99f, B.z * G);
+                    if (fabsf(alpha - 1.0f / 255.0f) < 4.0e-8f) {  // on the threshold: decide as the forward did
+                        G = expf(power);
+                        alpha = fminf(0.99f, __fmul_rn(B.z, G));
+                    }
                     if (!(alpha < 1.0f / 255.0f)) {
                         const float2 Cc = lds64(sc + j * 8);
                         const float4 dp = lds128(cb + CB_DP + lane * 16);
@@ -556,19 +328,13 @@ __global__ void __launch_bounds__(256, 4) blend_backward_chunked_kernel(
                 sts128(ma + 16, B.x, B.y, B.z, B.w);
                 sts32(ma + 32, lds32(sid + j * 4));
                 if (++nfill == CH) {
-                    chunk_flush(cb, CH, 0.5f * W, 0.5f * H, gacc);
+                    chunk_flush(cb, CH, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc);
                     nfill = 0;
                 }
             }
         }
-#if SGR_BWD_ONE_BARRIER
-        if (staging_warp) {  // next batch: own record has landed -> its membership bits, published by the next barrier
-            cp_async_wait<0>();
-            make_masks(id_cur, buf ^ 1);
-        }
-#endif
     }
-    if (nfill) chunk_flush(cb, nfill, 0.5f * W, 0.5f * H, gacc);
+    if (nfill) chunk_flush(cb, nfill, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1081,10 +847,10 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
         SGR_CUDA(cudaGetDevice(&dev));
         std::lock_guard<std::mutex> lock(mu);
         if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-#if SGR_BWD_CHUNKED
-            SGR_CUDA(cudaFuncSetAttribute(blend_backward_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            SGR_CUDA(cudaFuncSetAttribute(blend_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)BWD_SMEM_BYTES));
-#endif
+            SGR_CUDA(cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)BWD_SMEM_BYTES));
             SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           200 * 1024));
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
@@ -1092,20 +858,15 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     }
     SGR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 48, st));
     if (num_rendered > 0) {
-#ifndef SGR_BWD_CHUNKED
-#define SGR_BWD_CHUNKED 1
-#endif
-#if SGR_BWD_CHUNKED
-#define SGR_BLEND_BWD_KERNEL blend_backward_chunked_kernel
-#define SGR_BLEND_BWD_SMEM BWD_SMEM_BYTES
-#else
-#define SGR_BLEND_BWD_KERNEL blend_backward_kernel
-#define SGR_BLEND_BWD_SMEM 0
-#endif
         SGR_LAUNCH(K_BLEND_BWD, st,
-                   SGR_BLEND_BWD_KERNEL<<<dim3(gx, gy), dim3(SGR_TILE, SGR_TILE), SGR_BLEND_BWD_SMEM, st>>>(
-                       img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T, img.n_contrib,
-                       dL_dout_color, gacc));
+                   if (ids_packed(P))
+                       blend_backward_kernel<true><<<gx * gy, 256, BWD_SMEM_BYTES, st>>>(
+                           img.tile_order, img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T,
+                           img.n_contrib, dL_dout_color, gacc);
+                   else
+                       blend_backward_kernel<false><<<gx * gy, 256, BWD_SMEM_BYTES, st>>>(
+                           img.tile_order, img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T,
+                           img.n_contrib, dL_dout_color, gacc));
     }
     const bool staged_factors = hook && g->shs && !dL_dsh;
     if (staged_factors) {

@@ -287,12 +287,17 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
 // ------------------------------------------------------------------------------------------------
 // exclusive scan over tile counts -> tile_start[0..T], cursor copy, R
 // ------------------------------------------------------------------------------------------------
+// Also orders the tiles by decreasing instance count (counting sort on count / 8, 1024 classes): the
+// blend kernels take their tile from this list, so the hardware's in-order block dispatch starts the
+// heaviest tiles first and the tail of the grid consists of the lightest ones (longest-processing-time
+// -first; the order within a class is arbitrary and has no effect on any result).
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t *__restrict__ count, uint32_t *__restrict__ start,
-                                                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ counters, int T,
-                                                         uint32_t *host_mirror)
+                                                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ order,
+                                                         uint32_t *__restrict__ counters, int T, uint32_t *host_mirror)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_class[1024];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -340,56 +345,101 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t *__restr
         counters[0] = s_carry;
         if (host_mirror) *host_mirror = s_carry;
     }
+    // ---- tile order: class 0 = heaviest ----
+    s_class[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < T; i += 1024) atomicAdd(&s_class[1023u - min(count[i] >> 3, 1023u)], 1u);
+    __syncthreads();
+    {
+        const uint32_t c = s_class[tid];
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - w;
+        }
+        __syncthreads();
+        s_class[tid] = s_warp[wid] + inc - c;  // exclusive start of this class
+    }
+    __syncthreads();
+    for (int i = tid; i < T; i += 1024) order[atomicAdd(&s_class[1023u - min(count[i] >> 3, 1023u)], 1u)] = (uint32_t)i;
 }
 
 // ------------------------------------------------------------------------------------------------
-// scatter: one (depth|id) word per (Gaussian, tile) instance into its tile's segment
+// scatter: one (depth | id [| footprint mask]) word per (Gaussian, tile) instance into its tile's segment.
+// The kernel is bound by the round trip of its returning atomics (one slot claim per instance), so the
+// arithmetic it does while they are in flight is free: this is where the exact footprint mask of every
+// instance (sgr_internal.cuh, block_mask) is computed -- once, for both blend kernels.
 // ------------------------------------------------------------------------------------------------
+#ifndef SGR_SCATTER_SMALL
+#define SGR_SCATTER_SMALL 6
+#endif
+
 __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, const ushort4 *__restrict__ rect,
-                                                      const float *__restrict__ depth, uint32_t *__restrict__ cursor,
+                                                      const float *__restrict__ depth, const float4 *__restrict__ rec,
+                                                      uint32_t *__restrict__ cursor,
                                                       const uint32_t *__restrict__ counters, uint64_t capacity,
-                                                      uint64_t *__restrict__ inst)
+                                                      int packed, uint64_t *__restrict__ inst)
 {
     if ((uint64_t)counters[0] > capacity) return;  // overflow: host re-runs with a bigger buffer
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
     ushort4 rc = make_ushort4(0, 0, 0, 0);
     uint32_t dbits = 0;
+    EllipseBands eb;
+    eb.all = true;
+    eb.dead = false;
     if (idx < P) {
         rc = rect[idx];
-        if (rc.z > rc.x) dbits = __float_as_uint(depth[idx]);
+        if (rc.z > rc.x && rc.w > rc.y) {
+            dbits = __float_as_uint(depth[idx]);
+            if (packed) {
+                const float4 r0 = __ldg(rec + (size_t)idx * 3), r1 = __ldg(rec + (size_t)idx * 3 + 1);
+                eb = ellipse_bands(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y);
+            }
+        }
     }
-    // Rects of up to SMALL tiles are walked by their own thread, BATCH slots at a time (the returning
-    // atomics of a batch are in flight together; all lanes of the warp work concurrently); only very
-    // large rects are walked cooperatively by the whole warp.
-#ifndef SGR_SCATTER_SMALL
-#define SGR_SCATTER_SMALL 6
-#endif
-#ifndef SGR_SCATTER_BATCH
-#define SGR_SCATTER_BATCH 6
-#endif
-    constexpr int SMALL = SGR_SCATTER_SMALL, BATCH = SGR_SCATTER_BATCH;
+    // Rects of up to SMALL tiles are walked by their own thread: masks first (pure arithmetic), then all
+    // the slot claims back to back (the returning atomics are in flight together), then the stores.
+    // Larger rects are walked cooperatively by the whole warp, one tile per lane.
+    constexpr int SMALL = SGR_SCATTER_SMALL;
+    static_assert(SMALL <= 8, "masks of a small rect are packed into one 64-bit register");
     const int rw = (int)rc.z - (int)rc.x, rcnt = (rc.z > rc.x && rc.w > rc.y) ? rw * ((int)rc.w - (int)rc.y) : 0;
+    const uint32_t low_id = packed ? ((uint32_t)idx << 8) : (uint32_t)idx;
     if (rcnt > 0 && rcnt <= SMALL) {
-        const uint64_t word = ((uint64_t)dbits << 32) | (uint32_t)idx;
+        uint64_t masks = 0;
+        if (packed) {
+            int k = 0;
+            for (int ty = rc.y; ty < rc.w; ty++)
+                for (int tx = rc.x; tx < rc.z; tx++, k++)
+                    masks |= (uint64_t)block_mask(eb, tx * SGR_TILE, ty * SGR_TILE) << (8 * k);
+        }
+        uint32_t slot[SMALL];
         int tx = 0, trow = (int)rc.y * gx + (int)rc.x;
-        for (int done = 0; done < rcnt; done += BATCH) {
-            uint32_t slot[BATCH];
-            const int m = min(BATCH, rcnt - done);
 #pragma unroll
-            for (int k = 0; k < BATCH; k++) {
-                if (k < m) {
-                    slot[k] = atomicAdd(cursor + trow + tx, 1u);
-                    if (++tx == rw) {
-                        tx = 0;
-                        trow += gx;
-                    }
+        for (int k = 0; k < SMALL; k++) {
+            if (k < rcnt) {
+                slot[k] = atomicAdd(cursor + trow + tx, 1u);
+                if (++tx == rw) {
+                    tx = 0;
+                    trow += gx;
                 }
             }
-#pragma unroll
-            for (int k = 0; k < BATCH; k++)
-                if (k < m) inst[slot[k]] = word;
         }
+#pragma unroll
+        for (int k = 0; k < SMALL; k++)
+            if (k < rcnt) inst[slot[k]] = ((uint64_t)dbits << 32) | low_id | (uint32_t)((masks >> (8 * k)) & 0xffu);
     }
     unsigned todo = __ballot_sync(0xffffffffu, rcnt > SMALL);
     while (todo) {
@@ -398,12 +448,23 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, const ushor
         const int rx0 = __shfl_sync(0xffffffffu, (int)rc.x, src), ry0 = __shfl_sync(0xffffffffu, (int)rc.y, src);
         const int w = __shfl_sync(0xffffffffu, rw, src), cnt = __shfl_sync(0xffffffffu, rcnt, src);
         const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
-        const int gid = (idx - (int)lane) + src;
-        const uint64_t word = ((uint64_t)db << 32) | (uint32_t)gid;
+        const uint32_t lid = __shfl_sync(0xffffffffu, low_id, src);
+        EllipseBands es;
+        es.gx = __shfl_sync(0xffffffffu, eb.gx, src);
+        es.gy = __shfl_sync(0xffffffffu, eb.gy, src);
+        es.k_a = __shfl_sync(0xffffffffu, eb.k_a, src);
+        es.det_a2 = __shfl_sync(0xffffffffu, eb.det_a2, src);
+        es.b_a = __shfl_sync(0xffffffffu, eb.b_a, src);
+        es.v_r = __shfl_sync(0xffffffffu, eb.v_r, src);
+        es.r_lo = __shfl_sync(0xffffffffu, eb.r_lo, src);
+        es.r_hi = __shfl_sync(0xffffffffu, eb.r_hi, src);
+        es.all = __shfl_sync(0xffffffffu, (int)eb.all, src) != 0;
+        es.dead = __shfl_sync(0xffffffffu, (int)eb.dead, src) != 0;
         for (int k = lane; k < cnt; k += 32) {
             const int ty = k / w, tx = k - ty * w;
+            const uint32_t m = packed ? block_mask(es, (rx0 + tx) * SGR_TILE, (ry0 + ty) * SGR_TILE) : 0u;
             const uint32_t slot = atomicAdd(cursor + (ry0 + ty) * gx + rx0 + tx, 1u);
-            inst[slot] = word;
+            inst[slot] = ((uint64_t)db << 32) | lid | m;
         }
     }
 }
@@ -772,13 +833,14 @@ __global__ void __launch_bounds__(BK_T) tile_sort_bucket_kernel(const uint32_t *
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward blend: one CTA per 16x16 tile, one thread per pixel, one warp per 16x2 pixel strip.
-// Splat records are gathered once per tile into shared memory together with an 8-bit strip mask;
-// each warp then walks only the splats whose footprint can reach its strip (ffs over a per-strip
-// membership word) instead of testing every splat of the tile.  power / alpha / T / C follow the
-// reference's rounding exactly (forward.cu:261-374), so final_T, n_contrib and the image are
-// bit-identical to the reference; the strip mask and the `power < tau` test only skip pairs the
-// exact alpha test would reject.
+// forward blend: one CTA per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block
+// (block w = band * 2 + half, sgr_internal.cuh).  The records of a batch of the tile's list are
+// gathered once into shared memory -- only those whose footprint mask is not empty: a third of the
+// instances are dead in their tile -- and each warp walks only the splats whose mask has its block's
+// bit (ffs over a per-block membership word).  power / alpha / T / C follow the reference's rounding
+// exactly (forward.cu:261-374), so final_T, n_contrib and the image are bit-identical to the
+// reference; the masks and the `power < tau` test only skip pairs the exact alpha test would reject.
+// Tiles are taken heaviest first (tile_order).
 // ------------------------------------------------------------------------------------------------
 constexpr int BLEND_T = 256;
 
@@ -788,13 +850,9 @@ __device__ unsigned long long g_fwd_stats[8];
 #define FWD_STAT(k, v) atomicAdd(&g_fwd_stats[k], (unsigned long long)(v))
 #endif
 
-// Double-buffered records (as in the backward) measured slower here: 0.708 vs 0.673 ms -- most tiles
-// saturate before their last batch, so the prefetched batch is wasted work.  Kept for A/B.
-#ifndef SGR_FWD_PIPELINED
-#define SGR_FWD_PIPELINED 0
-#endif
-
-__global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *__restrict__ tile_start,
+template <bool packed>
+__global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *__restrict__ tile_order,
+                                                                const uint32_t *__restrict__ tile_start,
                                                                 const uint32_t *__restrict__ plist,
                                                                 const float4 *__restrict__ rec,
                                                                 const uint32_t *__restrict__ counters, uint64_t capacity,
@@ -803,81 +861,48 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
                                                                 uint32_t *__restrict__ n_contrib,
                                                                 float *__restrict__ out_color)
 {
-#if SGR_FWD_PIPELINED
-    constexpr int NBUF = 2;  // records are double-buffered: batch b+1 is copied while batch b is blended
-#else
-    constexpr int NBUF = 1;
-#endif
-    __shared__ float4 s_a[NBUF * BLEND_T];  // x, y, conic a, conic b
-    __shared__ float4 s_b[NBUF * BLEND_T];  // conic c, tau, opacity, r
-    __shared__ float2 s_c[NBUF * BLEND_T];  // g, b
+    __shared__ float4 s_a[BLEND_T];  // x, y, conic a, conic b
+    __shared__ float4 s_b[BLEND_T];  // conic c, tau, opacity, r
+    __shared__ float2 s_c[BLEND_T];  // g, b
     __shared__ uint32_t s_member[8][BLEND_T / 32];
     if ((uint64_t)counters[0] > capacity) return;
-    const int tile = blockIdx.y * gx + blockIdx.x;
-    const int tid = threadIdx.y * SGR_TILE + threadIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];
+    const int tile_y = tile / gx, tile_x = tile - tile_y * gx;
+    const int tid = threadIdx.x;
     const unsigned lane = tid & 31, wid = tid >> 5;
-    const uint32_t pxi = blockIdx.x * SGR_TILE + threadIdx.x, pyi = blockIdx.y * SGR_TILE + threadIdx.y;
+    const int tx0 = tile_x * SGR_TILE, ty0 = tile_y * SGR_TILE;
+    const uint32_t pxi = tx0 + (wid & 1u) * 8 + (lane & 7u), pyi = ty0 + (wid >> 1) * 4 + (lane >> 3);
     const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
     const float pxf = (float)pxi, pyf = (float)pyi;
-    const float tx0 = (float)(blockIdx.x * SGR_TILE), ty0 = (float)(blockIdx.y * SGR_TILE);
     const uint32_t lo = tile_start[tile], hi = tile_start[tile + 1];
     uint32_t done = inside ? 0u : 1u;  // 32-bit flag: a bool makes nvcc shuffle bytes (PRMT) in the hot loop
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0;
-    const uint32_t sa0 = smem_addr_pinned(s_a), sb0 = smem_addr_pinned(s_b), sc0 = smem_addr_pinned(s_c);
-#if SGR_FWD_PIPELINED
-    // record pipeline: every thread owns one slot of every batch; the id of batch b+2 and the
-    // cp.async (LDGSTS) copies of batch b+1 are in flight while batch b is blended, so the barriers
-    // at the batch boundary do not expose the plist -> record load chain.
-    auto fetch_id = [&](uint32_t b0) -> uint32_t { return (b0 + tid < hi) ? plist[b0 + tid] : 0xffffffffu; };
-    auto issue = [&](uint32_t id, uint32_t buf) {
-        if (id != 0xffffffffu) {
-            const float4 *r = rec + (size_t)id * 3;
-            const uint32_t e = buf * BLEND_T + tid;
-            cp_async16_a(sa0 + e * 16, r);
-            cp_async16_a(sb0 + e * 16, r + 1);
-            cp_async8_a(sc0 + e * 8, r + 2);
-        }
-        cp_async_commit();
-    };
-    uint32_t id_cur = fetch_id(lo);
-    issue(id_cur, 0);
-    uint32_t id_next = fetch_id(lo + BLEND_T);
-#endif
-    uint32_t buf = 0;
-    for (uint32_t b0 = lo; b0 < hi; b0 += BLEND_T, buf ^= (NBUF - 1)) {
-#if SGR_FWD_PIPELINED
-        cp_async_wait<0>();
-#endif
+    const uint32_t sa = smem_addr_pinned(s_a), sb = smem_addr_pinned(s_b), sc = smem_addr_pinned(s_c);
+    for (uint32_t b0 = lo; b0 < hi; b0 += BLEND_T) {
         if (__syncthreads_count(done != 0u) == BLEND_T) break;
-        const uint32_t sa = sa0 + buf * (BLEND_T * 16), sb = sb0 + buf * (BLEND_T * 16), sc = sc0 + buf * (BLEND_T * 8);
         uint32_t mask = 0;
-#if SGR_FWD_PIPELINED
-        if (id_cur != 0xffffffffu) {
-            const float4 r0 = lds128(sa + tid * 16), r1 = lds128(sb + tid * 16);
-            mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
-        }
-#else
         if (b0 + tid < hi) {
-            const uint32_t id = plist[b0 + tid];
-            const float4 *r = rec + (size_t)id * 3;
-            const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-            s_a[tid] = r0;
-            s_b[tid] = r1;
-            s_c[tid] = make_float2(r2.x, r2.y);
-            mask = strip_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+            const uint32_t w = plist[b0 + tid];
+            uint32_t id = w;
+            if (packed) {
+                id = w >> 8;
+                mask = w & 0xffu;
+            }
+            if (!packed || mask) {
+                const float4 *r = rec + (size_t)id * 3;
+                const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+                if (!packed) mask = block_mask_of_record(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+                s_a[tid] = r0;
+                s_b[tid] = r1;
+                s_c[tid] = make_float2(r2.x, r2.y);
+            }
         }
-#endif
 #pragma unroll
-        for (int sidx = 0; sidx < 8; sidx++) {
-            const uint32_t word = __ballot_sync(0xffffffffu, (mask >> sidx) & 1u);
-            if (lane == 0) s_member[sidx][wid] = word;
+        for (int blk = 0; blk < 8; blk++) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (mask >> blk) & 1u);
+            if (lane == 0) s_member[blk][wid] = word;
         }
-#if SGR_FWD_PIPELINED
-        issue(id_next, buf ^ 1u);  // the other buffer was released by the barrier above
-        id_cur = id_next;
-        id_next = fetch_id(b0 + 2 * BLEND_T);
-#endif
         __syncthreads();
         const uint32_t base_pos = b0 - lo;
 #ifdef SGR_BLEND_STATS
@@ -901,7 +926,7 @@ __global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *
                         const unsigned mc = __ballot_sync(0xffffffffu, cand), mh = __ballot_sync(0xffffffffu, hit);
                         const unsigned ml = __ballot_sync(0xffffffffu, !done);
                         if (lane == 0) {
-                            FWD_STAT(0, 1);            // strip-splat visits
+                            FWD_STAT(0, 1);            // block-splat visits
                             FWD_STAT(1, mc != 0);      // ... with a lane that passes the power test
                             FWD_STAT(2, mh != 0);      // ... with a lane that contributes
                             FWD_STAT(3, __popc(mc));   // lanes passing the power test
@@ -1033,8 +1058,8 @@ static int launch_binning_and_blend(const ViewConsts &v, int P, const GeomState 
 {
     const int T = v.gx * v.gy;
     SGR_LAUNCH(K_SCATTER, st,
-               scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, v.gx, geom.rect, geom.depth, img.tile_cursor,
-                                                               img.counters, capacity, bin.inst_a));
+               scatter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, v.gx, geom.rect, geom.depth, geom.rec, img.tile_cursor,
+                                                               img.counters, capacity, ids_packed(P) ? 1 : 0, bin.inst_a));
     sgr::prof_begin(K_SORT_SMEM, st);  // one timing bracket around the three size classes ...
     sgr::note_launches(2);             // ... but three launches
     const int small_grid = T < 296 ? T : 296;  // 2 CTAs per SM, grid-stride over tiles
@@ -1053,9 +1078,14 @@ static int launch_binning_and_blend(const ViewConsts &v, int P, const GeomState 
                tile_sort_kernel<1024, true><<<small_grid, 1024, 0, st>>>(img.tile_start, img.counters, capacity,
                                                                         bin.inst_a, bin.inst_b, bin.plist, T));
     SGR_LAUNCH(K_BLEND_FWD, st,
-               blend_forward_kernel<<<dim3(v.gx, v.gy), dim3(SGR_TILE, SGR_TILE), 0, st>>>(
-                   img.tile_start, bin.plist, geom.rec, img.counters, capacity, v.W, v.H, v.gx, v.bg, img.final_T,
-                   img.n_contrib, out_color));
+               if (ids_packed(P))
+                   blend_forward_kernel<true><<<T, BLEND_T, 0, st>>>(img.tile_order, img.tile_start, bin.plist, geom.rec,
+                                                                     img.counters, capacity, v.W, v.H, v.gx, v.bg,
+                                                                     img.final_T, img.n_contrib, out_color);
+               else
+                   blend_forward_kernel<false><<<T, BLEND_T, 0, st>>>(img.tile_order, img.tile_start, bin.plist, geom.rec,
+                                                                      img.counters, capacity, v.W, v.H, v.gx, v.bg,
+                                                                      img.final_T, img.n_contrib, out_color));
     SGR_CUDA(cudaGetLastError());
     return SGR_OK;
 }
@@ -1140,8 +1170,8 @@ int launch_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc geom_all
     a.tile_count = img.tile_count;
     SGR_LAUNCH(K_PREPROCESS, st, preprocess_kernel<<<(P + PRE_T - 1) / PRE_T, PRE_T, dyn, st>>>(a));
     SGR_LAUNCH(K_TILE_SCAN, st,
-               tile_scan_kernel<<<1, 1024, 0, st>>>(img.tile_count, img.tile_start, img.tile_cursor, img.counters, T,
-                                                    nullptr));
+               tile_scan_kernel<<<1, 1024, 0, st>>>(img.tile_count, img.tile_start, img.tile_cursor, img.tile_order,
+                                                    img.counters, T, nullptr));
     SGR_CUDA(cudaGetLastError());
     SGR_CUDA(cudaMemcpyAsync(slot->pinned, img.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SGR_CUDA(cudaEventRecord(slot->ev, st));

@@ -7,7 +7,7 @@
 //   rec    float4[3P]  48 B splat rec  final_T  f32[HW]                      inst_a  u64[C] depth|idx
 //   rect   ushort4[P]   8 B tile rect  n_contrib u32[HW]                     inst_b  u64[C] sort pong
 //   depth  f32[P]       4 B            tile_count u32[T]  tile_start u32[T+1] (plist is laid out FIRST)
-//   aux    u32[P]       4 B clamp bits tile_cursor u32[T] counters u32[16]
+//   aux    u32[P]       4 B clamp bits tile_cursor u32[T] tile_order u32[T] counters u32[16]
 //
 // Splat record (what the blend kernels gather, 48 B = 1.5 sectors instead of the reference's
 // three separate gathers xy / conic_opacity / rgb = 3-4 sectors):
@@ -53,11 +53,12 @@ struct ImageState {
     uint32_t *tile_count;
     uint32_t *tile_start;  // T+1
     uint32_t *tile_cursor;
+    uint32_t *tile_order;  // tiles by decreasing instance count: launch order of the blend kernels
     uint32_t *counters;    // [0] = num_rendered, [1] = overflow flag
     static size_t bytes(size_t W, size_t H)
     {
         size_t T = ((W + 15) / 16) * ((H + 15) / 16);
-        return 2 * align_up(W * H * 4) + 2 * align_up(T * 4) + align_up((T + 1) * 4) + align_up(64) + SGR_ALIGN;
+        return 2 * align_up(W * H * 4) + 3 * align_up(T * 4) + align_up((T + 1) * 4) + align_up(64) + SGR_ALIGN;
     }
     static ImageState carve(void *base, size_t W, size_t H)
     {
@@ -69,6 +70,7 @@ struct ImageState {
         s.tile_count = (uint32_t *)p; p += align_up(T * 4);
         s.tile_start = (uint32_t *)p; p += align_up((T + 1) * 4);
         s.tile_cursor = (uint32_t *)p; p += align_up(T * 4);
+        s.tile_order = (uint32_t *)p; p += align_up(T * 4);
         s.counters = (uint32_t *)p;
         return s;
     }
@@ -253,31 +255,110 @@ __device__ __forceinline__ float splat_power(float dx, float dy, float a, float 
 }
 
 
-// Conservative footprint of one splat inside a 16x16 tile, as an 8-bit mask over the tile's eight
-// 16x2 pixel strips (= warps of the blend kernels).  {d : power(d) >= tau} is the ellipse
-// d^T Q d <= -2 tau, Q = [[a,b],[b,c]], whose half extents are sqrt(-2 tau c/det), sqrt(-2 tau a/det).
-// A strip whose bit is clear cannot hold a pixel that passes the alpha test (tau already carries
-// a 1e-4 margin; 0.02 px + 1e-4 relative slack covers the rounding here), so skipping it never
-// changes a result.  Degenerate / non-finite inputs fall back to "every strip".
-__device__ __forceinline__ uint32_t strip_mask(float gx, float gy, float a, float b, float c, float tau, float tile_x0,
-                                               float tile_y0)
+// ---------------------------------------------------------------------------------------------
+// Footprint masks.  A 16x16 tile is cut into eight 8x4 pixel BLOCKS (= the warps of the blend
+// kernels): block w = band * 2 + half, band = 4-row band 0..3, half = left / right 8 columns.
+// A splat can only pass the alpha test at pixels with power >= tau, i.e. inside the ellipse
+//   a u^2 + 2 b u v + c v^2 <= k,  k = -2 tau,  (u, v) = pixel - centre
+// (tau already carries a 1e-4 margin on the power).  Bit w of a footprint mask is set when block w
+// may hold such a pixel; a clear bit is a proof that it does not, so skipping the block never changes
+// a result.  Mask 0 = the splat is dead in this tile (the reference's rectangle of 3 sigma_max is much
+// larger than the ellipse for anisotropic or faint splats: a third of all instances on the headline scene).
+//
+// EllipseBands: per-Gaussian constants; band_columns() gives, for the image rows [ra, rb] (clipped
+// to the ellipse's own row range), the absolute pixel-column interval [c_lo, c_hi] the ellipse reaches
+// inside that band -- exact up to the stated slack: the rightmost point of the ellipse within the band
+// sits at v = clamp(-(b/c) ex, band) because the boundary u_max(v) is concave.  The interval depends
+// on the band only, not on the tile column, so a Gaussian computes it once per band of its rectangle.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqrt_fast(float x)  // MUFU.SQRT: 2^-22 relative, covered by the slack below
 {
-    if (tau > 0.0f) return 0u;  // power <= 0 < tau for every pixel: never contributes
-    const float det = a * c - b * b, k = -2.0f * tau;
-    float ex = 3.0e38f, ey = 3.0e38f;
-    if (det > 0.0f && a > 0.0f && k < 3.0e38f) {
-        const float inv = 1.0f / det;
-        ex = sqrtf(k * c * inv) * 1.0001f + 0.02f;
-        ey = sqrtf(k * a * inv) * 1.0001f + 0.02f;
-    }
-    const float lx = gx - ex - tile_x0, hx = gx + ex - tile_x0;
-    const float ly = gy - ey - tile_y0, hy = gy + ey - tile_y0;
-    if (hx < 0.0f || lx > 15.0f || hy < 0.0f || ly > 15.0f) return 0u;
-    const int r0 = (int)ceilf(fmaxf(ly, 0.0f)), r1 = (int)floorf(fminf(hy, 15.0f));
-    if (r1 < r0) return 0u;  // between two pixel rows
-    const int s0 = r0 >> 1, s1 = r1 >> 1;
-    return ((2u << s1) - 1u) & ~((1u << s0) - 1u);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
+
+struct EllipseBands {
+    float gx, gy;        // centre (pixels)
+    float k_a, det_a2;   // k / a,  det / a^2
+    float b_a;           // b / a
+    float v_r;           // row offset of the rightmost point: -(b/c) ex   (the leftmost is at -v_r)
+    int r_lo, r_hi;      // rows the ellipse reaches (may exceed the image)
+    bool all;            // degenerate / non-finite: treat every block as reachable
+    bool dead;           // never reaches alpha >= 1/255 anywhere
+};
+
+__device__ __forceinline__ EllipseBands ellipse_bands(float gx, float gy, float a, float b, float c, float tau)
+{
+    EllipseBands e;
+    e.gx = gx;
+    e.gy = gy;
+    e.dead = tau > 0.0f;  // power <= 0 < tau for every pixel
+    const float det = a * c - b * b, k = -2.0f * tau;
+    e.all = !(det > 0.0f && a > 0.0f && c > 0.0f && k < 3.0e38f && k >= 0.0f);
+    e.k_a = e.det_a2 = e.b_a = e.v_r = 0.f;
+    e.r_lo = e.r_hi = 0;
+    if (!e.all && !e.dead) {
+        const float inv_det = __fdividef(1.0f, det), inv_a = __fdividef(1.0f, a);
+        const float ex = sqrt_fast(k * c * inv_det) * 1.0001f + 0.02f;
+        const float ey = sqrt_fast(k * a * inv_det) * 1.0001f + 0.02f;
+        e.k_a = k * inv_a * 1.0002f;
+        e.det_a2 = det * inv_a * inv_a;
+        e.b_a = b * inv_a;
+        e.v_r = -__fdividef(b, c) * ex;
+        e.r_lo = (int)ceilf(fmaxf(gy - ey, -1.0e6f));
+        e.r_hi = (int)floorf(fminf(gy + ey, 1.0e6f));
+        e.all = !(ex < 1.0e6f && ey < 1.0e6f);
+    }
+    return e;
+}
+
+// columns reached inside rows [ra, rb] (ra <= rb, both inside [r_lo, r_hi]); empty when c_hi < c_lo
+__device__ __forceinline__ void band_columns(const EllipseBands &e, int ra, int rb, int &c_lo, int &c_hi)
+{
+    const float v0 = (float)ra - e.gy, v1 = (float)rb - e.gy;
+    const float vr = fminf(fmaxf(e.v_r, v0), v1), vl = fminf(fmaxf(-e.v_r, v0), v1);
+    const float wr = sqrt_fast(fmaxf(e.k_a - e.det_a2 * vr * vr, 0.0f)) * 1.0001f + 0.02f;
+    const float wl = sqrt_fast(fmaxf(e.k_a - e.det_a2 * vl * vl, 0.0f)) * 1.0001f + 0.02f;
+    const float xmax = e.gx - e.b_a * vr + wr, xmin = e.gx - e.b_a * vl - wl;
+    c_lo = (int)ceilf(fmaxf(xmin, -1.0e6f));
+    c_hi = (int)floorf(fminf(xmax, 1.0e6f));
+}
+
+// footprint mask of one splat in the tile whose first pixel is (tile_x0, tile_y0): four bands, two halves
+__device__ __forceinline__ uint32_t block_mask(const EllipseBands &e, int tile_x0, int tile_y0)
+{
+    if (e.dead) return 0u;
+    if (e.all) return 0xffu;
+    uint32_t m = 0;
+#pragma unroll
+    for (int band = 0; band < 4; band++) {
+        const int ra = max(tile_y0 + 4 * band, e.r_lo), rb = min(tile_y0 + 4 * band + 3, e.r_hi);
+        if (ra > rb) continue;
+        int c_lo, c_hi;
+        band_columns(e, ra, rb, c_lo, c_hi);
+        if (c_hi < c_lo) continue;
+        const uint32_t left = (c_lo <= tile_x0 + 7 && c_hi >= tile_x0) ? 1u : 0u;
+        const uint32_t right = (c_lo <= tile_x0 + 15 && c_hi >= tile_x0 + 8) ? 2u : 0u;
+        m |= (left | right) << (2 * band);
+    }
+    return m;
+}
+
+// Footprint mask straight from a staged splat record, for lists that carry none (P > 2^24 Gaussians;
+// the blend kernels are instantiated once per list format so this costs the common one nothing).
+__device__ __forceinline__ uint32_t block_mask_of_record(float x, float y, float a, float b, float c, float tau,
+                                                         int tile_x0, int tile_y0)
+{
+    return block_mask(ellipse_bands(x, y, a, b, c, tau), tile_x0, tile_y0);
+}
+
+// Instance words carry the footprint mask next to the Gaussian id when the ids fit 24 bits:
+//   low word of the sort key = id << 8 | mask   (the order by (depth, id) is unchanged: ids are unique)
+// and the sorted list the blend kernels read holds the same low words.  For P > 2^24 Gaussians the low
+// word is the plain id and the blend kernels compute the mask while staging the record.
+#define SGR_PACKED_MAX_P (1 << 24)
+bool ids_packed(int P);  // host (sgr_api.cu): P <= 2^24, unless SGR_FORCE_UNPACKED_IDS=1 (tests of the other format)
 
 __device__ __forceinline__ float warp_sum(float v)
 {

@@ -139,3 +139,71 @@ def test_two_forwards_in_flight_on_two_streams():
         torch.cuda.synchronize()
         assert g1["num_rendered"] == want1["num_rendered"] and g2["num_rendered"] == want2["num_rendered"]
         assert torch.equal(g1["color"], want1["color"]) and torch.equal(g2["color"], want2["color"])
+
+
+@pytest.mark.parametrize("scene_kw", [dict(), dict(px_sigma=6.0), dict(mesh_bound=True), dict(px_sigma=0.6)],
+                         ids=["default", "large", "flat", "tiny"])
+def test_footprint_masks_are_conservative_and_tight(scene_kw):
+    """The per-instance footprint masks (which 8x4 blocks of its tile a splat can reach, computed once in the
+    scatter kernel and used by both blend kernels to skip work) must never clear a block that holds a pixel
+    passing the reference's alpha test (forward.cu:333-347), and should not be much looser than the truth."""
+    import torch
+    from sugar_b200 import _C, diff_gaussian_rasterization as ours, scenes
+    P, W, H = 20_000, 320, 192
+    sc = scenes.make_scene(P, W, H, seed=5, camera="posed", **scene_kw)
+    a = h.run_module(ours, sc, (0, 0, 0), None, use_sh=True, sh_degree=1)
+    R = a["num_rendered"]
+    st = _C.inspect_state(P, W, H, R, a["geom"], a["binning"], a["img"])
+    gx = (W + 15) // 16
+    tile = (st["keys"] >> 32).long()
+    ids = st["point_list"].long()
+    fp = st["footprint"].long()
+    m2, co = st["means2D"][ids], st["conic_opacity"][ids]
+    ty, tx = tile // gx, tile % gx
+    px = (tx[:, None, None] * 16 + torch.arange(16, device="cuda")[None, None, :]).float()   # [R,1,16]
+    py = (ty[:, None, None] * 16 + torch.arange(16, device="cuda")[None, :, None]).float()   # [R,16,1]
+    dx, dy = m2[:, 0, None, None] - px, m2[:, 1, None, None] - py
+    power = -0.5 * (co[:, 0, None, None] * dx * dx + co[:, 2, None, None] * dy * dy) - co[:, 1, None, None] * dx * dy
+    alpha = torch.clamp(co[:, 3, None, None] * torch.exp(power), max=0.99)
+    hit = (power <= 0) & (alpha >= 1.0 / 255.0)                                              # [R,16(y),16(x)]
+    blocks = hit.view(R, 4, 4, 2, 8).any(dim=4).any(dim=2)                                   # [R, band, half]
+    truth = (blocks.long() * (1 << (torch.arange(4, device="cuda")[:, None] * 2 + torch.arange(2, device="cuda")[None, :]))).sum((1, 2))
+    missed = truth & ~fp
+    assert int((missed != 0).sum()) == 0, "a footprint mask clears a block that holds a contributing pixel"
+    pop = lambda v: sum(((v >> b) & 1) for b in range(8)).sum().item()
+    assert pop(fp) <= 1.25 * pop(truth) + 64, (pop(fp), pop(truth))
+    assert int((fp == 0).sum()) > 0  # some instances are dead in their tile (the rect is 3 sigma_max wide)
+
+
+def test_unpacked_instance_lists_give_identical_results():
+    """P > 2^24 Gaussians cannot carry the footprint mask next to the id; the blend kernels then compute it
+    while staging.  SGR_FORCE_UNPACKED_IDS=1 selects that format at any P (read once per process, hence the
+    subprocess): image, radii and gradients must equal the packed format's."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    import torch
+    from sugar_b200 import diff_gaussian_rasterization as ours, scenes
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+import helpers as h
+from sugar_b200 import diff_gaussian_rasterization as ours, scenes
+sc = scenes.make_scene(60000, 480, 270, seed=9, camera="posed")
+o = h.run_module(ours, sc, (0.2, 0.1, 0.0), scenes.upstream_grad(480, 270), use_sh=True, sh_degree=3)
+np.savez(sys.argv[1], color=o["color"].cpu().numpy(), radii=o["radii"].cpu().numpy(), R=o["num_rendered"],
+         **{"g_" + k: v.cpu().numpy() for k, v in o["grads"].items()})
+''' % (h.ROOT, h.ROOT)
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "u.npz")
+        env = dict(os.environ, SGR_FORCE_UNPACKED_IDS="1")
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=600)
+        u = np.load(out)
+    sc = scenes.make_scene(60000, 480, 270, seed=9, camera="posed")
+    p = h.run_module(ours, sc, (0.2, 0.1, 0.0), scenes.upstream_grad(480, 270), use_sh=True, sh_degree=3)
+    assert int(u["R"]) == p["num_rendered"]
+    assert np.array_equal(u["radii"], p["radii"].cpu().numpy())
+    assert np.array_equal(u["color"].view(np.int32), p["color"].cpu().numpy().view(np.int32))
+    for k, g in p["grads"].items():
+        assert h.rel_err(u["g_" + k], g.cpu().numpy()) <= GRAD_RTOL, k
