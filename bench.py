@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sh-factors", action="store_true",
                     help="N>1: all-reduce the full dL_dsh instead of all-gathering the SH factors")
+    ap.add_argument("--chunks", type=int, default=4,
+                    help="N>1: Gaussian ranges of the per-Gaussian backward pass; each range's all-reduce overlaps the next")
     return ap.parse_args()
 
 
@@ -225,6 +227,47 @@ def cpu_baseline_density(args):
                       f"({cores} threads), {dt*1e3:.0f} ms per call"}
 
 
+def verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D, sh_factors, chunks):
+    """N > 1, before any timing: on a small scene every rank renders its own view twice -- once with the
+    exchange inside the backward, once plainly followed by an ordinary all-reduce of each gradient -- and the
+    two sets of summed gradients must agree.  Returns the largest |a-b|_inf / |b|_inf over tensors and ranks."""
+    P, W, H = 200_000, 640, 360
+    sc = scenes.make_scene(P, W, H, seed=3)
+    sc = scenes.with_camera_offset(sc, 0.04 * rank, (0.05 * rank, 0.0, 0.0))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    names = ("means3D", "scales", "rotations", "opacities", "shs")
+    dL = t(scenes.upstream_grad(W, H, seed=2 + rank))
+    st = mod.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy,
+                                           bg=torch.zeros(3, device=dev), scale_modifier=1.0, viewmatrix=t(sc.viewmatrix),
+                                           projmatrix=t(sc.projmatrix), sh_degree=D, campos=t(sc.campos),
+                                           prefiltered=False, debug=False)
+
+    def run():
+        ps = {k: t(getattr(sc, k)).requires_grad_(True) for k in names}
+        m2 = torch.zeros_like(ps["means3D"], requires_grad=True)
+        color, _ = mod.GaussianRasterizer(st)(means3D=ps["means3D"], means2D=m2, opacities=ps["opacities"],
+                                              shs=ps["shs"], scales=ps["scales"], rotations=ps["rotations"])
+        torch.autograd.backward(color, dL)
+        return ps
+    plain = run()
+    for k in names:
+        dist.all_reduce(plain[k].grad)
+    vp = parallel.ViewParallel(sh_factors=sh_factors, chunks=chunks)
+    with vp.context():
+        ex = run()
+    worst = 0.0
+    for k in names:
+        a, b = ex[k].grad, plain[k].grad
+        worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+    w = torch.tensor([worst], device=dev)
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    worst = float(w.item())
+    if not worst <= 1e-4:
+        raise RuntimeError(f"view-parallel exchange disagrees with a plain all-reduce: rel err {worst:.3e}")
+    return {"max_rel_err": worst, "tolerance": 1e-4, "scene": f"{P} Gaussians {W}x{H}, one view per rank",
+            "collectives_per_backward": vp.stats["collectives"]}
+
+
 def main():
     args = parse()
     import torch
@@ -286,21 +329,23 @@ def main():
     dL_h = torch.from_numpy(scenes.upstream_grad(W, H, seed=1 + rank) / max(world, 1)).pin_memory()
     viewmatrix, projmatrix, campos, bg, dL = (x.to(dev) for x in (viewmatrix_h, projmatrix_h, campos_h, bg_h, dL_h))
 
-    # every rank knows the whole batch's cameras (seeded view schedule): all positions, [world,3]
-    campos_all = campos.reshape(1, 3).repeat(max(world, 1), 1).contiguous()
 
     def settings(vm, pm, cp, b):
         return mod.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy,
                                                  bg=b, scale_modifier=1.0, viewmatrix=vm, projmatrix=pm, sh_degree=D,
                                                  campos=cp, prefiltered=False, debug=False)
 
-    arena = None
+    exchange_check = None
     if dist is not None:
+        # view-parallel exchange inside the op's backward (sugar_b200/parallel.py): SH factors all-gathered,
+        # the other 44 B/Gaussian all-reduced chunk by chunk underneath the per-Gaussian pass
+        import contextlib
         from sugar_b200 import parallel
-        arena = parallel.GradArena(P, 16, dev)
-        if not args.no_sh_factors:
-            # all-gather 12 B/Gaussian SH factors instead of all-reducing 192 B/Gaussian of dL_dsh
-            parallel.set_sh_factor_mode(True)
+        vp = parallel.ViewParallel(sh_factors=not args.no_sh_factors, chunks=args.chunks)
+        exchange_check = verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D,
+                                         sh_factors=not args.no_sh_factors, chunks=args.chunks)
+        stack = contextlib.ExitStack()
+        stack.enter_context(vp.context())  # the autograd node keeps the context for the backward thread
 
     def zero_grads():
         for p in params.values():
@@ -312,8 +357,6 @@ def main():
         color, radii = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
                             shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
         torch.autograd.backward(color, dL)
-        if arena is not None:
-            arena.all_reduce_from(params, campos=campos_all, sh_degree=D)
         zero_grads()
         return radii
 
@@ -350,8 +393,6 @@ def main():
                             shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
         loss = (color * g).sum()
         loss.backward()
-        if arena is not None:
-            arena.all_reduce_from(params, campos=campos_all, sh_degree=D)
         # device -> host read of the step's result
         loss_ring[(e2e_state["i"] - 1) % loss_ring.numel()].copy_(loss.detach(), non_blocking=True)
         zero_grads()
@@ -435,7 +476,9 @@ def main():
                       "visible": V_vis, "l2_policy": "inputs (708 MB of Gaussian parameters) larger than L2; no flush"},
            "parallelism": {"mode": f"view-dp{world}" if world > 1 else "single",
                            "exchange": ("none" if world == 1 else "all-reduce 236 B/Gaussian" if args.no_sh_factors else
-                                        "all-reduce 44 B/Gaussian + all-gather 12 B/Gaussian/view SH factors")},
+                                        f"inside the backward: all-gather 12 B/Gaussian/view SH factors under the "
+                                        f"per-Gaussian pass + all-reduce 44 B/Gaussian in {args.chunks} overlapped chunks"),
+                           "exchange_check": exchange_check},
            "clocks": clk}
     n_e2e = 1 if use_ref else world
     out["e2e"] = {"value": n_e2e / (ms_e2e * 1e-3), "unit": "views/s",

@@ -94,9 +94,12 @@ SGR_API int sgr_rasterize_forward(const SgrView *view, const SgrGaussians *g,
  * pass uninitialised memory.  `grad_scratch` must hold sgr_backward_scratch_bytes(P).
  *   dL_dmeans2D f32[P,3], dL_dcolors f32[P,3], dL_dopacity f32[P,1], dL_dmeans3D f32[P,3],
  *   dL_dcov3D f32[P,6], dL_dsh f32[P,M,3], dL_dscales f32[P,3], dL_drotations f32[P,4].
- * dL_dsh may be NULL: when M == 0, or with SH present to select "factor mode" -- dL_dsh is not
- * produced and dL_dcolors holds the clamp-masked dL/dRGB per Gaussian, from which
- * sgr_sh_grad_from_factors rebuilds (the sum over views of) dL_dsh.  All other outputs are unchanged. */
+ * dL_dcolors is the gradient of colors_precomp when colours were precomputed; with SH colours it is the
+ * clamp-masked dL/dRGB per Gaussian (the reference's value is unmasked there, but no caller can observe
+ * it: colors_precomp is absent).  dL_dsh may be NULL: when M == 0, or with SH present to select "factor
+ * mode" -- dL_dsh is not produced, and sgr_view_grad_finalize / sgr_sh_grad_from_factors rebuild (the sum over
+ * views of) dL_dsh from dL_dcolors.  All other outputs are unchanged.  Output pointers that are 16-byte aligned
+ * leave through TMA bulk stores. */
 SGR_API int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii,
                            const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
                            int64_t num_rendered, const float *dL_dout_color,
@@ -105,25 +108,52 @@ SGR_API int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, c
                            float *dL_dscales, float *dL_drotations,
                            void *grad_scratch, void *stream);
 
-/* The same backward with a stage hook.  In factor mode (SH present, dL_dsh == NULL) and with a
- * non-NULL hook, the masked dL/dRGB factors are produced by their own small kernel right after the
- * blend pass and `hook(hook_ctx, SGR_STAGE_SH_FACTORS_READY)` is called on the host at that point of
- * the enqueue: everything enqueued on `stream` so far makes dL_dcolors final, so the caller can record
- * an event / start the all-gather of the factors there and have it overlap the per-Gaussian backward
- * that is enqueued next.  Otherwise identical to sgr_rasterize_backward. */
-#define SGR_STAGE_SH_FACTORS_READY 1
+/* The same backward with a plan: stage hooks, a chunked per-Gaussian pass and record-form outputs.  This is
+ * what the view-parallel (one view per GPU) step drives, sugar_b200/parallel.py; the reference has no
+ * counterpart (it renders one view on one GPU, sugar_trainers/coarse_sdf.py:98,507).
+ *
+ * hook(hook_ctx, stage) is called on the HOST, between kernel enqueues on `stream`:
+ *   SGR_STAGE_BLEND_DONE        the blend pass is enqueued: everything on `stream` so far makes dL_dcolors final.
+ *                               With SH colours dL_dcolors holds the clamp-masked dL/dRGB per Gaussian -- this
+ *                               view's rank-1 SH factor: a caller that exchanges factors instead of dL_dsh
+ *                               (dL_dsh == NULL, "factor mode") starts its all-gather here, underneath the
+ *                               per-Gaussian pass that is enqueued next.
+ *   SGR_STAGE_CHUNK_DONE + c    chunk c of the per-Gaussian pass is enqueued: its rows of every per-Gaussian
+ *                               output are final on `stream`; the caller can start reducing them while the
+ *                               next chunk is computed.
+ * num_chunks (<= 1: one) splits the per-Gaussian pass into Gaussian ranges; sgr_backward_chunk_range() gives
+ * the range [p0, p1) of a chunk.
+ * reduce_records (optional, f32[P,11]): when non-NULL the pass writes (dL_dmeans3D 3 | dL_dopacity 1 |
+ * dL_dscales 3 | dL_drotations 4) of Gaussian i as ONE 44-byte record there INSTEAD of the four arrays
+ * (whose pointers are then ignored), so that a chunk's all-reduce is one contiguous range;
+ * sgr_view_grad_finalize() splits the reduced records back into the arrays. */
+#define SGR_STAGE_BLEND_DONE 1
+#define SGR_STAGE_CHUNK_DONE 16
 typedef void (*SgrStageHook)(void *ctx, int32_t stage);
+typedef struct SgrBackwardPlan {
+    SgrStageHook hook; /* may be NULL */
+    void *hook_ctx;
+    int32_t num_chunks;
+    float *reduce_records; /* may be NULL */
+} SgrBackwardPlan;
 SGR_API int sgr_rasterize_backward_staged(const SgrView *view, const SgrGaussians *g, const int32_t *radii,
                                           const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
                                           int64_t num_rendered, const float *dL_dout_color, float *dL_dmeans2D,
                                           float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D, float *dL_dcov3D,
                                           float *dL_dsh, float *dL_dscales, float *dL_drotations, void *grad_scratch,
-                                          void *stream, SgrStageHook hook, void *hook_ctx);
+                                          void *stream, const SgrBackwardPlan *plan);
+SGR_API int sgr_backward_chunk_range(int32_t P, int32_t num_chunks, int32_t chunk, int32_t *p0, int32_t *p1);
 
-/* dL_dsh[P,M,3] = sum over views v of basis_k(normalize(mean - campos[v])) * dRGB[v][P,3]  (the SH
- * part of backward.cu:20-139 is an outer product per view).  Used by the view-parallel step: ranks
- * all-gather the 12 B/Gaussian factors instead of all-reducing 12*M B/Gaussian of dL_dsh.
- *   campos f32[V,3], dRGB f32[V,P,3] (clamp-masked, from factor mode), dL_dsh f32[P,M,3] fully written. */
+/* Epilogue of the view-parallel step for the Gaussians [p0, p1), after the exchange (either half optional):
+ *  - dL_dsh[P,M,3] rows = sum over views v of basis_k(normalize(mean - campos[v])) * dRGB[v][P,3]  (the SH part of
+ *    backward.cu:20-139 is an outer product per view): campos f32[V,3], dRGB f32[V,P,3] = the gathered factors;
+ *  - reduced_records f32[P,11] (all-reduced) are split into dL_dmeans3D / dL_dopacity / dL_dscales / dL_drotations.
+ * Every output row of the range is fully written; `scale` (e.g. 1/num_views) multiplies everything. */
+SGR_API int sgr_view_grad_finalize(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree, int32_t num_views,
+                                   const float *means3D, const float *campos, const float *dRGB, float *dL_dsh,
+                                   const float *reduced_records, float scale, float *dL_dmeans3D, float *dL_dopacity,
+                                   float *dL_dscales, float *dL_drotations, void *stream);
+/* The SH half alone, over all Gaussians (kept for callers that only exchange factors). */
 SGR_API int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float *means3D,
                                      const float *campos, const float *dRGB, float *dL_dsh, void *stream);
 
@@ -214,6 +244,25 @@ SGR_API int sgr_normal_loss_backward(int32_t N, int32_t K, int32_t P, const floa
                                      const int64_t *nbr_idx, const float *points, const float *scaling,
                                      const float *quaternions, const float *nbr_opacity, const float *g_loss,
                                      float *g_quaternions, void *scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gaussians bound to a triangle mesh (refinement stage): the property code of a bound SuGaR model,
+ * sugar_scene/sugar_model.py:384-398 (points), :415-441 (scaling), :443-479 (quaternions), as one kernel
+ * and its backward.  F faces, n_per Gaussians per face (P = F * n_per), V vertices.
+ *   verts f32[V,3], faces i64[F,3], bary f32[n_per,3] (surface_triangle_bary_coords, device memory),
+ *   scales_raw f32[P,2] (_scales: log of the two in-plane scales), complex_raw f32[P,2] (_quaternions: the
+ *   learned in-plane rotation as a complex number, normalised here), thickness = surface_mesh_thickness.
+ * Outputs, fully written: points f32[P,3], scaling f32[P,3] = (thickness, exp, exp), quaternions f32[P,4]
+ * (normalised, w first; pytorch3d 0.7.4 matrix_to_quaternion of [normal | rotated edge | cross]).
+ * Backward: g_verts f32[V,3] (zeroed here, then accumulated), g_scales_raw, g_complex_raw f32[P,2] fully written.
+ * ------------------------------------------------------------------------------------------ */
+SGR_API int sgr_meshbind_forward(int32_t F, int32_t n_per, int32_t V, const float *verts, const int64_t *faces,
+                                 const float *bary, const float *scales_raw, const float *complex_raw, float thickness,
+                                 float *points, float *scaling, float *quaternions, void *stream);
+SGR_API int sgr_meshbind_backward(int32_t F, int32_t n_per, int32_t V, const float *verts, const int64_t *faces,
+                                  const float *bary, const float *scales_raw, const float *complex_raw,
+                                  const float *g_points, const float *g_scaling, const float *g_quaternions,
+                                  float *g_verts, float *g_scales_raw, float *g_complex_raw, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Exact K-nearest-neighbour search (uniform grid).  Replaces pytorch3d.ops.knn_points as SuGaR

@@ -226,77 +226,65 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     return R, out_color, radii, geom_t, binning_t, img_t
 
 
-# View-parallel "SH factor mode" (sugar_b200/parallel.py): when True the backward does not produce
-# dL_dsh (the returned tensor is the uninitialised arena slot) and dL_dcolors carries the clamp-masked
-# dL/dRGB factor; parallel.GradArena rebuilds the summed dL_dsh after an all-gather of the factors.
-SH_FACTOR_MODE = False
-# Optional callable(dRGB [P,3]) invoked (factor mode only) at the point of the backward's enqueue where
-# the factors are final on the stream, i.e. before the per-Gaussian backward is enqueued: the
-# view-parallel step starts its all-gather there (include/sugar_b200.h, sgr_rasterize_backward_staged).
-FACTOR_HOOK = None
+_PART_ALIGN = 16  # floats: every gradient array starts on a 64-byte boundary (TMA bulk stores need 16)
+
+
+def _alloc_backward(P: int, M: int, dev, with_records: bool):
+    """All eight gradients (+ the 44-byte reduce records of the view-parallel step) + the accumulator scratch in
+    ONE rounded allocation: a stable size for the caching allocator, one free when autograd lets go."""
+    widths = [("means3D", 3), ("opacity", 1), ("scales", 3), ("rotations", 4), ("sh", 3 * M), ("means2D", 3),
+              ("colors", 3), ("cov3D", 6)]
+    if with_records:
+        widths.append(("records", 11))
+    n_scratch = (lib.sgr_backward_scratch_bytes(P) + 3) // 4 if P else 0
+    offs, o = {}, 0
+    for name, w in widths:
+        offs[name] = o
+        o = _round_up(o + P * w, _PART_ALIGN)
+    total = o + n_scratch + 64
+    flat = _big_empty(_round_up(4 * total, _ROUND) // 4, torch.float32, dev)
+    skew = (-(flat.data_ptr() // 4)) % _PART_ALIGN  # the allocator aligns to 512 B; be explicit anyway
+    shapes = {"means3D": (P, 3), "opacity": (P, 1), "scales": (P, 3), "rotations": (P, 4), "sh": (P, M, 3),
+              "means2D": (P, 3), "colors": (P, 3), "cov3D": (P, 6), "records": (P, 11)}
+    bufs = {name: flat[skew + offs[name]:skew + offs[name] + P * w].view(shapes[name]) for name, w in widths}
+    bufs["scratch"] = flat[skew + o:skew + o + n_scratch]
+    return bufs
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh,
                                  degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, *,
                                  context: Context = None):
-    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:118-196)."""
+    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:118-196).  With a view-parallel exchange attached to
+    `context` (sugar_b200/parallel.py) the gradients come back already summed over the ranks."""
     context = context or current_context()
     dev = means3D.device
     P, H, W = means3D.size(0), dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    ex = context.exchange if (context.exchange is not None and context.exchange.enabled()) else None
     with torch.cuda.device(dev):
-        # All eight gradients + the accumulator scratch live in ONE rounded allocation.  The first
-        # (3 + 1 + 3 + 4 + 3M) * P floats are exactly the multi-GPU all-reduce arena
-        # [means3D | opacity | scales | rotations | sh] (sugar_b200/parallel.py), so the view-parallel
-        # step reduces them in place without packing (sh last: factor mode reduces only the 11P prefix).
-        widths = (3, 1, 3, 4, 3 * M, 3, 3, 6)
-        n_scratch = (lib.sgr_backward_scratch_bytes(P) + 3) // 4 if P else 0
-        flat = _big_empty(_round_up(4 * (P * sum(widths) + n_scratch) + 256, _ROUND) // 4, torch.float32, dev)
-        offs, o = [], 0
-        for w in widths:
-            offs.append(o)
-            o += P * w
-        part = lambda k, shape: flat[offs[k]:offs[k] + P * widths[k]].view(shape)
-        dL_dmeans3D = part(0, (P, 3))
-        dL_dopacity = part(1, (P, 1))
-        dL_dscales = part(2, (P, 3))
-        dL_drotations = part(3, (P, 4))
-        dL_dsh = part(4, (P, M, 3))
-        dL_dmeans2D = part(5, (P, 3))
-        dL_dcolors = part(6, (P, 3))
-        dL_dcov3D = part(7, (P, 6))
+        b = _alloc_backward(P, M, dev, with_records=ex is not None)
         if P != 0:
             means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color = map(
                 _c, (means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color))
             background, viewmatrix, projmatrix, campos = map(_c, (background, viewmatrix, projmatrix, campos))
-            scratch = flat[o:o + n_scratch]
             view = _view_struct(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, degree,
                                 campos, False, debug)
             # opacities are not an input of the reference's backward; the forward stored them
             g = _gauss_struct(P, M, means3D, None, sh, colors, scales, rotations, cov3D_precomp)
             stream = torch.cuda.current_stream(dev).cuda_stream
+            factor = ex is not None and bool(M) and ex.sh_factors
             args = (C.byref(view), C.byref(g), radii.data_ptr(), geomBuffer.data_ptr(), binningBuffer.data_ptr(),
-                    imageBuffer.data_ptr(), int(R), _ptr(dL_dout_color, "dL_dout_color"), dL_dmeans2D.data_ptr(),
-                    dL_dcolors.data_ptr(), dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(),
-                    dL_dsh.data_ptr() if (M and not SH_FACTOR_MODE) else None, dL_dscales.data_ptr(),
-                    dL_drotations.data_ptr(), scratch.data_ptr(), stream)
-            if M and SH_FACTOR_MODE and FACTOR_HOOK is not None:
-                failure = []
-
-                def _stage(_ctx, _stage_id):
-                    try:
-                        FACTOR_HOOK(dL_dcolors)
-                    except BaseException as e:  # never unwind through the C frame
-                        failure.append(e)
-
-                cb = _lib.STAGE_HOOK(_stage)
-                check(lib.sgr_rasterize_backward_staged(*args, cb, None))
-                if failure:
-                    raise failure[0]
-            else:
+                    imageBuffer.data_ptr(), int(R), _ptr(dL_dout_color, "dL_dout_color"), b["means2D"].data_ptr(),
+                    b["colors"].data_ptr(), b["opacity"].data_ptr(), b["means3D"].data_ptr(), b["cov3D"].data_ptr(),
+                    b["sh"].data_ptr() if (M and not factor) else None, b["scales"].data_ptr(),
+                    b["rotations"].data_ptr(), b["scratch"].data_ptr(), stream)
+            if ex is None:
                 check(lib.sgr_rasterize_backward(*args))
-    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+            else:
+                ex.run_backward(lib, check, _lib.STAGE_HOOK, _lib.SgrBackwardPlan, args, b, P, M, int(degree), means3D,
+                                campos, has_cov_precomp=cov3D_precomp is not None and cov3D_precomp.numel() != 0)
+    return (b["means2D"], b["colors"], b["opacity"], b["means3D"], b["cov3D"], b["sh"], b["scales"], b["rotations"])
 
 
 def mark_visible(means3D, viewmatrix, projmatrix) -> torch.Tensor:

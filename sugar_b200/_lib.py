@@ -42,6 +42,12 @@ class SgrFieldParams(C.Structure):
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 STAGE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32)
 
+
+class SgrBackwardPlan(C.Structure):
+    _fields_ = [("hook", STAGE_HOOK), ("hook_ctx", C.c_void_p), ("num_chunks", C.c_int32),
+                ("reduce_records", C.c_void_p)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 PROTOTYPES = {
     "sgr_rasterize_forward": (C.c_int, [C.POINTER(SgrView), C.POINTER(SgrGaussians), ALLOC_FN, C.c_void_p, ALLOC_FN,
@@ -50,7 +56,9 @@ PROTOTYPES = {
     "sgr_rasterize_backward": (C.c_int, [C.POINTER(SgrView), C.POINTER(SgrGaussians)] + [C.c_void_p] * 4 +
                                [C.c_int64] + [C.c_void_p] * 11),
     "sgr_rasterize_backward_staged": (C.c_int, [C.POINTER(SgrView), C.POINTER(SgrGaussians)] + [C.c_void_p] * 4 +
-                                      [C.c_int64] + [C.c_void_p] * 11 + [STAGE_HOOK, C.c_void_p]),
+                                      [C.c_int64] + [C.c_void_p] * 11 + [C.POINTER(SgrBackwardPlan)]),
+    "sgr_backward_chunk_range": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "sgr_view_grad_finalize": (C.c_int, [C.c_int32] * 6 + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 5),
     "sgr_mark_visible": (C.c_int, [C.c_int32] + [C.c_void_p] * 5),
     "sgr_sh_grad_from_factors": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "sgr_geometry_bytes": (C.c_size_t, [C.c_int32]),
@@ -64,6 +72,8 @@ PROTOTYPES = {
     "sgr_normal_loss_backward": (C.c_int, [C.c_int32] * 3 + [C.c_void_p] * 11),
     "sgr_field_forward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 12),
     "sgr_field_backward": (C.c_int, [C.POINTER(SgrFieldParams)] + [C.c_void_p] * 17),
+    "sgr_meshbind_forward": (C.c_int, [C.c_int32] * 3 + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 4),
+    "sgr_meshbind_backward": (C.c_int, [C.c_int32] * 3 + [C.c_void_p] * 12),
     "sgr_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_knn": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                           C.c_void_p]),

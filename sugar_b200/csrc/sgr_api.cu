@@ -75,7 +75,7 @@ bool ids_packed(int P)
         const char *e = getenv("SGR_FORCE_UNPACKED_IDS");
         return e && e[0] == '1';
     }();
-    return !force_unpacked && P <= SGR_PACKED_MAX_P;
+    return !force_unpacked && P < SGR_PACKED_MAX_P;  // strict: id 0xffffff | mask 0xff would read as the "no record" word
 }
 
 static int validate(const SgrView *view, const SgrGaussians *g, bool forward)
@@ -142,7 +142,7 @@ __global__ void inspect_geom_kernel(int P, GeomState g, const int32_t *radii_unu
         r1 = g.rec[(size_t)i * 3 + 1];
         r2 = g.rec[(size_t)i * 3 + 2];
         d = g.depth[i];
-        aux = g.aux[i];
+        aux = __float_as_uint(r2.z);
     }
     if (depths) depths[i] = d;
     if (means2D) {
@@ -269,7 +269,7 @@ const char *sgr_version(void) { return "sugar_b200 0.1 (sm_100a)"; }
 size_t sgr_geometry_bytes(int32_t P) { return GeomState::bytes((size_t)(P < 0 ? 0 : P)); }
 size_t sgr_binning_bytes(int64_t capacity) { return BinState::bytes((size_t)(capacity < 0 ? 0 : capacity)); }
 size_t sgr_image_bytes(int32_t width, int32_t height) { return ImageState::bytes((size_t)width, (size_t)height); }
-size_t sgr_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P < 0 ? 0 : P) * 48) + SGR_ALIGN; }
+size_t sgr_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P < 0 ? 0 : P) * 32) + SGR_ALIGN; }
 
 int sgr_rasterize_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc geom_alloc, void *geom_ctx,
                           SgrAlloc binning_alloc, void *binning_ctx, SgrAlloc image_alloc, void *image_ctx,
@@ -299,19 +299,20 @@ int sgr_rasterize_backward_staged(const SgrView *view, const SgrGaussians *g, co
                            const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
                            const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
                            float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales,
-                           float *dL_drotations, void *grad_scratch, void *stream, SgrStageHook hook, void *hook_ctx)
+                           float *dL_drotations, void *grad_scratch, void *stream, const SgrBackwardPlan *plan)
 {
     int rc = validate(view, g, false);
     if (rc) return rc;
     if (g->P == 0) return SGR_OK;
+    const bool records = plan && plan->reduce_records;
     if (!radii || !geom_buffer || !binning_buffer || !image_buffer || !dL_dout_color || !dL_dmeans2D || !dL_dcolors ||
-        !dL_dopacity || !dL_dmeans3D || !dL_dcov3D || !dL_dscales || !dL_drotations || !grad_scratch) {
+        !dL_dcov3D || !grad_scratch || (!records && (!dL_dopacity || !dL_dmeans3D || !dL_dscales || !dL_drotations))) {
         set_error("null pointer passed to sgr_rasterize_backward");
         return SGR_EINVAL;
     }
     return launch_backward(view, g, radii, geom_buffer, binning_buffer, image_buffer, num_rendered, dL_dout_color,
                            dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
-                           dL_drotations, grad_scratch, (cudaStream_t)stream, hook, hook_ctx);
+                           dL_drotations, grad_scratch, (cudaStream_t)stream, plan);
 }
 
 int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
@@ -322,7 +323,7 @@ int sgr_rasterize_backward(const SgrView *view, const SgrGaussians *g, const int
 {
     return sgr_rasterize_backward_staged(view, g, radii, geom_buffer, binning_buffer, image_buffer, num_rendered,
                                          dL_dout_color, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D,
-                                         dL_dsh, dL_dscales, dL_drotations, grad_scratch, stream, nullptr, nullptr);
+                                         dL_dsh, dL_dscales, dL_drotations, grad_scratch, stream, nullptr);
 }
 
 int sgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,

@@ -22,11 +22,18 @@ namespace sgr {
 constexpr int BWD_B = 128;  // Gaussians per shared-memory batch
 constexpr int BWD_NW = 8;   // warps per CTA (16x16 pixels)
 
-// accumulator record, 12 floats per Gaussian:
-//   [0] dmean2D.x [1] dmean2D.y [2] dconic.x [3] dconic.y | [4] dconic.w [5] dopacity [6] dR [7] dG | [8] dB
+// Blend accumulators (zeroed by a memset before the blend pass):
+//   gacc   f32[P][8]  (dmean2D.x, dmean2D.y, dconic.x, dconic.y | dconic.w, dopacity, -, -)   in the scratch buffer
+//   dcol   f32[P][3]  dL/dRGB, accumulated straight into the caller's dL_dcolors output.  With SH colours the
+//          channels the forward clamped (forward.cu:63-70) are masked here, so this array IS the per-view
+//          SH factor the view-parallel step exchanges, complete as soon as the blend pass ends.
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -65,12 +72,12 @@ int read_bwd_stats(unsigned long long *out, int reset)
 constexpr int CH = 16;             // splats per chunk
 constexpr int CH_PITCH = CH + 1;   // float2 elements per pixel row: odd pitch = conflict-free transpose
 // per-warp chunk scratch (bytes from its base): pair[32][CH_PITCH] float2 | meta[CH] x 48 B | dp[32] float4
-//   meta: (x, y, conic a, conic b) (conic c, tau, opacity, r) (id, -, -, -)
+//   meta: (x, y, conic a, conic b) (conic c, tau, opacity, r) (clamp bits, id, -, -)
 //   dp:   (dL/dpixel r g b, -T_final <bg, dL/dpixel>) of the block's pixels
 constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 48, CB_BYTES = CB_DP + 32 * 16;
 // CTA shared-memory map (dynamic): records of two batches, membership words, chunk scratch
-constexpr uint32_t SM_A = 0, SM_B = SM_A + 2 * BWD_B * 16, SM_C = SM_B + 2 * BWD_B * 16, SM_ID = SM_C + 2 * BWD_B * 8,
-                   SM_MEMBER = SM_ID + 2 * BWD_B * 4, SM_LAST = SM_MEMBER + BWD_NW * (BWD_B / 32) * 4,
+constexpr uint32_t SM_A = 0, SM_B = SM_A + 2 * BWD_B * 16, SM_C = SM_B + 2 * BWD_B * 16,
+                   SM_MEMBER = SM_C + 2 * BWD_B * 16, SM_LAST = SM_MEMBER + BWD_NW * (BWD_B / 32) * 4,
                    SM_CHUNK = SM_LAST + 16, BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
 
 __device__ __forceinline__ float ex2_approx(float x)
@@ -83,13 +90,14 @@ __device__ __forceinline__ float ex2_approx(float x)
 // phase 2: reduce the parked chunk (nf splats) over the block's pixels and add it to the Gaussians'
 // accumulators.  Lane = (chunk slot, half): half h holds block rows 2h, 2h+1 = phase-1 lanes 16h..16h+15.
 __device__ __forceinline__ void chunk_flush(uint32_t cb, int nf, float blk_x0, float blk_y0, float ddelx_dx,
-                                            float ddely_dy, float *__restrict__ gacc)
+                                            float ddely_dy, float *__restrict__ gacc, float *__restrict__ dcol)
 {
     const unsigned lane = threadIdx.x & 31u;
     const int slot = (int)(lane & (CH - 1)), half = (int)(lane >> 4);
     __syncwarp();
     const float4 M0 = lds128(cb + CB_META + slot * 48), M1 = lds128(cb + CB_META + slot * 48 + 16);
-    const uint32_t id = lds32(cb + CB_META + slot * 48 + 32);
+    const float2 M2 = lds64(cb + CB_META + slot * 48 + 32);
+    const uint32_t clamp = __float_as_uint(M2.x), id = __float_as_uint(M2.y);
     // d = mean - pixel = (ax - cx_i, ay - cy_i) with the half's centre as origin: cx_i = (i & 7) - 3.5,
     // cy_i = (i >> 3) - 0.5
     const float ax = M0.x - (blk_x0 + 3.5f), ay = M0.y - (blk_y0 + 2.0f * (float)half + 0.5f);
@@ -130,14 +138,16 @@ __device__ __forceinline__ void chunk_flush(uint32_t cb, int nf, float blk_x0, f
     c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
     if (slot < nf) {
         // moments -> gradients (backward.cu:537-554): dG/ddel = -G (Q d)
-        float *g = gacc + (size_t)id * 12;
+        float *g = gacc + (size_t)id * 8, *dc = dcol + (size_t)id * 3;
         if (half == 0) {
             const float gmx = -(M0.z * m1 + M0.w * m2) * ddelx_dx;
             const float gmy = -(M1.x * m2 + M0.w * m1) * ddely_dy;
             red_add_v4(g, gmx, gmy, -0.5f * m3, -0.5f * m4);
+            if (!(clamp & 1u)) atomicAdd(dc, c0);
         } else {
-            red_add_v4(g + 4, -0.5f * m5, __fdividef(m0, M1.z), c0, c1);
-            atomicAdd(g + 8, c2);
+            red_add_v2(g + 4, -0.5f * m5, __fdividef(m0, M1.z));
+            if (!(clamp & 2u)) atomicAdd(dc + 1, c1);
+            if (!(clamp & 4u)) atomicAdd(dc + 2, c2);
         }
     }
     __syncwarp();
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
     const uint32_t *__restrict__ tile_order, const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ plist,
     const float4 *__restrict__ rec, int W, int H, int gx, const float *__restrict__ bg,
     const float *__restrict__ final_Ts, const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dpixels,
-    float *__restrict__ gacc)
+    float *__restrict__ gacc, float *__restrict__ dcol)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int tile = (int)tile_order[blockIdx.x];
@@ -214,8 +224,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
             const uint32_t e = buf * BWD_B + tid;
             cp_async16_a(sm + SM_A + e * 16, r);
             cp_async16_a(sm + SM_B + e * 16, r + 1);
-            cp_async8_a(sm + SM_C + e * 8, r + 2);
-            sts32(sm + SM_ID + e * 4, id);
+            cp_async16_a(sm + SM_C + e * 16, r + 2);
         }
         cp_async_commit();
     };
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
 
     for (int b0 = 0, buf = 0; b0 < n; b0 += BWD_B, buf ^= 1) {
         const uint32_t sa = sm + SM_A + buf * (BWD_B * 16), sb = sm + SM_B + buf * (BWD_B * 16),
-                       sc = sm + SM_C + buf * (BWD_B * 8), sid = sm + SM_ID + buf * (BWD_B * 4);
+                       sc = sm + SM_C + buf * (BWD_B * 16);
         cp_async_wait<0>();
         __syncthreads();  // batch b0 has landed in `buf`; every warp is done with the other buffer
         if (loader) {
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
                         alpha = fminf(0.99f, __fmul_rn(B.z, G));
                     }
                     if (!(alpha < 1.0f / 255.0f)) {
-                        const float2 Cc = lds64(sc + j * 8);
+                        const float2 Cc = lds64(sc + j * 16);
                         const float4 dp = lds128(cb + CB_DP + lane * 16);
                         const float om = 1.0f - alpha;  // in [0.01, 1): a bare MUFU.RCP suffices
                         float inv;
@@ -326,15 +335,18 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
                 const uint32_t ma = cb + CB_META + nfill * 48;
                 sts128(ma, A.x, A.y, A.z, A.w);
                 sts128(ma + 16, B.x, B.y, B.z, B.w);
-                sts32(ma + 32, lds32(sid + j * 4));
+                {
+                    const float2 Cm = lds64(sc + j * 16 + 8);  // (clamp bits, id)
+                    sts64(ma + 32, Cm.x, Cm.y);
+                }
                 if (++nfill == CH) {
-                    chunk_flush(cb, CH, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc);
+                    chunk_flush(cb, CH, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc, dcol);
                     nfill = 0;
                 }
             }
         }
     }
-    if (nfill) chunk_flush(cb, nfill, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc);
+    if (nfill) chunk_flush(cb, nfill, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc, dcol);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -345,15 +357,17 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
 // overwrites the SH row in place, and all outputs leave through coalesced stores.
 // ------------------------------------------------------------------------------------------------
 struct PreBwdArgs {
-    int P;
+    int p0, p1;  // Gaussian range of this launch (one chunk of the per-Gaussian pass); p0 % PB_T == 0
     const float *means, *scales, *rots, *shs, *cov_pre;
     ViewConsts v;
     const int32_t *radii;
-    const uint32_t *aux;  // clamp bits
-    const float *gacc;
-    float *dmeans2D, *dcolors, *dopacity, *dmeans3D, *dcov3D, *dsh, *dscales, *drots;
-    int bulk_ok, sh_stride, sh_vec;
-    int skip_dcolors;  // dL_dcolors was already produced by sh_factor_kernel
+    const float *gacc;  // [P][8] blend accumulators
+    const float *dcol;  // [P][3] accumulated dL/dRGB (= the dL_dcolors output; clamp-masked with SH)
+    float *dmeans2D, *dopacity, *dmeans3D, *dcov3D, *dsh, *dscales, *drots;
+    // optional f32[P][11]: (dL_dmeans3D 3 | dL_dopacity 1 | dL_dscales 3 | dL_drotations 4) of a Gaussian as ONE
+    // 44-byte record instead of the four arrays (the view-parallel step all-reduces these records chunk by chunk)
+    float *rec11;
+    int in_bulk_ok, out_bulk_ok, sh_stride, sh_vec;
 };
 
 #define SH_C0 0.28209479177387814f
@@ -429,21 +443,32 @@ __device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *row, 
 #define SGR_PB_T 64
 #endif
 constexpr int PB_T = SGR_PB_T;
-// dynamic shared memory carve-up (floats): inputs then outputs then the SH block
-constexpr int PB_GACC = 0;                    // PB_T*12
-constexpr int PB_MEANS = PB_GACC + PB_T * 12; // PB_T*3
+// dynamic shared memory carve-up (floats): inputs, outputs, then the SH block
+constexpr int PB_GACC = 0;                     // PB_T*8
+constexpr int PB_DCOL = PB_GACC + PB_T * 8;    // PB_T*3
+constexpr int PB_MEANS = PB_DCOL + PB_T * 3;   // PB_T*3
 constexpr int PB_SCALES = PB_MEANS + PB_T * 3;
-constexpr int PB_ROTS = PB_SCALES + PB_T * 3; // PB_T*4 (16B aligned: offset is a multiple of 4 floats)
-constexpr int PB_COV = PB_ROTS + PB_T * 4;    // PB_T*6
-constexpr int PB_O_M2D = PB_COV + PB_T * 6;   // outputs
-constexpr int PB_O_COL = PB_O_M2D + PB_T * 3;
-constexpr int PB_O_OPA = PB_O_COL + PB_T * 3;
+constexpr int PB_ROTS = PB_SCALES + PB_T * 3;  // PB_T*4 (16B aligned: offset is a multiple of 4 floats)
+constexpr int PB_COV = PB_ROTS + PB_T * 4;     // PB_T*6
+constexpr int PB_O_M2D = PB_COV + PB_T * 6;    // outputs
+constexpr int PB_O_COV = PB_O_M2D + PB_T * 3;
+// the 11 all-reduce-bound floats per Gaussian: four arrays (OPA | M3D | SCL | ROT) or PB_T records of 11
+constexpr int PB_O_R11 = PB_O_COV + PB_T * 6;
+constexpr int PB_O_OPA = PB_O_R11;
 constexpr int PB_O_M3D = PB_O_OPA + PB_T;
-constexpr int PB_O_COV = PB_O_M3D + PB_T * 3;
-constexpr int PB_O_SCL = PB_O_COV + PB_T * 6;
+constexpr int PB_O_SCL = PB_O_M3D + PB_T * 3;
 constexpr int PB_O_ROT = PB_O_SCL + PB_T * 3;  // multiple of 4 floats
-constexpr int PB_SH = PB_O_ROT + PB_T * 4;     // PB_T * sh_stride
+constexpr int PB_SH = PB_O_R11 + PB_T * 11 + (PB_T & 3 ? 4 - (PB_T & 3) : 0);  // PB_T * sh_stride
+static_assert(PB_T % 4 == 0, "every region starts on a 16-byte boundary");
 static_assert(PB_ROTS % 4 == 0 && PB_O_ROT % 4 == 0 && PB_SH % 4 == 0, "16-byte alignment of float4 regions");
+
+// 1-D bulk async copy shared -> global (TMA store, no tensor map); bytes % 16 == 0, both sides 16-byte aligned
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
 
 __device__ __forceinline__ void pb_stage(float *dst, const float *__restrict__ src, int n)
 {
@@ -459,21 +484,23 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x;
-    const int base = blockIdx.x * PB_T;
-    const int n = min(PB_T, a.P - base);
+    const int base = a.p0 + blockIdx.x * PB_T;
+    const int n = min(PB_T, a.p1 - base);
     const int i = base + tid;
     const int M = a.v.M;
     const bool full = (n == PB_T);
 
-    if (a.bulk_ok && full) {
+    if (a.in_bulk_ok && full) {
         if (tid == 0) {
             mbar_init(&s_bar, 1);
             mbar_fence_init();
-            uint32_t bytes = PB_T * 48 + PB_T * 12;
+            uint32_t bytes = PB_T * 32 + PB_T * 12;
+            if (a.shs) bytes += PB_T * 12;  // dL/dRGB is only an input of the SH backward
             if (a.scales) bytes += PB_T * 12 + PB_T * 16;
             if (a.cov_pre) bytes += PB_T * 24;
             mbar_expect_tx(&s_bar, bytes);
-            bulk_g2s(sm + PB_GACC, a.gacc + (size_t)base * 12, PB_T * 48, &s_bar);
+            bulk_g2s(sm + PB_GACC, a.gacc + (size_t)base * 8, PB_T * 32, &s_bar);
+            if (a.shs) bulk_g2s(sm + PB_DCOL, a.dcol + (size_t)base * 3, PB_T * 12, &s_bar);
             bulk_g2s(sm + PB_MEANS, a.means + (size_t)base * 3, PB_T * 12, &s_bar);
             if (a.scales) {
                 bulk_g2s(sm + PB_SCALES, a.scales + (size_t)base * 3, PB_T * 12, &s_bar);
@@ -482,7 +509,8 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             if (a.cov_pre) bulk_g2s(sm + PB_COV, a.cov_pre + (size_t)base * 6, PB_T * 24, &s_bar);
         }
     } else {
-        pb_stage(sm + PB_GACC, a.gacc + (size_t)base * 12, n * 12);
+        pb_stage(sm + PB_GACC, a.gacc + (size_t)base * 8, n * 8);
+        if (a.shs) pb_stage(sm + PB_DCOL, a.dcol + (size_t)base * 3, n * 3);
         pb_stage(sm + PB_MEANS, a.means + (size_t)base * 3, n * 3);
         if (a.scales) {
             pb_stage(sm + PB_SCALES, a.scales + (size_t)base * 3, n * 3);
@@ -517,13 +545,9 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
         cp_async_commit();
     }
     int radius = 0;
-    uint32_t cl = 0;
-    if (tid < n) {
-        radius = a.radii[i];
-        if (a.shs) cl = a.aux[i];
-    }
+    if (tid < n) radius = a.radii[i];
     __syncthreads();
-    if (a.bulk_ok && full) mbar_wait(&s_bar, 0);
+    if (a.in_bulk_ok && full) mbar_wait(&s_bar, 0);
     if (a.shs) {
         cp_async_wait<0>();
         __syncthreads();
@@ -531,38 +555,33 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
 
     if (tid < n) {
         const bool vis = radius > 0;
-        float *o_m2d = sm + PB_O_M2D + tid * 3, *o_col = sm + PB_O_COL + tid * 3, *o_m3d = sm + PB_O_M3D + tid * 3;
-        float *o_cov = sm + PB_O_COV + tid * 6, *o_scl = sm + PB_O_SCL + tid * 3;
-        float4 *o_rot = (float4 *)(sm + PB_O_ROT) + tid;
+        // the 11 all-reduce-bound outputs: four arrays, or one 44-byte record per Gaussian (stride 11: conflict-free)
+        const bool aos = a.rec11 != nullptr;
+        float *o_m2d = sm + PB_O_M2D + tid * 3, *o_cov = sm + PB_O_COV + tid * 6;
+        float *o_m3d = aos ? sm + PB_O_R11 + tid * 11 : sm + PB_O_M3D + tid * 3;
+        float *o_opa = aos ? o_m3d + 3 : sm + PB_O_OPA + tid;
+        float *o_scl = aos ? o_m3d + 4 : sm + PB_O_SCL + tid * 3;
+        float *o_rot = aos ? o_m3d + 7 : sm + PB_O_ROT + tid * 4;
         float *row = s_sh + tid * a.sh_stride;
         if (!vis) {
             o_m2d[0] = o_m2d[1] = o_m2d[2] = 0.f;
-            o_col[0] = o_col[1] = o_col[2] = 0.f;
-            sm[PB_O_OPA + tid] = 0.f;
+            *o_opa = 0.f;
             o_m3d[0] = o_m3d[1] = o_m3d[2] = 0.f;
 #pragma unroll
             for (int k = 0; k < 6; k++) o_cov[k] = 0.f;
             o_scl[0] = o_scl[1] = o_scl[2] = 0.f;
-            *o_rot = make_float4(0, 0, 0, 0);
-            if (a.shs)
+            o_rot[0] = o_rot[1] = o_rot[2] = o_rot[3] = 0.f;
+            if (a.shs && a.dsh)
                 for (int k = 0; k < row_f; k++) row[k] = 0.f;
         } else {
-            const float4 *gr = (const float4 *)(sm + PB_GACC) + tid * 3;
+            const float4 *gr = (const float4 *)(sm + PB_GACC) + tid * 2;
             const float4 g0 = gr[0], g1 = gr[1];
-            const float g2 = gr[2].x;
             const float dmx = g0.x, dmy = g0.y;
             const float dcx = g0.z, dcy = g0.w, dcz = g1.x;
             o_m2d[0] = dmx;
             o_m2d[1] = dmy;
             o_m2d[2] = 0.f;
-            sm[PB_O_OPA + tid] = g1.y;
-            // dL/dcolour of the Gaussian.  In SH "factor mode" (SH present but no dL_dsh buffer: the
-            // view-parallel path rebuilds dL_dsh from per-view factors, sgr_sh_grad_from_factors) this
-            // output carries the clamp-masked gradient, i.e. exactly the factor dL/dRGB.
-            const bool factor_mode = a.shs && !a.dsh;
-            o_col[0] = (factor_mode && (cl & 1u)) ? 0.f : g1.z;
-            o_col[1] = (factor_mode && (cl & 2u)) ? 0.f : g1.w;
-            o_col[2] = (factor_mode && (cl & 4u)) ? 0.f : g2;
+            *o_opa = g1.y;
 
             const float *vm = a.v.viewmatrix, *proj = a.v.projmatrix;
             const float mx = sm[PB_MEANS + tid * 3], my = sm[PB_MEANS + tid * 3 + 1], mz = sm[PB_MEANS + tid * 3 + 2];
@@ -649,7 +668,8 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             dmean.y += (proj[4] * m_w - proj[7] * mul1) * dmx + (proj[5] * m_w - proj[7] * mul2) * dmy;
             dmean.z += (proj[8] * m_w - proj[11] * mul1) * dmx + (proj[9] * m_w - proj[11] * mul2) * dmy;
             if (a.shs) {
-                const f3 dRGB = {(cl & 1u) ? 0.f : g1.z, (cl & 2u) ? 0.f : g1.w, (cl & 4u) ? 0.f : g2};
+                // accumulated dL/dRGB, already masked where the forward clamped the colour
+                const f3 dRGB = {sm[PB_DCOL + tid * 3], sm[PB_DCOL + tid * 3 + 1], sm[PB_DCOL + tid * 3 + 2]};
                 const float *cp = a.v.campos;
                 sh_backward_inplace(a.v.D, M, row, {mx - cp[0], my - cp[1], mz - cp[2]}, dRGB, dmean);
             }
@@ -687,22 +707,47 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
                        4 * y * (dMt[2][2] + dMt[0][0]);
                 dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) -
                        4 * z * (dMt[1][1] + dMt[0][0]);
-                *o_rot = dq;
+                o_rot[0] = dq.x;
+                o_rot[1] = dq.y;
+                o_rot[2] = dq.z;
+                o_rot[3] = dq.w;
             } else {
                 o_scl[0] = o_scl[1] = o_scl[2] = 0.f;
-                *o_rot = make_float4(0, 0, 0, 0);
+                o_rot[0] = o_rot[1] = o_rot[2] = o_rot[3] = 0.f;
             }
         }
     }
+    // ---- write-out: the small arrays leave as 1-D bulk copies (TMA stores issued by one thread) when the
+    // block is full and everything is 16-byte aligned, else through coalesced loops
+    const bool out_bulk = a.out_bulk_ok && full;
+    if (out_bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    // ---- coalesced write-out -------------------------------------------------------------------
-    pb_flush(a.dmeans2D + (size_t)base * 3, sm + PB_O_M2D, n * 3);
-    if (!a.skip_dcolors) pb_flush(a.dcolors + (size_t)base * 3, sm + PB_O_COL, n * 3);
-    pb_flush(a.dopacity + base, sm + PB_O_OPA, n);
-    pb_flush(a.dmeans3D + (size_t)base * 3, sm + PB_O_M3D, n * 3);
-    pb_flush(a.dcov3D + (size_t)base * 6, sm + PB_O_COV, n * 6);
-    pb_flush(a.dscales + (size_t)base * 3, sm + PB_O_SCL, n * 3);
-    pb_flush(a.drots + (size_t)base * 4, sm + PB_O_ROT, n * 4);
+    if (out_bulk) {
+        if (tid == 0) {
+            bulk_s2g(a.dmeans2D + (size_t)base * 3, sm + PB_O_M2D, PB_T * 12);
+            bulk_s2g(a.dcov3D + (size_t)base * 6, sm + PB_O_COV, PB_T * 24);
+            if (a.rec11) {
+                bulk_s2g(a.rec11 + (size_t)base * 11, sm + PB_O_R11, PB_T * 44);
+            } else {
+                bulk_s2g(a.dopacity + base, sm + PB_O_OPA, PB_T * 4);
+                bulk_s2g(a.dmeans3D + (size_t)base * 3, sm + PB_O_M3D, PB_T * 12);
+                bulk_s2g(a.dscales + (size_t)base * 3, sm + PB_O_SCL, PB_T * 12);
+                bulk_s2g(a.drots + (size_t)base * 4, sm + PB_O_ROT, PB_T * 16);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    } else {
+        pb_flush(a.dmeans2D + (size_t)base * 3, sm + PB_O_M2D, n * 3);
+        pb_flush(a.dcov3D + (size_t)base * 6, sm + PB_O_COV, n * 6);
+        if (a.rec11) {
+            pb_flush(a.rec11 + (size_t)base * 11, sm + PB_O_R11, n * 11);
+        } else {
+            pb_flush(a.dopacity + base, sm + PB_O_OPA, n);
+            pb_flush(a.dmeans3D + (size_t)base * 3, sm + PB_O_M3D, n * 3);
+            pb_flush(a.dscales + (size_t)base * 3, sm + PB_O_SCL, n * 3);
+            pb_flush(a.drots + (size_t)base * 4, sm + PB_O_ROT, n * 4);
+        }
+    }
     if (a.dsh && M > 0) {
         float *dst = a.dsh + (size_t)base * row_f;
         if (a.shs) {
@@ -730,33 +775,60 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             for (int k = tid; k < n * row_f; k += PB_T) dst[k] = 0.f;
         }
     }
+    // the bulk stores read shared memory asynchronously: it must stay valid until they have
+    if (out_bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
-// dL_dsh from per-view factors (view-parallel multi-GPU step).  One thread per Gaussian keeps the
-// 3*M accumulators in registers, loops over the views' (camera position, dL/dRGB) pairs, and the
-// block writes the rows out through shared memory with 16-byte coalesced stores.
+// View-parallel epilogue (one thread per Gaussian of a chunk), after the exchange:
+//  * dL_dsh from the views' factors: dL_dsh[i] = sum_v basis(normalize(mean_i - campos_v)) (x) dRGB_v[i]
+//    (the SH part of backward.cu:20-139 is an outer product per view).  The 3*M accumulators stay in
+//    registers over the views and the rows leave through shared memory as coalesced stores.
+//  * the all-reduced 44-byte records (means3D 3 | opacity 1 | scales 3 | rotations 4) are split into
+//    the four gradient arrays autograd expects.
+// Either half is optional.
 // ------------------------------------------------------------------------------------------------
 constexpr int SF_T = 128;
 
-__global__ void __launch_bounds__(SF_T) sh_grad_from_factors_kernel(int P, int M, int deg, int nviews,
-                                                                     const float *__restrict__ means,
-                                                                     const float *__restrict__ campos,
-                                                                     const float *__restrict__ dRGB, float *__restrict__ dsh)
+__global__ void __launch_bounds__(SF_T) view_grad_finalize_kernel(int p0, int p1, int P, int M, int deg, int nviews,
+                                                                   const float *__restrict__ means,
+                                                                   const float *__restrict__ campos,
+                                                                   const float *__restrict__ dRGB, float *__restrict__ dsh,
+                                                                   const float *__restrict__ rec11, float scale,
+                                                                   float *__restrict__ dmeans3D, float *__restrict__ dopacity,
+                                                                   float *__restrict__ dscales, float *__restrict__ drots)
 {
-    extern __shared__ __align__(16) float s_rows[];  // SF_T rows x stride floats
-    const int tid = threadIdx.x, base = blockIdx.x * SF_T, i = base + tid;
-    const int n = min(SF_T, P - base);
+    extern __shared__ __align__(16) float s_rows[];  // SF_T rows x stride floats (SH half only)
+    const int tid = threadIdx.x, base = p0 + blockIdx.x * SF_T, i = base + tid;
+    const int n = min(SF_T, p1 - base);
+    if (rec11 && tid < n) {
+        const float *r = rec11 + (size_t)i * 11;
+        float v[11];
+#pragma unroll
+        for (int k = 0; k < 11; k++) v[k] = r[k] * scale;
+        dmeans3D[3 * (size_t)i] = v[0];
+        dmeans3D[3 * (size_t)i + 1] = v[1];
+        dmeans3D[3 * (size_t)i + 2] = v[2];
+        dopacity[i] = v[3];
+        dscales[3 * (size_t)i] = v[4];
+        dscales[3 * (size_t)i + 1] = v[5];
+        dscales[3 * (size_t)i + 2] = v[6];
+        drots[4 * (size_t)i] = v[7];
+        drots[4 * (size_t)i + 1] = v[8];
+        drots[4 * (size_t)i + 2] = v[9];
+        drots[4 * (size_t)i + 3] = v[10];
+    }
+    if (!dsh) return;
     const int row_f = M * 3;
     const int stride = (row_f & 1) ? row_f : row_f + 1;  // odd stride: conflict-free scalar access
     float acc[16][3];
 #pragma unroll
     for (int k = 0; k < 16; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
     if (tid < n) {
-        const float mx = means[3 * i], my = means[3 * i + 1], mz = means[3 * i + 2];
+        const float mx = means[3 * (size_t)i], my = means[3 * (size_t)i + 1], mz = means[3 * (size_t)i + 2];
         for (int v = 0; v < nviews; v++) {
             const float *g = dRGB + ((size_t)v * P + i) * 3;
-            const float gr = g[0], gg = g[1], gb = g[2];
+            const float gr = g[0] * scale, gg = g[1] * scale, gb = g[2] * scale;
             if (gr == 0.f && gg == 0.f && gb == 0.f) continue;  // not visible in this view
             const float ox = mx - campos[3 * v], oy = my - campos[3 * v + 1], oz = mz - campos[3 * v + 2];
             const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
@@ -812,25 +884,11 @@ __global__ void __launch_bounds__(SF_T) sh_grad_from_factors_kernel(int P, int M
     }
 }
 
-// Factor mode, staged: the clamp-masked dL/dRGB straight from the blend accumulators, so that the
-// caller can start exchanging it (hook) while preprocess_backward is still running.
-__global__ void __launch_bounds__(256) sh_factor_kernel(int P, const int32_t *__restrict__ radii,
-                                                        const uint32_t *__restrict__ aux, const float *__restrict__ gacc,
-                                                        float *__restrict__ dcolors)
-{
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    if (k >= 3 * P) return;
-    const int i = k / 3, c = k - 3 * i;
-    float v = 0.f;
-    if (radii[i] > 0 && !((aux[i] >> c) & 1u)) v = gacc[(size_t)i * 12 + 6 + c];
-    dcolors[k] = v;
-}
-
 int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
                     const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
                     const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
                     float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
-                    void *grad_scratch, cudaStream_t st, SgrStageHook hook, void *hook_ctx)
+                    void *grad_scratch, cudaStream_t st, const SgrBackwardPlan *plan)
 {
     const int P = g->P, W = view->image_width, H = view->image_height;
     const int gx = (W + SGR_TILE - 1) / SGR_TILE, gy = (H + SGR_TILE - 1) / SGR_TILE;
@@ -838,6 +896,9 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     ImageState img = ImageState::carve((void *)image_buffer, W, H);
     BinState bin = BinState::carve((void *)binning_buffer, (size_t)num_rendered);
     float *gacc = (float *)align_up((size_t)grad_scratch);
+    const SgrStageHook hook = plan ? plan->hook : nullptr;
+    void *hook_ctx = plan ? plan->hook_ctx : nullptr;
+    float *rec11 = plan ? plan->reduce_records : nullptr;
     {
         // opt in to > 48 KB of dynamic shared memory once per device (the call is not free); calls
         // may come from several threads (autograd engine threads of different devices)
@@ -856,26 +917,23 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
     }
-    SGR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 48, st));
+    // the blend accumulators: 32 B per Gaussian of scratch + the dL_dcolors output itself
+    SGR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 32, st));
+    SGR_CUDA(cudaMemsetAsync(dL_dcolors, 0, (size_t)P * 12, st));
     if (num_rendered > 0) {
         SGR_LAUNCH(K_BLEND_BWD, st,
                    if (ids_packed(P))
                        blend_backward_kernel<true><<<gx * gy, 256, BWD_SMEM_BYTES, st>>>(
                            img.tile_order, img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T,
-                           img.n_contrib, dL_dout_color, gacc);
+                           img.n_contrib, dL_dout_color, gacc, dL_dcolors);
                    else
                        blend_backward_kernel<false><<<gx * gy, 256, BWD_SMEM_BYTES, st>>>(
                            img.tile_order, img.tile_start, bin.plist, geom.rec, W, H, gx, view->bg, img.final_T,
-                           img.n_contrib, dL_dout_color, gacc));
+                           img.n_contrib, dL_dout_color, gacc, dL_dcolors));
     }
-    const bool staged_factors = hook && g->shs && !dL_dsh;
-    if (staged_factors) {
-        SGR_LAUNCH(K_MISC, st, sh_factor_kernel<<<(3 * P + 255) / 256, 256, 0, st>>>(P, radii, geom.aux, gacc, dL_dcolors));
-        hook(hook_ctx, SGR_STAGE_SH_FACTORS_READY);
-    }
+    // dL_dcolors is final here (with SH colours: the clamp-masked dL/dRGB, i.e. this view's SH factor)
+    if (hook) hook(hook_ctx, SGR_STAGE_BLEND_DONE);
     PreBwdArgs a;
-    a.P = P;
-    a.skip_dcolors = staged_factors ? 1 : 0;
     a.means = g->means3D;
     a.scales = g->scales;
     a.rots = g->rotations;
@@ -898,19 +956,24 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     a.v.M = g->M;
     a.v.prefiltered = view->prefiltered;
     a.radii = radii;
-    a.aux = geom.aux;
     a.gacc = gacc;
+    a.dcol = dL_dcolors;
     a.dmeans2D = dL_dmeans2D;
-    a.dcolors = dL_dcolors;
     a.dopacity = dL_dopacity;
     a.dmeans3D = dL_dmeans3D;
     a.dcov3D = dL_dcov3D;
     a.dsh = dL_dsh;
     a.dscales = dL_dscales;
     a.drots = dL_drotations;
+    a.rec11 = rec11;
     auto al16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
-    a.bulk_ok = al16(gacc) && al16(g->means3D) && (!g->scales || al16(g->scales)) && (!g->rotations || al16(g->rotations)) &&
-                (!g->cov3D_precomp || al16(g->cov3D_precomp));
+    a.in_bulk_ok = al16(gacc) && al16(dL_dcolors) && al16(g->means3D) && (!g->scales || al16(g->scales)) &&
+                   (!g->rotations || al16(g->rotations)) && (!g->cov3D_precomp || al16(g->cov3D_precomp));
+    a.out_bulk_ok = al16(dL_dmeans2D) && al16(dL_dcov3D) &&
+                    (rec11 ? al16(rec11) : (al16(dL_dopacity) && al16(dL_dmeans3D) && al16(dL_dscales) && al16(dL_drotations)));
+#ifdef SGR_PB_NO_BULK_STORE
+    a.out_bulk_ok = 0;
+#endif
     a.sh_stride = 0;
     a.sh_vec = 0;
     if (g->shs) {
@@ -925,7 +988,18 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
         }
     }
     const size_t dyn = (size_t)(PB_SH + PB_T * a.sh_stride) * sizeof(float);
-    SGR_LAUNCH(K_PRE_BWD, st, preprocess_backward_kernel<<<(P + PB_T - 1) / PB_T, PB_T, dyn, st>>>(a));
+    // the per-Gaussian pass, in `num_chunks` Gaussian ranges (multiples of the CTA size) so that a caller
+    // can start reducing a finished range while the next one is computed
+    int nchunks = plan && plan->num_chunks > 1 ? plan->num_chunks : 1;
+    const int blocks = (P + PB_T - 1) / PB_T;
+    if (nchunks > blocks) nchunks = blocks;
+    for (int c = 0; c < nchunks; c++) {
+        const int b0 = (int)((int64_t)blocks * c / nchunks), b1 = (int)((int64_t)blocks * (c + 1) / nchunks);
+        a.p0 = b0 * PB_T;
+        a.p1 = min(P, b1 * PB_T);
+        if (b1 > b0) SGR_LAUNCH(K_PRE_BWD, st, preprocess_backward_kernel<<<b1 - b0, PB_T, dyn, st>>>(a));
+        if (hook) hook(hook_ctx, SGR_STAGE_CHUNK_DONE + c);
+    }
     SGR_CUDA(cudaGetLastError());
     if (view->debug) SGR_CUDA(cudaStreamSynchronize(st));
     return SGR_OK;
@@ -933,23 +1007,59 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
 
 }  // namespace sgr
 
+extern "C" int sgr_backward_chunk_range(int32_t P, int32_t num_chunks, int32_t chunk, int32_t *p0, int32_t *p1)
+{
+    using namespace sgr;
+    if (P < 0 || num_chunks < 1 || chunk < 0 || chunk >= num_chunks || !p0 || !p1) {
+        set_error("bad arguments to sgr_backward_chunk_range");
+        return SGR_EINVAL;
+    }
+    const int blocks = (P + PB_T - 1) / PB_T;
+    const int nchunks = num_chunks > blocks ? (blocks > 0 ? blocks : 1) : num_chunks;
+    if (chunk >= nchunks) {
+        *p0 = *p1 = P;
+        return SGR_OK;
+    }
+    *p0 = (int)((int64_t)blocks * chunk / nchunks) * PB_T;
+    *p1 = (int)((int64_t)blocks * (chunk + 1) / nchunks) * PB_T;
+    if (*p1 > P) *p1 = P;
+    if (*p0 > P) *p0 = P;
+    return SGR_OK;
+}
+
+extern "C" int sgr_view_grad_finalize(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree, int32_t num_views,
+                                      const float *means3D, const float *campos, const float *dRGB, float *dL_dsh,
+                                      const float *reduced_records, float scale, float *dL_dmeans3D, float *dL_dopacity,
+                                      float *dL_dscales, float *dL_drotations, void *stream)
+{
+    using namespace sgr;
+    const bool sh = dL_dsh != nullptr, rec = reduced_records != nullptr;
+    if (P < 0 || p0 < 0 || p1 < p0 || p1 > P || (!sh && !rec) ||
+        (sh && (M <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M || num_views <= 0 ||
+                !means3D || !campos || !dRGB)) ||
+        (rec && (!dL_dmeans3D || !dL_dopacity || !dL_dscales || !dL_drotations))) {
+        set_error("bad arguments to sgr_view_grad_finalize");
+        return SGR_EINVAL;
+    }
+    if (p1 == p0) return SGR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int row_f = M * 3, stride = (row_f & 1) ? row_f : row_f + 1;
+    const size_t dyn = sh ? (size_t)SF_T * stride * sizeof(float) : 0;
+    SGR_LAUNCH(K_MISC, st,
+               view_grad_finalize_kernel<<<(p1 - p0 + SF_T - 1) / SF_T, SF_T, dyn, st>>>(
+                   p0, p1, P, M, sh_degree, num_views, means3D, campos, dRGB, dL_dsh, reduced_records, scale, dL_dmeans3D,
+                   dL_dopacity, dL_dscales, dL_drotations));
+    SGR_CUDA(cudaGetLastError());
+    return SGR_OK;
+}
 
 extern "C" int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float *means3D,
                                         const float *campos, const float *dRGB, float *dL_dsh, void *stream)
 {
-    using namespace sgr;
-    if (P < 0 || M <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M || num_views <= 0 ||
-        (P > 0 && (!means3D || !campos || !dRGB || !dL_dsh))) {
-        set_error("bad arguments to sgr_sh_grad_from_factors");
+    if (!dL_dsh && P > 0) {
+        sgr::set_error("bad arguments to sgr_sh_grad_from_factors");
         return SGR_EINVAL;
     }
-    if (P == 0) return SGR_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int row_f = M * 3, stride = (row_f & 1) ? row_f : row_f + 1;
-    const size_t dyn = (size_t)SF_T * stride * sizeof(float);
-    SGR_LAUNCH(K_MISC, st,
-               sh_grad_from_factors_kernel<<<(P + SF_T - 1) / SF_T, SF_T, dyn, st>>>(P, M, sh_degree, num_views, means3D,
-                                                                                     campos, dRGB, dL_dsh));
-    SGR_CUDA(cudaGetLastError());
-    return SGR_OK;
+    return sgr_view_grad_finalize(P, 0, P, M, sh_degree, num_views, means3D, campos, dRGB, dL_dsh, nullptr, 1.0f, nullptr,
+                                  nullptr, nullptr, nullptr, stream);
 }

@@ -251,9 +251,10 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
             float4 *rec = a.geom.rec + (size_t)idx * 3;
             rec[0] = make_float4(px, py, con_a, con_b);
             rec[1] = make_float4(con_c, tau, opacity, r);
-            rec[2] = make_float4(g, b, 0.f, 0.f);
+            // the SH clamp bits and the Gaussian's own index ride in the record's spare words: the backward
+            // blend masks dL/dRGB with the bits and addresses its accumulators with the index
+            rec[2] = make_float4(g, b, __uint_as_float(clamp_bits), __uint_as_float((uint32_t)idx));
             a.geom.depth[idx] = depth;
-            a.geom.aux[idx] = clamp_bits;
             a.geom.rect[idx] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
             a.radii[idx] = radius;
         } else {
@@ -419,11 +420,37 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, int gx, const ushor
     const uint32_t low_id = packed ? ((uint32_t)idx << 8) : (uint32_t)idx;
     if (rcnt > 0 && rcnt <= SMALL) {
         uint64_t masks = 0;
-        if (packed) {
+        if (packed && !eb.dead) {
+            // the columns a band reaches do not depend on the tile column: once per tile row, then every
+            // tile of the row only compares its two 8-column halves with them
             int k = 0;
-            for (int ty = rc.y; ty < rc.w; ty++)
-                for (int tx = rc.x; tx < rc.z; tx++, k++)
-                    masks |= (uint64_t)block_mask(eb, tx * SGR_TILE, ty * SGR_TILE) << (8 * k);
+            for (int ty = rc.y; ty < rc.w; ty++) {
+                int lo[4], hi[4];
+#pragma unroll
+                for (int band = 0; band < 4; band++) {
+                    lo[band] = 1;
+                    hi[band] = 0;  // empty
+                    if (eb.all) {
+                        lo[band] = -(1 << 30);
+                        hi[band] = 1 << 30;
+                    } else {
+                        const int ra = max(ty * SGR_TILE + 4 * band, eb.r_lo), rb = min(ty * SGR_TILE + 4 * band + 3, eb.r_hi);
+                        if (ra <= rb) band_columns(eb, ra, rb, lo[band], hi[band]);
+                    }
+                }
+                for (int tx = rc.x; tx < rc.z; tx++, k++) {
+                    const int x0 = tx * SGR_TILE;
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int band = 0; band < 4; band++) {
+                        const bool any = hi[band] >= lo[band];
+                        const uint32_t left = (any && lo[band] <= x0 + 7 && hi[band] >= x0) ? 1u : 0u;
+                        const uint32_t right = (any && lo[band] <= x0 + 15 && hi[band] >= x0 + 8) ? 2u : 0u;
+                        m |= (left | right) << (2 * band);
+                    }
+                    masks |= (uint64_t)m << (8 * k);
+                }
+            }
         }
         uint32_t slot[SMALL];
         int tx = 0, trow = (int)rc.y * gx + (int)rc.x;

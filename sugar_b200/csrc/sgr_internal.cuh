@@ -7,11 +7,11 @@
 //   rec    float4[3P]  48 B splat rec  final_T  f32[HW]                      inst_a  u64[C] depth|idx
 //   rect   ushort4[P]   8 B tile rect  n_contrib u32[HW]                     inst_b  u64[C] sort pong
 //   depth  f32[P]       4 B            tile_count u32[T]  tile_start u32[T+1] (plist is laid out FIRST)
-//   aux    u32[P]       4 B clamp bits tile_cursor u32[T] tile_order u32[T] counters u32[16]
+//                                      tile_cursor u32[T] tile_order u32[T] counters u32[16]
 //
 // Splat record (what the blend kernels gather, 48 B = 1.5 sectors instead of the reference's
 // three separate gathers xy / conic_opacity / rgb = 3-4 sectors):
-//   rec[0] = (x, y, conic_a, conic_b)   rec[1] = (conic_c, tau, opacity, r)   rec[2] = (g, b, -, -)
+//   rec[0] = (x, y, conic_a, conic_b)   rec[1] = (conic_c, tau, opacity, r)   rec[2] = (g, b, clamp bits, id)
 // tau = conservative power threshold below which alpha < 1/255 is certain (see blend kernels).
 #pragma once
 #include <cuda_runtime.h>
@@ -30,19 +30,14 @@ struct GeomState {
     float4 *rec;
     ushort4 *rect;
     float *depth;
-    uint32_t *aux;
-    static size_t bytes(size_t P)
-    {
-        return align_up(P * 48) + align_up(P * 8) + align_up(P * 4) + align_up(P * 4) + SGR_ALIGN;
-    }
+    static size_t bytes(size_t P) { return align_up(P * 48) + align_up(P * 8) + align_up(P * 4) + SGR_ALIGN; }
     static GeomState carve(void *base, size_t P)
     {
         char *p = (char *)align_up((size_t)base);
         GeomState s;
         s.rec = (float4 *)p; p += align_up(P * 48);
         s.rect = (ushort4 *)p; p += align_up(P * 8);
-        s.depth = (float *)p; p += align_up(P * 4);
-        s.aux = (uint32_t *)p;
+        s.depth = (float *)p;
         return s;
     }
 };
@@ -355,10 +350,10 @@ __device__ __forceinline__ uint32_t block_mask_of_record(float x, float y, float
 
 // Instance words carry the footprint mask next to the Gaussian id when the ids fit 24 bits:
 //   low word of the sort key = id << 8 | mask   (the order by (depth, id) is unchanged: ids are unique)
-// and the sorted list the blend kernels read holds the same low words.  For P > 2^24 Gaussians the low
+// and the sorted list the blend kernels read holds the same low words.  For P >= 2^24 Gaussians the low
 // word is the plain id and the blend kernels compute the mask while staging the record.
 #define SGR_PACKED_MAX_P (1 << 24)
-bool ids_packed(int P);  // host (sgr_api.cu): P <= 2^24, unless SGR_FORCE_UNPACKED_IDS=1 (tests of the other format)
+bool ids_packed(int P);  // host (sgr_api.cu): P < 2^24, unless SGR_FORCE_UNPACKED_IDS=1 (tests of the other format)
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -480,6 +475,6 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
                     const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
                     const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
                     float *dL_dmeans3D, float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
-                    void *grad_scratch, cudaStream_t stream, SgrStageHook hook, void *hook_ctx);
+                    void *grad_scratch, cudaStream_t stream, const SgrBackwardPlan *plan);
 
 }  // namespace sgr

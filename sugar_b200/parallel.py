@@ -1,29 +1,49 @@
-"""View-sharded multi-GPU step: one process per GPU, Gaussian parameters replicated, each rank
-renders its own view(s), per-Gaussian gradients summed with ONE NCCL all-reduce over
-NVLink 5 / NVSwitch (the reference is strictly 1 view / 1 GPU,
-sugar_trainers/coarse_sdf.py:98,507, so this is new behaviour: loss = mean over the batch's views).
+"""View-sharded multi-GPU step: one process per GPU, Gaussian parameters replicated, each rank renders its
+own view(s); the per-Gaussian gradients of the rasterizer are summed over the ranks INSIDE the op's backward,
+overlapped with it, over NCCL (NVLink 5 / NVSwitch) -- SURVEY.md section 8e.  The reference is strictly
+1 view / 1 GPU (sugar_trainers/coarse_sdf.py:98,507), so this is new behaviour: loss = sum (or mean) over the
+batch's views.
 
-The path has no other exchange step.  The flat arena
-    [ points 3 | opacity 1 | scales 3 | quaternions 4 | sh 3M ]  x P   fp32
-is reduced in place by `torch.distributed.all_reduce` (backend "nccl", or "gloo" in CPU tests).
+    vp = ViewParallel(scale=1.0 / world)          # one per model; owns the exchange state (no globals)
+    with vp.context():                            # or: _C.use_context(vp.ctx)
+        image, radii = rasterizer(means3D=..., shs=..., ...)      # the drop-in module, unchanged
+        loss(image).backward()                    # gradients arrive already summed over the ranks
 
-SH factor mode (`sh_factor_mode()`): 3M of the 11+3M floats per Gaussian are dL_dsh, and each view's
-dL_dsh is an outer product  basis(dir_view)[M] x dL/dRGB[3]  (backward.cu:20-139).  Instead of
-all-reducing 12M bytes per Gaussian the ranks all-gather the 12-byte dL/dRGB factors (plus their
-camera positions) and every rank rebuilds the summed dL_dsh with one kernel
-(sgr_sh_grad_from_factors); only the other 11 floats go through the all-reduce.  At M=16 that is
-5.4x less data on the wire at 2 GPUs and 2.6x less at 8, and each rank's backward skips writing
-its 192 B/Gaussian of dL_dsh.
-Per-view densification statistics (|means2D.grad|, radii) must NOT be summed this way
-(sugar_scene/sugar_densifier.py:156-164); they stay rank-local.
+What the backward does when an exchange is attached (sugar_b200/_C.py, include/sugar_b200.h):
+
+    blend pass ─► hook BLEND_DONE ─► per-Gaussian pass, chunk 0 ─► hook ─► chunk 1 ─► hook ─► ... ─► finalize
+                     │ all-gather of the SH factors                │ all-reduce of chunk 0's records
+                     └─ runs underneath the per-Gaussian pass       └─ runs underneath chunk 1 ...
+
+  * SH factor mode (default): 192 of the 236 B/Gaussian of gradients are dL_dsh, and each view's dL_dsh is an
+    outer product  basis(dir_view)[M] x dL/dRGB[3]  (backward.cu:20-139).  The ranks all-gather the 12-byte
+    factors dL/dRGB (they are the blend pass's colour accumulators, final when it ends) plus their camera
+    positions, and every rank rebuilds the summed dL_dsh itself (sgr_view_grad_finalize); the per-Gaussian pass
+    does not even write its own dL_dsh.
+  * The other 11 floats (means3D 3, opacity 1, scales 3, rotations 4) are written by the per-Gaussian pass as
+    one 44-byte record per Gaussian, in `chunks` Gaussian ranges; each range is all-reduced as soon as it is
+    enqueued, so only the last range's collective is exposed.  The finalize kernel splits the reduced records
+    into the arrays autograd expects (and applies `scale`).
+  * Because the sum happens on the rasterizer's OUTPUT gradients, anything in front of the op (exp / sigmoid /
+    normalize / cat of SuGaR's raw parameters) just backpropagates the summed gradient: inputs need not be
+    leaves, and several backwards per step (several views per rank) each do their own exchange.
+  * dL_dmeans2D and radii are per-view densification statistics (sugar_scene/sugar_densifier.py:156-164) and
+    are NOT summed.
+  * Losses that reach the parameters without going through the rasterizer (density / SDF regularisation,
+    evaluated per view on its rank) are summed with `reduce_grad(tensor)`: identity in the forward, all-reduce of
+    the incoming gradient in the backward.
+
+`GradArena` is the plain utility underneath the CPU tests and for callers that prefer one explicit all-reduce
+of leaf gradients after the backward (236 B/Gaussian, not overlapped).
 """
 import contextlib
-from typing import Dict
+import ctypes as C
+from typing import Dict, Optional
 
 import torch
 import torch.distributed as dist
 
-ARENA_FIELDS = ("means3D", "opacities", "scales", "rotations", "shs")  # = layout of the backward's flat buffer
+ARENA_FIELDS = ("means3D", "opacities", "scales", "rotations", "shs")
 
 
 def shard_views(num_views: int, rank: int, world: int):
@@ -31,50 +51,141 @@ def shard_views(num_views: int, rank: int, world: int):
     return list(range(rank, num_views, world))
 
 
-@contextlib.contextmanager
-def sh_factor_mode(enabled: bool = True):
-    """Within this context sugar_b200's rasterizer backward emits SH factors instead of dL_dsh; the
-    gradients must then go through `GradArena.all_reduce_from(..., campos=, sh_degree=)`."""
-    from . import _C
-    old = (_C.SH_FACTOR_MODE, _C.FACTOR_HOOK)
-    set_sh_factor_mode(enabled)
-    try:
-        yield
-    finally:
-        _C.SH_FACTOR_MODE, _C.FACTOR_HOOK = old
-        _early_gather.clear()
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
 
-_early_gather = {}  # data_ptr of the factor tensor -> (gathered [world,P,3], work handle)
+class _ReduceGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, scale, group):
+        ctx.scale, ctx.group = scale, group
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        if _world(ctx.group) > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        if ctx.scale != 1.0:
+            g.mul_(ctx.scale)
+        return g, None, None
 
 
-def _start_gather(dRGB: torch.Tensor) -> None:
-    """Stage hook of the backward: the factors are final on the current stream, the per-Gaussian
-    backward is not enqueued yet -> the all-gather runs on NCCL's stream underneath it."""
-    world = dist.get_world_size()
-    d_all = torch.empty((world,) + tuple(dRGB.shape), dtype=dRGB.dtype, device=dRGB.device)
-    _early_gather.clear()
-    _early_gather[dRGB.data_ptr()] = (d_all, dist.all_gather_into_tensor(d_all, dRGB, async_op=True))
+def reduce_grad(t: torch.Tensor, scale: float = 1.0, group=None) -> torch.Tensor:
+    """Identity whose backward sums the incoming gradient over the ranks (x scale): wrap the tensors that feed
+    per-view losses which do not go through the rasterizer."""
+    return _ReduceGrad.apply(t, scale, group)
 
 
-def set_sh_factor_mode(enabled: bool = True) -> None:
-    """Process-wide switch behind `sh_factor_mode()` (for loops that do not want a context manager)."""
-    from . import _C
-    _C.SH_FACTOR_MODE = bool(enabled)
-    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-    _C.FACTOR_HOOK = _start_gather if (enabled and multi) else None
+class ViewParallel:
+    """Exchange state of one model's view-parallel step (see the module docstring).
 
+    sh_factors  exchange 12 B/Gaussian/view SH factors instead of all-reducing dL_dsh (default True)
+    chunks      Gaussian ranges of the per-Gaussian pass; each range's all-reduce overlaps the next range
+    scale       multiplies every summed gradient (1/num_views for a mean over the batch)
+    force       run the record / finalize path even with a single rank (tests; no collectives are issued)
+    """
 
-def gather_factors(dRGB: torch.Tensor, campos: torch.Tensor):
-    """All-gather the per-view SH factors: returns (dRGB_all [V,P,3], campos_all [V,3]), V = world size."""
-    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-    if world == 1:
-        return dRGB.reshape(1, -1, 3), campos.reshape(1, 3)
-    d_all = torch.empty((world,) + tuple(dRGB.shape), dtype=dRGB.dtype, device=dRGB.device)
-    c_all = torch.empty((world, 3), dtype=campos.dtype, device=campos.device)
-    dist.all_gather_into_tensor(d_all, dRGB.contiguous())
-    dist.all_gather_into_tensor(c_all, campos.reshape(3).contiguous())
-    return d_all.view(world, -1, 3), c_all
+    def __init__(self, sh_factors: bool = True, chunks: int = 4, scale: float = 1.0, group=None, force: bool = False):
+        from . import _C
+        self.sh_factors, self.chunks, self.scale, self.group, self.force = bool(sh_factors), int(chunks), float(scale), group, force
+        self.ctx = _C.Context()
+        self.ctx.exchange = self
+        self.stats = {"backwards": 0, "collectives": 0}
+
+    # -- selection ---------------------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def context(self):
+        from . import _C
+        with _C.use_context(self.ctx):
+            yield self
+
+    def enabled(self) -> bool:
+        return self.force or _world(self.group) > 1
+
+    # -- the exchange, driven from _C.rasterize_gaussians_backward ------------------------------------------
+    def run_backward(self, lib, check, stage_hook_type, plan_type, args, bufs, P, M, degree, means3D, campos,
+                     has_cov_precomp):
+        """`args`: the positional arguments of sgr_rasterize_backward_staged without the trailing plan;
+        `bufs`: dict of the gradient tensors + "records" f32[P,11].  Returns nothing: bufs hold the reduced
+        gradients when the enqueued work completes."""
+        world = _world(self.group)
+        multi = world > 1
+        dev = means3D.device
+        factor = bool(M) and self.sh_factors
+        nchunks = max(1, self.chunks)
+        rng = lambda c: self._range(lib, check, P, nchunks, c)
+        pending = {c: [] for c in range(nchunks)}
+        early = []
+        state = {"d_all": None}
+        failure = []
+        # every view's camera position (tiny; long done when the finalize needs it)
+        if factor:
+            c_all = torch.empty((world, 3), dtype=torch.float32, device=dev)
+            if multi:
+                early.append(dist.all_gather_into_tensor(c_all, campos.reshape(3).float().contiguous(), group=self.group,
+                                                         async_op=True))
+            else:
+                c_all.copy_(campos.reshape(1, 3))
+
+        def on_stage(_ctx, stage):
+            try:
+                if stage == 1:  # SGR_STAGE_BLEND_DONE: dL_dcolors is final
+                    if factor:
+                        if multi:
+                            state["d_all"] = torch.empty((world, P, 3), dtype=torch.float32, device=dev)
+                            early.append(dist.all_gather_into_tensor(state["d_all"], bufs["colors"], group=self.group,
+                                                                     async_op=True))
+                        else:
+                            state["d_all"] = bufs["colors"].view(1, P, 3)
+                    elif not M and multi:  # colours were precomputed: their gradient is an ordinary sum
+                        early.append(dist.all_reduce(bufs["colors"], group=self.group, async_op=True))
+                elif stage >= 16 and multi:  # SGR_STAGE_CHUNK_DONE + c
+                    c = stage - 16
+                    p0, p1 = rng(c)
+                    if p1 > p0:
+                        pending[c].append(dist.all_reduce(bufs["records"][p0:p1], group=self.group, async_op=True))
+                        if M and not factor:
+                            pending[c].append(dist.all_reduce(bufs["sh"][p0:p1], group=self.group, async_op=True))
+                        if has_cov_precomp:
+                            pending[c].append(dist.all_reduce(bufs["cov3D"][p0:p1], group=self.group, async_op=True))
+            except BaseException as e:  # never unwind through the C frame
+                failure.append(e)
+
+        cb = stage_hook_type(on_stage)
+        plan = plan_type(cb, None, nchunks, bufs["records"].data_ptr())
+        check(lib.sgr_rasterize_backward_staged(*args, C.byref(plan)))
+        if failure:
+            raise failure[0]
+        for h in early:
+            h.wait()  # stream-ordered: the host does not block
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        d_all = state["d_all"]
+        for c in range(nchunks):
+            p0, p1 = rng(c)
+            for h in pending[c]:
+                h.wait()
+            if p1 > p0:
+                check(lib.sgr_view_grad_finalize(
+                    P, p0, p1, M, degree, world, means3D.data_ptr(), c_all.data_ptr() if factor else None,
+                    d_all.data_ptr() if factor else None, bufs["sh"].data_ptr() if factor else None,
+                    bufs["records"].data_ptr(), self.scale, bufs["means3D"].data_ptr(), bufs["opacity"].data_ptr(),
+                    bufs["scales"].data_ptr(), bufs["rotations"].data_ptr(), stream))
+        if self.scale != 1.0:  # what the finalize kernel did not touch
+            if M and not factor:
+                bufs["sh"].mul_(self.scale)
+            if not M:
+                bufs["colors"].mul_(self.scale)
+            if has_cov_precomp:
+                bufs["cov3D"].mul_(self.scale)
+        self.stats["backwards"] += 1
+        self.stats["collectives"] += len(early) + sum(len(v) for v in pending.values())
+
+    @staticmethod
+    def _range(lib, check, P, nchunks, c):
+        p0, p1 = C.c_int32(0), C.c_int32(0)
+        check(lib.sgr_backward_chunk_range(P, nchunks, c, C.byref(p0), C.byref(p1)))
+        return p0.value, p1.value
 
 
 def sh_grad_from_factors(means3D: torch.Tensor, campos_all: torch.Tensor, dRGB_all: torch.Tensor, M: int,
@@ -93,7 +204,8 @@ def sh_grad_from_factors(means3D: torch.Tensor, campos_all: torch.Tensor, dRGB_a
 
 
 class GradArena:
-    """Flat per-Gaussian gradient buffer laid out for a single all-reduce."""
+    """Flat per-Gaussian gradient buffer [means3D 3 | opacities 1 | scales 3 | rotations 4 | shs 3M] x P for ONE
+    explicit all-reduce of leaf gradients after the backward (backend "nccl", or "gloo" in the CPU tests)."""
 
     def __init__(self, P: int, M: int, device, fields=ARENA_FIELDS):
         widths = {"means3D": 3, "shs": 3 * M, "opacities": 1, "scales": 3, "rotations": 4}
@@ -110,7 +222,6 @@ class GradArena:
 
     @property
     def flat(self) -> torch.Tensor:
-        """Staging buffer of the packing fallback; allocated on first use (the in-place path never needs it)."""
         if self._flat is None:
             self._flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
         return self._flat
@@ -128,92 +239,18 @@ class GradArena:
             else:
                 v.copy_(g.reshape(-1))
 
-    def _shared_base(self, params: Dict[str, torch.Tensor]):
-        """If the gradients already sit back to back in one storage in arena order (they do when they
-        come from sugar_b200's backward: autograd hands the leaves detached aliases of the backward's
-        flat buffer), return that run as one flat tensor so the reduction needs no packing."""
-        g0 = params[self.fields[0]].grad
-        if g0 is None or g0.dtype != torch.float32:
-            return None
-        store, s0 = g0.untyped_storage(), g0.storage_offset()
-        for f in self.fields:
-            g = params[f].grad
-            o, n = self.offsets[f]
-            if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.numel() != n \
-                    or g.untyped_storage().data_ptr() != store.data_ptr() or g.storage_offset() != s0 + o:
-                return None
-        whole = torch.empty(0, dtype=torch.float32, device=g0.device).set_(store)
-        self._base = whole[s0:]
-        return self._base[:self.numel]
-
-    def _all_reduce_factored(self, params, buf, campos, sh_degree):
-        """SH factor mode: all-reduce everything but the sh slot, all-gather the factors, rebuild dL_dsh.
-        The collectives are issued asynchronously (factors first) so that the rebuild kernel overlaps
-        the all-reduce of the other fields."""
-        P = self.P
-        o_sh, n_sh = self.offsets["shs"]
-        M = n_sh // (3 * P)
-        # dL_dcolors sits behind [arena | dL_dmeans2D 3P] in the backward's buffer (sugar_b200/_C.py)
-        o_col = self.numel + 3 * P
-        dRGB = self._base[o_col:o_col + 3 * P]
-        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        pending = []
-        if world > 1:
-            early = _early_gather.pop(dRGB.data_ptr(), None)  # started by the backward's stage hook?
-            if early is not None:
-                d_all, hg = early[0].view(world, P, 3), [early[1]]
-            else:
-                d_all = torch.empty((world, P, 3), dtype=torch.float32, device=buf.device)
-                hg = [dist.all_gather_into_tensor(d_all, dRGB, async_op=True)]
-            if campos.dim() == 1:  # this rank's camera only: gather the others'
-                c_all = torch.empty((world, 3), dtype=torch.float32, device=buf.device)
-                hg.append(dist.all_gather_into_tensor(c_all, campos.reshape(3).contiguous(), async_op=True))
-            else:                  # [world,3]: the caller already knows every rank's camera
-                c_all = campos.contiguous()
-            # fields before / after the sh slot are contiguous runs of the arena
-            if o_sh > 0:
-                pending.append(dist.all_reduce(buf[:o_sh], op=dist.ReduceOp.SUM, async_op=True))
-            if o_sh + n_sh < buf.numel():
-                pending.append(dist.all_reduce(buf[o_sh + n_sh:], op=dist.ReduceOp.SUM, async_op=True))
-            for h in hg:
-                h.wait()
-        else:
-            d_all, c_all = dRGB.view(1, P, 3), campos.reshape(-1, 3)[:1].contiguous()
-        sh_grad_from_factors(params["means3D"].detach(), c_all, d_all, M, sh_degree, out=buf[o_sh:o_sh + n_sh])
-        for h in pending:
-            h.wait()
-
-    def all_reduce_from(self, params: Dict[str, torch.Tensor], scale: float = 1.0, campos: torch.Tensor = None,
-                        sh_degree: int = None) -> torch.Tensor:
-        """Sum the ranks' local gradients over the process group (in place when possible) and scale
-        by 1/num_views.  Returns the reduced flat arena.  Under `sh_factor_mode()` pass this rank's
-        camera position ([3]; or all ranks' positions [world,3], saving a tiny all-gather) and the active
-        SH degree."""
-        from . import _C
-        buf = self._shared_base(params)
-        if _C.SH_FACTOR_MODE and "shs" in self.offsets and self.offsets["shs"][1] > 0:
-            if buf is None or campos is None or sh_degree is None:
-                raise RuntimeError("sh_factor_mode needs the gradients of ONE sugar_b200 backward per step "
-                                   "(no accumulation) plus campos= and sh_degree=")
-            self._all_reduce_factored(params, buf, campos, sh_degree)
-            if scale != 1.0:
-                buf.mul_(scale)
-            self.reduced = buf
-            return buf
-        if buf is None:
-            self.pack(params)
-            buf = self.flat
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    def all_reduce_from(self, params: Dict[str, torch.Tensor], scale: float = 1.0, group=None) -> torch.Tensor:
+        """Pack the leaves' gradients, sum them over the ranks, scale.  Returns the reduced flat arena."""
+        self.pack(params)
+        buf = self.flat
+        if _world(group) > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         if scale != 1.0:
             buf.mul_(scale)
-        self.reduced = buf
         return buf
 
     def unpack_to(self, params: Dict[str, torch.Tensor]) -> None:
         """Write the reduced gradients back as .grad of the (replicated) parameters."""
-        src = self.reduced if hasattr(self, "reduced") else self.flat
         for f in self.fields:
             o, n = self.offsets[f]
-            if params[f].grad is None or params[f].grad.data_ptr() != src.data_ptr() + o * 4:
-                params[f].grad = src[o:o + n].view_as(params[f]).clone()
+            params[f].grad = self.flat[o:o + n].view_as(params[f]).clone()

@@ -26,10 +26,10 @@ def test_sizes_and_errors_without_gpu():
     from sugar_b200 import _lib
     L = _lib.lib
     assert b"sm_100a" in L.sgr_version()
-    assert L.sgr_geometry_bytes(1000) >= 1000 * 64
+    assert L.sgr_geometry_bytes(1000) >= 1000 * 60
     assert L.sgr_binning_bytes(0) > 0
     assert L.sgr_image_bytes(1920, 1080) >= 1920 * 1080 * 8
-    assert L.sgr_backward_scratch_bytes(10) >= 480
+    assert L.sgr_backward_scratch_bytes(10) >= 320
     # argument validation happens before any CUDA call
     v = _lib.SgrView(); g = _lib.SgrGaussians()
     v.image_width, v.image_height, g.P = 0, 0, 5
@@ -64,7 +64,7 @@ def test_new_entry_points_validate_arguments_without_gpu():
     assert L.sgr_sh_grad_from_factors(10, 16, 4, 1, None, None, None, None, None) == -1     # degree > 3
     assert L.sgr_sh_grad_from_factors(10, 16, 3, 1, None, None, None, None, None) == -1     # null pointers
     assert b"sgr_sh_grad_from_factors" in L.sgr_last_error()
-    assert L.sgr_sh_grad_from_factors(0, 16, 3, 1, None, None, None, None, None) == 0       # P == 0: nothing to do
+    assert L.sgr_sh_grad_from_factors(0, 16, 3, 1, None, None, None, None, None) == -1      # nothing to write into
     assert L.sgr_normal_loss_forward(5, 0, 10, *([None] * 10)) == -1                        # K must be > 0
     assert L.sgr_normal_loss_forward(5, 16, 10, *([None] * 10)) == -1                       # null pointers
     assert L.sgr_normal_loss_backward(5, 16, 10, *([None] * 11)) == -1
@@ -77,5 +77,18 @@ def test_new_entry_points_validate_arguments_without_gpu():
     v = _lib.SgrView(); g = _lib.SgrGaussians()
     v.image_width, v.image_height, g.P = 0, 0, 5
     hook = _lib.STAGE_HOOK(lambda ctx, stage: None)
+    plan = _lib.SgrBackwardPlan(hook, None, 4, None)
     assert L.sgr_rasterize_backward_staged(ctypes.byref(v), ctypes.byref(g), *([None] * 4), 0, *([None] * 11),
-                                           hook, None) == -1
+                                           ctypes.byref(plan)) == -1
+    # chunk ranges of the per-Gaussian pass: contiguous, cover [0, P), boundaries on CTA multiples
+    p0, p1 = ctypes.c_int32(), ctypes.c_int32()
+    for P, nch in ((1000, 4), (64, 4), (3_000_000, 4), (1, 1), (129, 3)):
+        prev, seen = 0, 0
+        for c in range(nch):
+            assert L.sgr_backward_chunk_range(P, nch, c, ctypes.byref(p0), ctypes.byref(p1)) == 0
+            assert p0.value == min(prev, P) and p0.value <= p1.value <= P
+            assert p0.value % 64 == 0 or p0.value == P
+            prev, seen = p1.value, seen + (p1.value - p0.value)
+        assert seen == P and prev == P
+    assert L.sgr_backward_chunk_range(10, 2, 2, ctypes.byref(p0), ctypes.byref(p1)) == -1
+    assert L.sgr_view_grad_finalize(10, 0, 10, 16, 3, 1, *([None] * 5), 1.0, *([None] * 5)) == -1

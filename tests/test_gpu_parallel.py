@@ -1,6 +1,7 @@
-"""SH factor mode of the view-parallel step (sugar_b200/parallel.py) on one GPU: the dL_dsh rebuilt from
-the per-view factors (sgr_sh_grad_from_factors) must equal the sum of the per-view dL_dsh of the
-ordinary backward, and every other gradient must be unchanged by the mode."""
+"""View-parallel exchange (sugar_b200/parallel.py) on ONE GPU: `ViewParallel(force=True)` drives the same
+record / chunk / factor / finalize path as a multi-rank run, with the collectives left out, so its gradients
+must equal the plain backward's.  The multi-rank numbers are checked by bench.py itself at N > 1 (`exchange_check`
+in its JSON line) and by scripts/check_view_parallel.py under torchrun."""
 import numpy as np
 import pytest
 
@@ -13,86 +14,131 @@ def _err(a, b):
     return h.rel_err(a.detach().float().cpu().numpy(), b.detach().float().cpu().numpy())
 
 
-@pytest.mark.parametrize("deg", [0, 1, 2, 3])
-def test_sh_factors_match_summed_dsh(deg):
+def _render_loss(mod, t, sc, dL, deg, ps, bg=(0.1, 0.2, 0.3), colors=None):
+    import torch
+    means2D = torch.zeros_like(ps["means3D"], requires_grad=True)
+    st = mod.GaussianRasterizationSettings(
+        image_height=sc.height, image_width=sc.width, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy,
+        bg=torch.tensor(bg, device="cuda"), scale_modifier=1.0, viewmatrix=t["viewmatrix"], projmatrix=t["projmatrix"],
+        sh_degree=deg, campos=t["campos"], prefiltered=False, debug=False)
+    kw = dict(colors_precomp=colors) if colors is not None else dict(shs=ps["shs"])
+    color, radii = mod.GaussianRasterizer(st)(means3D=ps["means3D"], means2D=means2D, opacities=ps["opacities"],
+                                              scales=ps["scales"], rotations=ps["rotations"], **kw)
+    return (color * dL).sum(), means2D
+
+
+@pytest.mark.parametrize("deg,chunks,factors", [(3, 4, True), (1, 3, True), (0, 1, True), (3, 4, False), (2, 7, True)])
+def test_forced_exchange_matches_plain_backward(deg, chunks, factors):
     import torch
     from sugar_b200 import diff_gaussian_rasterization as mod
     from sugar_b200 import parallel, scenes
-    P, W, H = 6000, 160, 96
-    base = scenes.make_scene(P, W, H, seed=31 + deg, camera="posed")
-    views = [base, scenes.with_camera_offset(base, 0.15, (0.3, -0.1, 0.2)),
-             scenes.with_camera_offset(base, -0.2, (-0.4, 0.2, 0.5))]
-    bg = (0.1, 0.2, 0.3)
-    want, factors, campos = None, [], []
-    for v, sc in enumerate(views):
-        dL = scenes.upstream_grad(W, H, seed=5 + v)
-        ref = h.run_module(mod, sc, bg, dL=dL, sh_degree=deg)["grads"]
-        with parallel.sh_factor_mode():
-            t = h.to_torch(sc)
-            leaf = lambda x: x.clone().requires_grad_(True)
-            ps = {k: leaf(t[k]) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
-            means2D = torch.zeros_like(ps["means3D"], requires_grad=True)
-            st = mod.GaussianRasterizationSettings(
-                image_height=H, image_width=W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy,
-                bg=torch.tensor(bg, device="cuda"), scale_modifier=1.0, viewmatrix=t["viewmatrix"],
-                projmatrix=t["projmatrix"], sh_degree=deg, campos=t["campos"], prefiltered=False, debug=False)
-            color, _ = mod.GaussianRasterizer(st)(means3D=ps["means3D"], means2D=means2D, opacities=ps["opacities"],
-                                                  shs=ps["shs"], scales=ps["scales"], rotations=ps["rotations"])
-            (color * torch.from_numpy(dL).cuda()).sum().backward()
-            arena = parallel.GradArena(P, 16, "cuda")
-            buf = arena._shared_base(ps)
-            assert buf is not None
-            o_col = arena.flat.numel() + 3 * P
-            factors.append(arena._base[o_col:o_col + 3 * P].clone().view(P, 3))
-            campos.append(t["campos"].clone())
-            # single-process all_reduce_from == this view's own gradients, dL_dsh rebuilt from its factor
-            arena.all_reduce_from(ps, campos=t["campos"], sh_degree=deg)
-        for k in ("means3D", "opacities", "scales", "rotations"):
-            assert _err(ps[k].grad, ref[k]) <= 1e-4, k  # fp32 atomics: run-to-run order differs
-        assert _err(ps["shs"].grad, ref["shs"]) <= 1e-4
-        want = ref["shs"].double() if want is None else want + ref["shs"].double()
-    got = parallel.sh_grad_from_factors(torch.from_numpy(base.means3D).cuda(), torch.stack(campos).contiguous(),
-                                        torch.stack(factors).contiguous(), 16, deg)
-    assert _err(got, want) <= 1e-4
+    P, W, H = 6001, 160, 96          # not a multiple of the CTA size: partial last block, ragged chunks
+    sc = scenes.make_scene(P, W, H, seed=31 + deg, camera="posed")
+    dL = torch.from_numpy(scenes.upstream_grad(W, H, seed=5)).cuda()
+    t = h.to_torch(sc)
+    leaf = lambda x: x.clone().requires_grad_(True)
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+    ps_a = {k: leaf(t[k]) for k in names}
+    loss, m2a = _render_loss(mod, t, sc, dL, deg, ps_a)
+    loss.backward()
+    vp = parallel.ViewParallel(sh_factors=factors, chunks=chunks, scale=0.5, force=True)
+    ps_b = {k: leaf(t[k]) for k in names}
+    with vp.context():
+        loss, m2b = _render_loss(mod, t, sc, dL, deg, ps_b)
+        loss.backward()
+    assert vp.stats["backwards"] == 1
+    for k in names:
+        assert _err(ps_b[k].grad, 0.5 * ps_a[k].grad) <= 1e-4, k   # fp32 atomics: run-to-run order differs
+    assert _err(m2b.grad, m2a.grad) <= 1e-4                        # per-view statistic: neither summed nor scaled
     used = (deg + 1) ** 2
     if used < 16:
-        assert float(got[:, used:].abs().max()) == 0.0
+        assert float(ps_b["shs"].grad[:, used:].abs().max()) == 0.0
 
 
-def test_staged_backward_hook_sees_final_factors():
-    """sgr_rasterize_backward_staged: at hook time the factors enqueued so far are already the final
-    masked dL/dRGB, and the remaining gradients equal the unstaged factor-mode backward."""
+def test_exchange_with_precomputed_colours_and_activations_in_front():
+    """The trainers' path: raw parameters -> exp / sigmoid / normalize (+ python colours) -> rasterizer.  The
+    exchange acts on the op's output gradients, so non-leaf inputs need nothing special."""
     import torch
-    from sugar_b200 import _C, parallel, scenes
     from sugar_b200 import diff_gaussian_rasterization as mod
-    P, W, H, deg = 5000, 160, 96, 3
-    sc = scenes.make_scene(P, W, H, seed=77, camera="posed")
+    from sugar_b200 import parallel, scenes
+    P, W, H = 5000, 160, 96
+    sc = scenes.make_scene(P, W, H, seed=3, camera="posed")
     dL = torch.from_numpy(scenes.upstream_grad(W, H, seed=9)).cuda()
     t = h.to_torch(sc)
 
-    def run(hook):
-        ps = {k: t[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
-        means2D = torch.zeros_like(ps["means3D"], requires_grad=True)
-        st = mod.GaussianRasterizationSettings(
-            image_height=H, image_width=W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy, bg=torch.zeros(3, device="cuda"),
-            scale_modifier=1.0, viewmatrix=t["viewmatrix"], projmatrix=t["projmatrix"], sh_degree=deg,
-            campos=t["campos"], prefiltered=False, debug=False)
-        with parallel.sh_factor_mode():
-            _C.FACTOR_HOOK = hook
-            color, _ = mod.GaussianRasterizer(st)(means3D=ps["means3D"], means2D=means2D, opacities=ps["opacities"],
-                                                  shs=ps["shs"], scales=ps["scales"], rotations=ps["rotations"])
-            (color * dL).sum().backward()
-            arena = parallel.GradArena(P, 16, "cuda")
-            assert arena._shared_base(ps) is not None
-            o_col = arena.flat.numel() + 3 * P
-            final = arena._base[o_col:o_col + 3 * P].clone().view(P, 3)
-        return ps, final
+    def raw():
+        r = dict(means3D=t["means3D"].clone(), log_scales=t["scales"].log(), quats=t["rotations"] * 1.7,
+                 logit=torch.logit(t["opacities"].clamp(1e-4, 1 - 1e-4)), colors=t["colors_precomp"].clone())
+        return {k: v.requires_grad_(True) for k, v in r.items()}
 
-    seen = []
-    ps_a, fin_a = run(lambda d: seen.append(d.clone()))   # clone is stream-ordered: snapshot at hook time
-    ps_b, fin_b = run(None)
-    assert len(seen) == 1 and seen[0].shape == (P, 3)
-    assert torch.equal(seen[0], fin_a)
-    assert _err(fin_a, fin_b) <= 1e-4 and float(fin_a.abs().max()) > 0
-    for k in ("means3D", "opacities", "scales", "rotations"):
-        assert _err(ps_a[k].grad, ps_b[k].grad) <= 1e-4, k
+    def run(r):
+        ps = dict(means3D=r["means3D"], opacities=torch.sigmoid(r["logit"]), scales=torch.exp(r["log_scales"]),
+                  rotations=torch.nn.functional.normalize(r["quats"], dim=-1))
+        loss, _ = _render_loss(mod, t, sc, dL, 0, ps, colors=r["colors"] * 1.0)
+        loss.backward()
+
+    a = raw()
+    run(a)
+    b = raw()
+    vp = parallel.ViewParallel(chunks=4, force=True)
+    with vp.context():
+        run(b)
+    for k in a:
+        assert _err(b[k].grad, a[k].grad) <= 1e-4, k
+
+
+def test_two_backwards_per_step_accumulate():
+    """Two views rendered by one rank in one step (gradient accumulation): each backward runs its own exchange."""
+    import torch
+    from sugar_b200 import diff_gaussian_rasterization as mod
+    from sugar_b200 import parallel, scenes
+    P, W, H, deg = 5000, 160, 96, 3
+    sc1 = scenes.make_scene(P, W, H, seed=77, camera="posed")
+    sc2 = scenes.with_camera_offset(sc1, 0.15, (0.3, -0.1, 0.2))
+    dL = torch.from_numpy(scenes.upstream_grad(W, H, seed=9)).cuda()
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+    t1, t2 = h.to_torch(sc1), h.to_torch(sc2)
+
+    def both(ctxmgr):
+        ps = {k: t1[k].clone().requires_grad_(True) for k in names}
+        with ctxmgr:
+            for t, sc in ((t1, sc1), (t2, sc2)):
+                loss, _ = _render_loss(mod, t, sc, dL, deg, ps)
+                loss.backward()
+        return ps
+    import contextlib
+    a = both(contextlib.nullcontext())
+    vp = parallel.ViewParallel(chunks=2, force=True)
+    b = both(vp.context())
+    assert vp.stats["backwards"] == 2
+    for k in names:
+        assert _err(b[k].grad, a[k].grad) <= 1e-4, k
+
+
+def test_sh_factors_of_three_views_rebuild_the_summed_dsh():
+    """sgr_sh_grad_from_factors on the gathered factors of several views == the sum of the views' dL_dsh; the
+    factor of a view is the dL_dcolors the backward returns with SH colours (clamp-masked dL/dRGB)."""
+    import torch
+    from sugar_b200 import _C, parallel, scenes
+    P, W, H, deg = 6000, 160, 96, 3
+    base = scenes.make_scene(P, W, H, seed=34, camera="posed")
+    views = [base, scenes.with_camera_offset(base, 0.15, (0.3, -0.1, 0.2)),
+             scenes.with_camera_offset(base, -0.2, (-0.4, 0.2, 0.5))]
+    want, factors, campos = None, [], []
+    E = torch.Tensor([])
+    for v, sc in enumerate(views):
+        t = h.to_torch(sc)
+        dL = torch.from_numpy(scenes.upstream_grad(W, H, seed=5 + v)).cuda()
+        bg = torch.zeros(3, device="cuda")
+        R, color, radii, geom, binning, img = _C.rasterize_gaussians(
+            bg, t["means3D"], E, t["opacities"], t["scales"], t["rotations"], 1.0, E, t["viewmatrix"], t["projmatrix"],
+            sc.tanfovx, sc.tanfovy, H, W, t["shs"], deg, t["campos"], False, False)
+        g = _C.rasterize_gaussians_backward(bg, t["means3D"], radii, E, t["scales"], t["rotations"], 1.0, E,
+                                            t["viewmatrix"], t["projmatrix"], sc.tanfovx, sc.tanfovy, dL, t["shs"], deg,
+                                            t["campos"], geom, R, binning, img, False)
+        factors.append(g[1].clone())
+        campos.append(t["campos"].clone())
+        want = g[5].double() if want is None else want + g[5].double()
+    got = parallel.sh_grad_from_factors(torch.from_numpy(base.means3D).cuda(), torch.stack(campos).contiguous(),
+                                        torch.stack(factors).contiguous(), 16, deg)
+    assert _err(got, want) <= 1e-4

@@ -60,42 +60,48 @@ def test_arena_allreduce_gloo_world2():
     assert 59 * 50 == sum(n for _, n in __import__("sugar_b200.parallel", fromlist=["x"]).GradArena(50, 16, "cpu").offsets.values())
 
 
-def test_arena_reduces_backward_buffer_in_place():
-    """Gradients handed out by an autograd Function as slices of one flat buffer (what sugar_b200's
-    backward does) are recognised and reduced in place: no packing copy."""
-    import torch
+def _rg_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
     from sugar_b200 import parallel
-    P, M = 10, 2
-    widths = (3, 1, 3, 4, 3 * M, 3, 3, 6)
+    x = torch.arange(6, dtype=torch.float32).reshape(2, 3).requires_grad_(True)
+    y = parallel.reduce_grad(x * 2.0, scale=0.5)          # not a leaf: the sum happens on its gradient
+    (y * (rank + 1)).sum().backward()
+    q.put((rank, x.grad.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.close()
+    q.join_thread()
 
-    class Fn(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, *a):
-            return sum(x.sum() for x in a).reshape(1)
 
-        @staticmethod
-        def backward(ctx, g):
-            flat = torch.arange(8 + P * sum(widths) + 20, dtype=torch.float32)[8:]  # nonzero storage offset
-            outs, o = [], 0
-            for k in widths[:5]:
-                outs.append(flat[o:o + P * k])
-                o += P * k
-            return (outs[0].view(P, 3), outs[1].view(P, 1), outs[4].view(P, M, 3), outs[2].view(P, 3),
-                    outs[3].view(P, 4))
+def test_reduce_grad_sums_incoming_gradient_gloo_world2():
+    """parallel.reduce_grad: identity forward; backward = all-reduce(sum) of the incoming gradient x scale, so
+    per-view losses that do not pass through the rasterizer still reach the parameters summed over the ranks."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [ctx.Process(target=_rg_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    import numpy as np
+    want = np.full((2, 3), (1 + 2) * 0.5 * 2.0, np.float32)  # sum over ranks of (rank+1), x scale, x d(2x)/dx
+    for r in range(world):
+        assert np.allclose(res[r], want), (r, res[r])
 
-    ps = dict(means3D=torch.zeros(P, 3), opacities=torch.zeros(P, 1), shs=torch.zeros(P, M, 3),
-              scales=torch.zeros(P, 3), rotations=torch.zeros(P, 4))
-    ps = {k: v.requires_grad_(True) for k, v in ps.items()}
-    Fn.apply(*ps.values()).sum().backward()
-    arena = parallel.GradArena(P, M, "cpu")
-    buf = arena._shared_base(ps)
-    assert buf is not None and buf.numel() == arena.flat.numel()
-    assert buf.data_ptr() == ps["means3D"].grad.data_ptr()
-    out = arena.all_reduce_from(ps, scale=2.0)
-    assert out.data_ptr() == buf.data_ptr()
-    assert float(ps["means3D"].grad[0, 0]) == 16.0  # scaled through the alias
-    # separate tensors (e.g. after gradient accumulation) fall back to packing
-    ps2 = {k: v.detach().clone().requires_grad_(True) for k, v in ps.items()}
-    for v in ps2.values():
-        v.grad = torch.ones_like(v)
-    assert arena._shared_base(ps2) is None
+
+def test_reduce_grad_single_process_is_identity_times_scale():
+    from sugar_b200 import parallel
+    x = torch.ones(4, requires_grad=True)
+    parallel.reduce_grad(x, scale=0.25).sum().backward()
+    assert torch.allclose(x.grad, torch.full((4,), 0.25))
+    assert parallel.shard_views(5, 1, 2) == [1, 3]
