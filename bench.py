@@ -53,9 +53,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gaussians", type=int, default=3_000_000)
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--workload", default="raster", choices=["raster", "c5", "coarse_sdf_step", "refine_step"],
+                    help="raster: the headline (one view per GPU per step, fwd+bwd); c5: BASELINE config 5, a batch of "
+                         "8 views of 6M Gaussians at 3840x2160 sharded over the GPUs (strong scaling); the others: "
+                         "bench_workloads.py")
+    ap.add_argument("--views-per-step", type=int, default=None,
+                    help="views in one step's batch, sharded round-robin over the ranks (default: one per GPU)")
+    ap.add_argument("--gaussians", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sh-factors", action="store_true",
@@ -270,10 +276,21 @@ def verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D, sh_
 
 def main():
     args = parse()
-    import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "c5":   # BASELINE.json configs[4]; SURVEY 8(d): strong scaling of a fixed 8-view batch
+        args.gaussians, args.width, args.height = args.gaussians or 6_000_000, args.width or 3840, args.height or 2160
+        args.views_per_step = args.views_per_step or 8
+    elif args.workload != "raster":
+        if rank != 0:
+            return 0  # single-GPU workloads: rank 0 alone runs them
+        import bench_workloads
+        return bench_workloads.run(args, load_scenes(), load_peaks, ClockSampler, cpu_baseline_density)
+    args.gaussians = args.gaussians or 3_000_000
+    args.width = args.width or 1920
+    args.height = args.height or 1080
+    import torch
     dist = None
     if world > 1:
         if args.impl == "reference" and rank != 0:
@@ -315,20 +332,25 @@ def main():
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     params = {k: t(getattr(sc, k)).requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
     means2D = torch.zeros_like(params["means3D"], requires_grad=True)
-    # each rank looks at the cloud from a slightly different (seeded) pose: rotate about the view axis
-    ang = 0.05 * rank
-    Rz = np.eye(4, dtype=np.float64)
-    Rz[0, 0] = Rz[1, 1] = math.cos(ang); Rz[0, 1] = -math.sin(ang); Rz[1, 0] = math.sin(ang)
-    V = Rz  # world->view
-    viewmatrix_h = torch.from_numpy(V.T.astype(np.float32)).pin_memory()
+    # every view of the batch looks at the cloud from its own (seeded) pose: rotated about the view axis.  The
+    # batch's views are dealt round-robin to the ranks (parallel.shard_views); loss = mean over the batch: the
+    # 1/views factor is folded into the upstream gradients.
+    views_total = args.views_per_step or max(world, 1)
+    my_views = list(range(rank, views_total, max(world, 1))) if not use_ref else [0]
     Pm = scenes.projection_matrix(0.01, 100.0, sc.tanfovx, sc.tanfovy)
-    projmatrix_h = torch.from_numpy((V.T @ Pm.T).astype(np.float32)).pin_memory()
-    campos_h = torch.zeros(3).pin_memory()
-    bg_h = torch.zeros(3).pin_memory()
-    # loss = mean over the batch's views: the 1/world factor is folded into the upstream gradient
-    dL_h = torch.from_numpy(scenes.upstream_grad(W, H, seed=1 + rank) / max(world, 1)).pin_memory()
-    viewmatrix, projmatrix, campos, bg, dL = (x.to(dev) for x in (viewmatrix_h, projmatrix_h, campos_h, bg_h, dL_h))
 
+    def make_view(v):
+        ang = 0.05 * v
+        Rz = np.eye(4, dtype=np.float64)
+        Rz[0, 0] = Rz[1, 1] = math.cos(ang); Rz[0, 1] = -math.sin(ang); Rz[1, 0] = math.sin(ang)
+        host = (torch.from_numpy(Rz.T.astype(np.float32)).pin_memory(),
+                torch.from_numpy((Rz.T @ Pm.T).astype(np.float32)).pin_memory(), torch.zeros(3).pin_memory(),
+                torch.zeros(3).pin_memory(),
+                torch.from_numpy(scenes.upstream_grad(W, H, seed=1 + v) / (views_total if not use_ref else 1)).pin_memory())
+        return {"host": host, "dev": tuple(x.to(dev) for x in host)}
+    views = [make_view(v) for v in my_views]
+    dL_h = views[0]["host"][4]
+    viewmatrix, projmatrix, campos, bg, dL = views[0]["dev"]
 
     def settings(vm, pm, cp, b):
         return mod.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy,
@@ -353,10 +375,12 @@ def main():
         means2D.grad = None
 
     def step_device():
-        rast = mod.GaussianRasterizer(settings(viewmatrix, projmatrix, campos, bg))
-        color, radii = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
-                            shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
-        torch.autograd.backward(color, dL)
+        for view in views:   # this rank's views of the batch: each backward runs its own exchange
+            vm, pm, cp, b, g = view["dev"]
+            rast = mod.GaussianRasterizer(settings(vm, pm, cp, b))
+            color, radii = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
+                                shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+            torch.autograd.backward(color, g)
         zero_grads()
         return radii
 
@@ -372,29 +396,30 @@ def main():
     e2e_state = {"i": 0}
     loss_ring = torch.full((4096,), float("nan")).pin_memory()
 
-    def prefetch(k):
+    def prefetch(k, view):
         with torch.cuda.stream(copy_stream):
-            slots[k] = tuple(x.to(dev, non_blocking=True) for x in (viewmatrix_h, projmatrix_h, campos_h, bg_h, dL_h))
+            slots[k] = tuple(x.to(dev, non_blocking=True) for x in view["host"])
             slot_ready[k].record(copy_stream)
 
     def step_e2e():
-        k = e2e_state["i"] & 1
-        e2e_state["i"] += 1
-        if slots[k] is None:
-            prefetch(k)
-        cur = torch.cuda.current_stream(dev)
-        cur.wait_event(slot_ready[k])
-        vm, pm, cp, b, g = slots[k]
-        for x in slots[k]:
-            x.record_stream(cur)  # allocated on the copy stream, consumed on this one
-        prefetch(k ^ 1)  # next step's inputs (fresh tensors: nothing in flight is overwritten)
-        rast = mod.GaussianRasterizer(settings(vm, pm, cp, b))
-        color, radii = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
-                            shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
-        loss = (color * g).sum()
-        loss.backward()
-        # device -> host read of the step's result
-        loss_ring[(e2e_state["i"] - 1) % loss_ring.numel()].copy_(loss.detach(), non_blocking=True)
+        for n, view in enumerate(views):
+            k = e2e_state["i"] & 1
+            e2e_state["i"] += 1
+            if slots[k] is None:
+                prefetch(k, view)
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(slot_ready[k])
+            vm, pm, cp, b, g = slots[k]
+            for x in slots[k]:
+                x.record_stream(cur)  # allocated on the copy stream, consumed on this one
+            prefetch(k ^ 1, views[(n + 1) % len(views)])  # the next view's inputs (fresh tensors)
+            rast = mod.GaussianRasterizer(settings(vm, pm, cp, b))
+            color, radii = rast(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
+                                shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
+            loss = (color * g).sum()
+            loss.backward()
+            # device -> host read of the view's result
+            loss_ring[(e2e_state["i"] - 1) % loss_ring.numel()].copy_(loss.detach(), non_blocking=True)
         zero_grads()
 
     def barrier():
@@ -464,15 +489,21 @@ def main():
         step_e2e()
     e2e_first = e2e_state["i"]
     ms_e2e = timed(step_e2e, args.steps)
-    e2e_losses = loss_ring[[(e2e_first + k) % loss_ring.numel() for k in range(args.steps)]]
+    e2e_losses = loss_ring[[(e2e_first + k) % loss_ring.numel() for k in range(args.steps * len(views))]]
     if not bool(torch.isfinite(e2e_losses).all()):
         raise RuntimeError("e2e: a step's loss did not reach the host")
 
     # `config` is identical in both arms (the driver compares them); arm-specific facts live elsewhere
-    out = {"metric": METRIC, "value": world / (ms * 1e-3) if not use_ref else 1.0 / (ms * 1e-3), "unit": "views/s",
+    strong = args.views_per_step is not None
+    metric = METRIC if args.workload == "raster" and args.gaussians == 3_000_000 and (W, H) == (1920, 1080) else \
+        f"forward+backward views/sec @{P} Gaussians {W}x{H}"
+    out = {"metric": metric, "value": views_total / (ms * 1e-3) if not use_ref else 1.0 / (ms * 1e-3), "unit": "views/s",
            "n_gpus": 1 if use_ref else world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{P} Gaussians (SH deg {D}, M=16) {W}x{H}, 1 view per GPU per step, fwd+bwd",
+           "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": (f"{P} Gaussians (SH deg {D}, M=16) {W}x{H}, " +
+                                   (f"a batch of {views_total} views per step sharded over the GPUs" if strong else
+                                    "1 view per GPU per step") + ", fwd+bwd"),
                       "visible": V_vis, "l2_policy": "inputs (708 MB of Gaussian parameters) larger than L2; no flush"},
            "parallelism": {"mode": f"view-dp{world}" if world > 1 else "single",
                            "exchange": ("none" if world == 1 else "all-reduce 236 B/Gaussian" if args.no_sh_factors else
@@ -480,9 +511,10 @@ def main():
                                         f"per-Gaussian pass + all-reduce 44 B/Gaussian in {args.chunks} overlapped chunks"),
                            "exchange_check": exchange_check},
            "clocks": clk}
-    n_e2e = 1 if use_ref else world
+    n_e2e = 1 if use_ref else views_total
     out["e2e"] = {"value": n_e2e / (ms_e2e * 1e-3), "unit": "views/s",
-                  "h2d_bytes_per_step": int(dL_h.numel() * 4 + (16 + 16 + 3 + 3) * 4), "d2h_bytes_per_step": 4,
+                  "h2d_bytes_per_step": int((dL_h.numel() * 4 + (16 + 16 + 3 + 3) * 4) * len(views)),
+                  "d2h_bytes_per_step": 4 * len(views),
                   "ms_per_step": ms_e2e,
                   "resident": "the Gaussian parameters (708 MB: the trainer's nn.Parameters) stay device-resident in "
                               "both arms, as in the reference's training loop; per-step H2D = this view's camera "

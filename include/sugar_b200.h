@@ -67,7 +67,16 @@ typedef struct SgrGaussians {
     const float *scales;         /* f32[P,3]   or NULL */
     const float *rotations;      /* f32[P,4] (w,x,y,z; pre-normalised by the caller) or NULL */
     const float *cov3D_precomp;  /* f32[P,6]   or NULL */
+    /* Raw-parameter mode (0 = the reference's contract above).  SGR_ACT_RAW: the arrays are a SuGaR model's raw
+     * parameters and its activations (sugar_scene/sugar_model.py:400-479) are applied in the kernels, their chain
+     * rule in the backward: opacities = all_densities (sigmoid), scales = _scales (exp), rotations = _quaternions
+     * (normalize), and the SH coefficients stay in the model's two arrays: shs = _sh_coordinates_dc f32[P,1,3],
+     * sh_rest = _sh_coordinates_rest f32[P,M-1,3].  The backward's dL_dopacity / dL_dscales / dL_drotations are
+     * then gradients of the RAW parameters, dL_dsh is f32[P,1,3] and dL_dsh_rest (SgrBackwardPlan) f32[P,M-1,3]. */
+    int32_t activations;
+    const float *sh_rest;        /* f32[P,M-1,3], raw mode only */
 } SgrGaussians;
+#define SGR_ACT_RAW 1
 
 /* Scratch allocator: replaces `std::function<char*(size_t)>` (rasterizer.h:31-34,
  * rasterize_points.cu:27-33).  Must return device memory aligned to >= 256 bytes that stays
@@ -135,6 +144,7 @@ typedef struct SgrBackwardPlan {
     void *hook_ctx;
     int32_t num_chunks;
     float *reduce_records; /* may be NULL */
+    float *dL_dsh_rest;    /* raw-parameter mode (SgrGaussians.activations): f32[P,M-1,3], fully written */
 } SgrBackwardPlan;
 SGR_API int sgr_rasterize_backward_staged(const SgrView *view, const SgrGaussians *g, const int32_t *radii,
                                           const void *geom_buffer, const void *binning_buffer, const void *image_buffer,

@@ -48,7 +48,7 @@ def knn_idx(points: torch.Tensor, K: int, queries: torch.Tensor = None) -> torch
 
 
 def field_values_torch(x, nbr_idx, points, scaling, quaternions, strengths, density_factor=1.0,
-                       density_threshold=1.0, opacity_min_clamp=1e-16):
+                       density_threshold=1.0, opacity_min_clamp=1e-16, return_sdf_grad=False, sdf_grad_max_value=10.0):
     """get_field_values with closest_gaussians_idx given; tensors may require grad."""
     s = 1.0 / scaling.clamp(min=1e-8)
     inv_scaled_rot = quaternion_to_matrix(quaternions) * s[:, None]          # :730-735
@@ -67,7 +67,46 @@ def field_values_torch(x, nbr_idx, points, scaling, quaternions, strengths, dens
     clamped = densities.clamp(min=opacity_min_clamp)
     out["beta"] = beta
     out["sdf"] = beta * (torch.sqrt(-2.0 * torch.log(clamped)) - np.sqrt(-2.0 * np.log(min(density_threshold, 1.0))))
+    if return_sdf_grad:                                                                    # :1307-1314
+        g = (nb[..., None] * (c_isr @ warped)[..., 0]).sum(dim=-2)
+        g = (beta / (clamped * torch.sqrt(-2.0 * torch.log(clamped))).clamp(min=opacity_min_clamp))[..., None] * g
+        out["sdf_grad"] = g.clamp(min=-sdf_grad_max_value, max=sdf_grad_max_value)
     return out
+
+
+# sugar_utils/spherical_harmonics.py:1-40 (constants), :117-172 (eval_sh)
+_C0 = 0.28209479177387814
+_C1 = 0.4886025119029199
+_C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+_C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+       1.445305721320277, -0.5900435899266435]
+
+
+def eval_sh(deg, sh, dirs):
+    """eval_sh (sugar_utils/spherical_harmonics.py:117-172), degrees 0-3: sh [..., C, (deg+1)^2], dirs [..., 3]."""
+    result = _C0 * sh[..., 0]
+    if deg > 0:
+        x, y, z = dirs[..., 0:1], dirs[..., 1:2], dirs[..., 2:3]
+        result = (result - _C1 * y * sh[..., 1] + _C1 * z * sh[..., 2] - _C1 * x * sh[..., 3])
+        if deg > 1:
+            xx, yy, zz = x * x, y * y, z * z
+            xy, yz, xz = x * y, y * z, x * z
+            result = (result + _C2[0] * xy * sh[..., 4] + _C2[1] * yz * sh[..., 5] +
+                      _C2[2] * (2.0 * zz - xx - yy) * sh[..., 6] + _C2[3] * xz * sh[..., 7] + _C2[4] * (xx - yy) * sh[..., 8])
+            if deg > 2:
+                result = (result + _C3[0] * y * (3 * xx - yy) * sh[..., 9] + _C3[1] * xy * z * sh[..., 10] +
+                          _C3[2] * y * (4 * zz - xx - yy) * sh[..., 11] + _C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12] +
+                          _C3[4] * x * (4 * zz - xx - yy) * sh[..., 13] + _C3[5] * z * (xx - yy) * sh[..., 14] +
+                          _C3[6] * x * (xx - 3 * yy) * sh[..., 15])
+    return result
+
+
+def points_rgb_torch(positions, sh_coordinates, camera_center, sh_levels):
+    """SuGaR.get_points_rgb (sugar_model.py:839-883): the trainers' python colour path
+    (compute_color_in_rasterizer=False, coarse_sdf.py:51)."""
+    dirs = torch.nn.functional.normalize(positions - camera_center.reshape(1, 3), dim=-1)
+    shs_view = sh_coordinates[:, :sh_levels ** 2].transpose(-1, -2).reshape(-1, 3, sh_levels ** 2)
+    return torch.clamp_min(eval_sh(sh_levels - 1, shs_view, dirs) + 0.5, 0.0).view(-1, 3)
 
 
 def smallest_axis(scaling, quaternions):

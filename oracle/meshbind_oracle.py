@@ -51,7 +51,8 @@ def bind_to_mesh_torch(verts, faces, bary, scales_raw, complex_raw, thickness):
     faces_verts = verts[faces]                                                    # :391
     points = (faces_verts[:, None] * bary.reshape(n, 3, 1)[None]).sum(dim=-2).reshape(F * n, 3)   # :394-398
     plane = torch.exp(scales_raw)                                                 # :418
-    scaling = torch.cat([thickness * torch.ones(len(scales_raw), 1, dtype=plane.dtype), plane], dim=-1)   # :438-441
+    scaling = torch.cat([thickness * torch.ones(len(scales_raw), 1, dtype=plane.dtype, device=plane.device), plane],
+                        dim=-1)                                                      # :438-441
     R_0 = torch.nn.functional.normalize(faces_normals(verts, faces), dim=-1)       # :448
     base_R_1 = torch.nn.functional.normalize(faces_verts[:, 0] - faces_verts[:, 1], dim=-1)   # :452
     base_R_2 = torch.nn.functional.normalize(torch.cross(R_0, base_R_1, dim=-1))   # :455

@@ -4,8 +4,8 @@
 # Everything lands in gpurun_out/<tag>_*; nothing here is a bench value except <tag>_bench*.json.
 tag=${1:-sess}; mode=${2:-full}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x 2>&1 | tail -40 > gpurun_out/${tag}_tests.log
-tail -3 gpurun_out/${tag}_tests.log
+python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/${tag}_tests.log
+tail -15 gpurun_out/${tag}_tests.log
 if [ -f sugar_b200/lib/variants/lib_stats2.so ]; then
   SGR_LIB_PATH=$PWD/sugar_b200/lib/variants/lib_stats2.so python scripts/blend_stats.py > gpurun_out/${tag}_stats.json 2> gpurun_out/${tag}_stats.err
 fi

@@ -165,8 +165,10 @@ def _view_struct(bg, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy,
     return v
 
 
-def _gauss_struct(P, M, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp) -> SgrGaussians:
+def _gauss_struct(P, M, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp, sh_rest=None) -> SgrGaussians:
     g = SgrGaussians()
+    g.activations = 1 if sh_rest is not None else 0   # SGR_ACT_RAW: raw SuGaR parameters, (dc, rest) SH arrays
+    g.sh_rest = _ptr(sh_rest, "sh_rest") if sh_rest is not None else None
     g.P, g.M = int(P), int(M)
     g.means3D = _ptr(means3D, "means3D")
     g.opacities = _ptr(opacity, "opacity")
@@ -184,11 +186,12 @@ def _c(t):
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug, *, context: Context = None) -> Tuple[int, torch.Tensor, torch.Tensor,
-                                                                                   torch.Tensor, torch.Tensor,
-                                                                                   torch.Tensor]:
-    """RasterizeGaussiansCUDA (rasterize_points.cu:36-115).  `context` (keyword-only, not part of the
-    reference signature) selects whose capacity hint is used; default: the calling thread's current one."""
+                        prefiltered, debug, *, context: Context = None, sh_rest: torch.Tensor = None
+                        ) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """RasterizeGaussiansCUDA (rasterize_points.cu:36-115).  Keyword-only extras that are not part of the
+    reference signature: `context` selects whose capacity hint is used (default: the calling thread's current
+    one); `sh_rest` selects raw-parameter mode (sugar_b200/fused.py): `sh` is then the model's DC array [P,1,3],
+    `sh_rest` [P,M-1,3], and opacity / scales / rotations are the RAW parameters, activated in the kernel."""
     context = context or current_context()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -197,6 +200,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     dev = means3D.device
     P, H, W = means3D.size(0), int(image_height), int(image_width)
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    if sh_rest is not None:
+        if M != 1 or sh_rest.dim() != 3 or sh_rest.size(0) != P:
+            raise RuntimeError("raw-parameter mode: sh must be [P,1,3] and sh_rest [P,M-1,3]")
+        M = 1 + sh_rest.size(1)
+        sh_rest = _c(sh_rest)
     with torch.cuda.device(dev):
         out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
@@ -211,7 +219,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         background, viewmatrix, projmatrix, campos = map(_c, (background, viewmatrix, projmatrix, campos))
         view = _view_struct(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, degree,
                             campos, prefiltered, debug)
-        g = _gauss_struct(P, M, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp)
+        g = _gauss_struct(P, M, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp, sh_rest)
         rendered = C.c_int64(0)
         stream = torch.cuda.current_stream(dev).cuda_stream
         check(lib.sgr_rasterize_forward(C.byref(view), C.byref(g), arena.cbs["geom"], None, arena.cbs["binning"], None,
@@ -229,13 +237,15 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 _PART_ALIGN = 16  # floats: every gradient array starts on a 64-byte boundary (TMA bulk stores need 16)
 
 
-def _alloc_backward(P: int, M: int, dev, with_records: bool):
+def _alloc_backward(P: int, M: int, dev, with_records: bool, split_sh: bool = False):
     """All eight gradients (+ the 44-byte reduce records of the view-parallel step) + the accumulator scratch in
     ONE rounded allocation: a stable size for the caching allocator, one free when autograd lets go."""
-    widths = [("means3D", 3), ("opacity", 1), ("scales", 3), ("rotations", 4), ("sh", 3 * M), ("means2D", 3),
-              ("colors", 3), ("cov3D", 6)]
+    widths = [("means3D", 3), ("opacity", 1), ("scales", 3), ("rotations", 4), ("sh", 3 if split_sh else 3 * M),
+              ("means2D", 3), ("colors", 3), ("cov3D", 6)]
     if with_records:
         widths.append(("records", 11))
+    if split_sh:
+        widths.append(("sh_rest", 3 * (M - 1)))
     n_scratch = (lib.sgr_backward_scratch_bytes(P) + 3) // 4 if P else 0
     offs, o = {}, 0
     for name, w in widths:
@@ -244,8 +254,9 @@ def _alloc_backward(P: int, M: int, dev, with_records: bool):
     total = o + n_scratch + 64
     flat = _big_empty(_round_up(4 * total, _ROUND) // 4, torch.float32, dev)
     skew = (-(flat.data_ptr() // 4)) % _PART_ALIGN  # the allocator aligns to 512 B; be explicit anyway
-    shapes = {"means3D": (P, 3), "opacity": (P, 1), "scales": (P, 3), "rotations": (P, 4), "sh": (P, M, 3),
-              "means2D": (P, 3), "colors": (P, 3), "cov3D": (P, 6), "records": (P, 11)}
+    shapes = {"means3D": (P, 3), "opacity": (P, 1), "scales": (P, 3), "rotations": (P, 4),
+              "sh": (P, 1 if split_sh else M, 3), "sh_rest": (P, max(M - 1, 0), 3), "means2D": (P, 3), "colors": (P, 3),
+              "cov3D": (P, 6), "records": (P, 11)}
     bufs = {name: flat[skew + offs[name]:skew + offs[name] + P * w].view(shapes[name]) for name, w in widths}
     bufs["scratch"] = flat[skew + o:skew + o + n_scratch]
     return bufs
@@ -254,16 +265,25 @@ def _alloc_backward(P: int, M: int, dev, with_records: bool):
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh,
                                  degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug, *,
-                                 context: Context = None):
+                                 context: Context = None, sh_rest: torch.Tensor = None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:118-196).  With a view-parallel exchange attached to
-    `context` (sugar_b200/parallel.py) the gradients come back already summed over the ranks."""
+    `context` (sugar_b200/parallel.py) the gradients come back already summed over the ranks.  With `sh_rest`
+    (raw-parameter mode, see rasterize_gaussians) a ninth tensor dL_dsh_rest is returned and dL_dopacity /
+    dL_dscales / dL_drotations / dL_dsh are gradients of the raw parameters."""
     context = context or current_context()
     dev = means3D.device
     P, H, W = means3D.size(0), dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    raw = sh_rest is not None
+    if raw:
+        M = 1 + sh_rest.size(1)
+        sh_rest = _c(sh_rest)
     ex = context.exchange if (context.exchange is not None and context.exchange.enabled()) else None
+    if raw and ex is not None:
+        raise NotImplementedError("raw-parameter mode under a view-parallel exchange: activate in PyTorch instead "
+                                  "(the exchange acts on the op's output gradients either way)")
     with torch.cuda.device(dev):
-        b = _alloc_backward(P, M, dev, with_records=ex is not None)
+        b = _alloc_backward(P, M, dev, with_records=ex is not None, split_sh=raw)
         if P != 0:
             means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color = map(
                 _c, (means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color))
@@ -271,7 +291,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             view = _view_struct(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, degree,
                                 campos, False, debug)
             # opacities are not an input of the reference's backward; the forward stored them
-            g = _gauss_struct(P, M, means3D, None, sh, colors, scales, rotations, cov3D_precomp)
+            g = _gauss_struct(P, M, means3D, None, sh, colors, scales, rotations, cov3D_precomp, sh_rest)
             stream = torch.cuda.current_stream(dev).cuda_stream
             factor = ex is not None and bool(M) and ex.sh_factors
             args = (C.byref(view), C.byref(g), radii.data_ptr(), geomBuffer.data_ptr(), binningBuffer.data_ptr(),
@@ -279,12 +299,16 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                     b["colors"].data_ptr(), b["opacity"].data_ptr(), b["means3D"].data_ptr(), b["cov3D"].data_ptr(),
                     b["sh"].data_ptr() if (M and not factor) else None, b["scales"].data_ptr(),
                     b["rotations"].data_ptr(), b["scratch"].data_ptr(), stream)
-            if ex is None:
+            if raw:
+                plan = _lib.SgrBackwardPlan(_lib.STAGE_HOOK(0), None, 1, None, b["sh_rest"].data_ptr() if M > 1 else None)
+                check(lib.sgr_rasterize_backward_staged(*args, C.byref(plan)))
+            elif ex is None:
                 check(lib.sgr_rasterize_backward(*args))
             else:
                 ex.run_backward(lib, check, _lib.STAGE_HOOK, _lib.SgrBackwardPlan, args, b, P, M, int(degree), means3D,
                                 campos, has_cov_precomp=cov3D_precomp is not None and cov3D_precomp.numel() != 0)
-    return (b["means2D"], b["colors"], b["opacity"], b["means3D"], b["cov3D"], b["sh"], b["scales"], b["rotations"])
+    out = (b["means2D"], b["colors"], b["opacity"], b["means3D"], b["cov3D"], b["sh"], b["scales"], b["rotations"])
+    return out + (b["sh_rest"],) if raw else out
 
 
 def mark_visible(means3D, viewmatrix, projmatrix) -> torch.Tensor:

@@ -30,7 +30,7 @@ class SgrGaussians(C.Structure):
         ("P", C.c_int32), ("M", C.c_int32),
         ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("shs", C.c_void_p),
         ("colors_precomp", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
-        ("cov3D_precomp", C.c_void_p),
+        ("cov3D_precomp", C.c_void_p), ("activations", C.c_int32), ("sh_rest", C.c_void_p),
     ]
 
 
@@ -45,7 +45,7 @@ STAGE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32)
 
 class SgrBackwardPlan(C.Structure):
     _fields_ = [("hook", STAGE_HOOK), ("hook_ctx", C.c_void_p), ("num_chunks", C.c_int32),
-                ("reduce_records", C.c_void_p)]
+                ("reduce_records", C.c_void_p), ("dL_dsh_rest", C.c_void_p)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header

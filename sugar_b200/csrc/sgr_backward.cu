@@ -71,14 +71,16 @@ int read_bwd_stats(unsigned long long *out, int reset)
 #endif
 constexpr int CH = 16;             // splats per chunk
 constexpr int CH_PITCH = CH + 1;   // float2 elements per pixel row: odd pitch = conflict-free transpose
-// per-warp chunk scratch (bytes from its base): pair[32][CH_PITCH] float2 | meta[CH] x 48 B | dp[32] float4
-//   meta: (x, y, conic a, conic b) (conic c, tau, opacity, r) (clamp bits, id, -, -)
+// per-warp chunk scratch (bytes from its base): pair[32][CH_PITCH] float2 | meta[CH] x 32 B | dp[32] float4
+//   meta: (x, y, conic a, conic b) (conic c, opacity, clamp bits, id) -- what phase 2 needs of a parked splat
 //   dp:   (dL/dpixel r g b, -T_final <bg, dL/dpixel>) of the block's pixels
-constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 48, CB_BYTES = CB_DP + 32 * 16;
+// (55.4 KB per CTA in total: four CTAs per SM fit, with 64 registers per thread)
+constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 32, CB_BYTES = CB_DP + 32 * 16;
 // CTA shared-memory map (dynamic): records of two batches, membership words, chunk scratch
 constexpr uint32_t SM_A = 0, SM_B = SM_A + 2 * BWD_B * 16, SM_C = SM_B + 2 * BWD_B * 16,
                    SM_MEMBER = SM_C + 2 * BWD_B * 16, SM_LAST = SM_MEMBER + BWD_NW * (BWD_B / 32) * 4,
                    SM_CHUNK = SM_LAST + 16, BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
+static_assert(4 * (BWD_SMEM_BYTES + 1024) <= 228 * 1024, "four CTAs of the backward blend must fit one SM's shared memory");
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -95,9 +97,8 @@ __device__ __forceinline__ void chunk_flush(uint32_t cb, int nf, float blk_x0, f
     const unsigned lane = threadIdx.x & 31u;
     const int slot = (int)(lane & (CH - 1)), half = (int)(lane >> 4);
     __syncwarp();
-    const float4 M0 = lds128(cb + CB_META + slot * 48), M1 = lds128(cb + CB_META + slot * 48 + 16);
-    const float2 M2 = lds64(cb + CB_META + slot * 48 + 32);
-    const uint32_t clamp = __float_as_uint(M2.x), id = __float_as_uint(M2.y);
+    const float4 M0 = lds128(cb + CB_META + slot * 32), M1 = lds128(cb + CB_META + slot * 32 + 16);
+    const uint32_t clamp = __float_as_uint(M1.z), id = __float_as_uint(M1.w);
     // d = mean - pixel = (ax - cx_i, ay - cy_i) with the half's centre as origin: cx_i = (i & 7) - 3.5,
     // cy_i = (i >> 3) - 0.5
     const float ax = M0.x - (blk_x0 + 3.5f), ay = M0.y - (blk_y0 + 2.0f * (float)half + 0.5f);
@@ -145,7 +146,7 @@ __device__ __forceinline__ void chunk_flush(uint32_t cb, int nf, float blk_x0, f
             red_add_v4(g, gmx, gmy, -0.5f * m3, -0.5f * m4);
             if (!(clamp & 1u)) atomicAdd(dc, c0);
         } else {
-            red_add_v2(g + 4, -0.5f * m5, __fdividef(m0, M1.z));
+            red_add_v2(g + 4, -0.5f * m5, __fdividef(m0, M1.y));
             if (!(clamp & 2u)) atomicAdd(dc + 1, c1);
             if (!(clamp & 4u)) atomicAdd(dc + 2, c2);
         }
@@ -332,12 +333,11 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
                 // park: every lane its pair; the record + id by all lanes alike (same address, same
                 // value: one wavefront, no branch)
                 sts64(cb + (lane * CH_PITCH + nfill) * 8, S, dchannel);
-                const uint32_t ma = cb + CB_META + nfill * 48;
+                const uint32_t ma = cb + CB_META + nfill * 32;
                 sts128(ma, A.x, A.y, A.z, A.w);
-                sts128(ma + 16, B.x, B.y, B.z, B.w);
                 {
                     const float2 Cm = lds64(sc + j * 16 + 8);  // (clamp bits, id)
-                    sts64(ma + 32, Cm.x, Cm.y);
+                    sts128(ma + 16, B.x, B.z, Cm.x, Cm.y);
                 }
                 if (++nfill == CH) {
                     chunk_flush(cb, CH, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc, dcol);
@@ -368,6 +368,11 @@ struct PreBwdArgs {
     // 44-byte record instead of the four arrays (the view-parallel step all-reduces these records chunk by chunk)
     float *rec11;
     int in_bulk_ok, out_bulk_ok, sh_stride, sh_vec;
+    // raw-parameter mode (SgrGaussians.activations): scales / rots are the model's raw parameters, shs its DC
+    // array and sh_rest the others; dopacity / dscales / drots / dsh / dsh_rest are gradients of the RAW parameters
+    const float *sh_rest;
+    const float4 *rec;  // splat records of the forward: rec[3i+1].z = the activated opacity
+    float *dsh_rest;
 };
 
 #define SH_C0 0.28209479177387814f
@@ -384,14 +389,17 @@ struct f3 {
 
 // SH backward (backward.cu:20-139) on one shared-memory row [M][3], in place: row k is read once
 // (t_k = <sh_k, dL/dRGB> feeds the view-direction gradient) and then overwritten by dL/dsh_k.
-__device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *row, f3 dir_orig, f3 dRGB, f3 &dmean)
+// `dc` is coefficient 0's row of three, `rest` coefficient 1's (one combined row: rest = dc + 3; raw-parameter
+// mode: two arrays).
+__device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *dc, float *rest, f3 dir_orig, f3 dRGB,
+                                                    f3 &dmean)
 {
     const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
     const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;
 #define SHB(k, w, cx, cy, cz)                                                          \
     {                                                                                  \
-        float *q_ = row + (k) * 3;                                                     \
+        float *q_ = (k) == 0 ? dc : rest + ((k) - 1) * 3;                              \
         const float t_ = q_[0] * dRGB.x + q_[1] * dRGB.y + q_[2] * dRGB.z;             \
         ddx += (cx) * t_;                                                              \
         ddy += (cy) * t_;                                                              \
@@ -429,7 +437,7 @@ __device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *row, 
     }
 #undef SHB
     // rows above the active degree stay zero (the reference returns zero-filled dL_dsh)
-    for (int k = (deg + 1) * (deg + 1) * 3; k < M * 3; k++) row[k] = 0.f;
+    for (int k = (deg + 1) * (deg + 1) * 3 - 3; k < (M - 1) * 3; k++) rest[k] = 0.f;
     // dnormvdv (auxiliary.h:107-117)
     const f3 o = dir_orig;
     const float sum2 = o.x * o.x + o.y * o.y + o.z * o.z;
@@ -458,7 +466,8 @@ constexpr int PB_O_OPA = PB_O_R11;
 constexpr int PB_O_M3D = PB_O_OPA + PB_T;
 constexpr int PB_O_SCL = PB_O_M3D + PB_T * 3;
 constexpr int PB_O_ROT = PB_O_SCL + PB_T * 3;  // multiple of 4 floats
-constexpr int PB_SH = PB_O_R11 + PB_T * 11 + (PB_T & 3 ? 4 - (PB_T & 3) : 0);  // PB_T * sh_stride
+constexpr int PB_SHDC = PB_O_R11 + PB_T * 11;  // raw mode: the DC coefficients / their gradient, PB_T*3
+constexpr int PB_SH = PB_SHDC + PB_T * 3 + (PB_T & 3 ? 4 - (PB_T & 3) : 0);  // PB_T * sh_stride
 static_assert(PB_T % 4 == 0, "every region starts on a 16-byte boundary");
 static_assert(PB_ROTS % 4 == 0 && PB_O_ROT % 4 == 0 && PB_SH % 4 == 0, "16-byte alignment of float4 regions");
 
@@ -479,6 +488,7 @@ __device__ __forceinline__ void pb_flush(float *__restrict__ dst, const float *s
     for (int i = threadIdx.x; i < n; i += PB_T) dst[i] = src[i];
 }
 
+template <bool RAW>
 __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdArgs a)
 {
     extern __shared__ __align__(16) float sm[];
@@ -496,6 +506,12 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             mbar_fence_init();
             uint32_t bytes = PB_T * 32 + PB_T * 12;
             if (a.shs) bytes += PB_T * 12;  // dL/dRGB is only an input of the SH backward
+            if (RAW && a.shs) {
+                bytes += PB_T * 12 + PB_T * (uint32_t)(a.v.M - 1) * 12;
+                bulk_g2s(sm + PB_SHDC, a.shs + (size_t)base * 3, PB_T * 12, &s_bar);
+                if (a.v.M > 1)
+                    bulk_g2s(sm + PB_SH, a.sh_rest + (size_t)base * (a.v.M - 1) * 3, PB_T * (uint32_t)(a.v.M - 1) * 12, &s_bar);
+            }
             if (a.scales) bytes += PB_T * 12 + PB_T * 16;
             if (a.cov_pre) bytes += PB_T * 24;
             mbar_expect_tx(&s_bar, bytes);
@@ -517,17 +533,22 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             pb_stage(sm + PB_ROTS, a.rots + (size_t)base * 4, n * 4);
         }
         if (a.cov_pre) pb_stage(sm + PB_COV, a.cov_pre + (size_t)base * 6, n * 6);
+        if (RAW && a.shs) {
+            pb_stage(sm + PB_SHDC, a.shs + (size_t)base * 3, n * 3);
+            pb_stage(sm + PB_SH, a.sh_rest + (size_t)base * (M - 1) * 3, n * (M - 1) * 3);
+        }
     }
     float *s_sh = sm + PB_SH;
-    const int row_f = M * 3;
-    if (a.shs) {
+    const int row_f = RAW ? (M - 1) * 3 : M * 3;  // floats per row of the SH block in shared memory
+    if (!RAW && a.shs) {
         const float *src = a.shs + (size_t)base * row_f;
         if (a.sh_vec) {
             const int row_v = row_f >> 2, total = n * row_v;
             int r = tid / row_v, c = tid - r * row_v;
             const int dr = PB_T / row_v, dc = PB_T - dr * row_v;
             for (int k = tid; k < total; k += PB_T) {
-                cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)k * 4);
+                // rows of culled Gaussians are never read (their dL_dsh rows are written as zeros below)
+                if (__ldg(a.radii + base + r) > 0) cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)k * 4);
                 r += dr;
                 c += dc;
                 if (c >= row_v) {
@@ -548,7 +569,7 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
     if (tid < n) radius = a.radii[i];
     __syncthreads();
     if (a.in_bulk_ok && full) mbar_wait(&s_bar, 0);
-    if (a.shs) {
+    if (!RAW && a.shs) {
         cp_async_wait<0>();
         __syncthreads();
     }
@@ -562,7 +583,7 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
         float *o_opa = aos ? o_m3d + 3 : sm + PB_O_OPA + tid;
         float *o_scl = aos ? o_m3d + 4 : sm + PB_O_SCL + tid * 3;
         float *o_rot = aos ? o_m3d + 7 : sm + PB_O_ROT + tid * 4;
-        float *row = s_sh + tid * a.sh_stride;
+        float *row = s_sh + tid * (RAW ? row_f : a.sh_stride);
         if (!vis) {
             o_m2d[0] = o_m2d[1] = o_m2d[2] = 0.f;
             *o_opa = 0.f;
@@ -571,8 +592,10 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             for (int k = 0; k < 6; k++) o_cov[k] = 0.f;
             o_scl[0] = o_scl[1] = o_scl[2] = 0.f;
             o_rot[0] = o_rot[1] = o_rot[2] = o_rot[3] = 0.f;
-            if (a.shs && a.dsh)
+            if (a.shs && a.dsh) {
                 for (int k = 0; k < row_f; k++) row[k] = 0.f;
+                if (RAW) sm[PB_SHDC + tid * 3] = sm[PB_SHDC + tid * 3 + 1] = sm[PB_SHDC + tid * 3 + 2] = 0.f;
+            }
         } else {
             const float4 *gr = (const float4 *)(sm + PB_GACC) + tid * 2;
             const float4 g0 = gr[0], g1 = gr[1];
@@ -581,19 +604,31 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             o_m2d[0] = dmx;
             o_m2d[1] = dmy;
             o_m2d[2] = 0.f;
-            *o_opa = g1.y;
+            // raw mode: d sigmoid = o (1 - o), with the activated opacity the forward stored in the splat record
+            float act_o = 1.0f;
+            if (RAW) {
+                const float o = __ldg(&a.rec[(size_t)i * 3 + 1]).z;
+                act_o = o * (1.0f - o);
+            }
+            *o_opa = g1.y * act_o;
 
             const float *vm = a.v.viewmatrix, *proj = a.v.projmatrix;
             const float mx = sm[PB_MEANS + tid * 3], my = sm[PB_MEANS + tid * 3 + 1], mz = sm[PB_MEANS + tid * 3 + 2];
             float c3[6];
             float4 q = make_float4(1, 0, 0, 0);
-            float sc0 = 0, sc1 = 0, sc2 = 0;
+            float sc0 = 0, sc1 = 0, sc2 = 0, q_len = 1.0f;
             if (a.cov_pre) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) c3[k] = sm[PB_COV + tid * 6 + k];
             } else {
                 sc0 = sm[PB_SCALES + tid * 3], sc1 = sm[PB_SCALES + tid * 3 + 1], sc2 = sm[PB_SCALES + tid * 3 + 2];
                 q = ((const float4 *)(sm + PB_ROTS))[tid];
+                if (RAW) {  // the forward's activations, recomputed (sugar_model.py:417, 479)
+                    sc0 = expf(sc0), sc1 = expf(sc1), sc2 = expf(sc2);
+                    q_len = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+                    const float inv = __fdiv_rn(1.0f, q_len);
+                    q = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+                }
                 cov3d_from_scale_rot(sc0, sc1, sc2, a.v.scale_modifier, q, c3);
             }
             // ---- computeCov2DCUDA (backward.cu:144-274) ----
@@ -671,7 +706,8 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
                 // accumulated dL/dRGB, already masked where the forward clamped the colour
                 const f3 dRGB = {sm[PB_DCOL + tid * 3], sm[PB_DCOL + tid * 3 + 1], sm[PB_DCOL + tid * 3 + 2]};
                 const float *cp = a.v.campos;
-                sh_backward_inplace(a.v.D, M, row, {mx - cp[0], my - cp[1], mz - cp[2]}, dRGB, dmean);
+                sh_backward_inplace(a.v.D, M, RAW ? sm + PB_SHDC + tid * 3 : row, RAW ? row : row + 3,
+                                    {mx - cp[0], my - cp[1], mz - cp[2]}, dRGB, dmean);
             }
             o_m3d[0] = dmean.x;
             o_m3d[1] = dmean.y;
@@ -707,6 +743,15 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
                        4 * y * (dMt[2][2] + dMt[0][0]);
                 dq.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) -
                        4 * z * (dMt[1][1] + dMt[0][0]);
+                if (RAW) {
+                    // chain rule of the activations: exp -> x s;  normalize -> (g - q <q, g>) / |q_raw|
+                    o_scl[0] *= sc0;
+                    o_scl[1] *= sc1;
+                    o_scl[2] *= sc2;
+                    const float qd = q.x * dq.x + q.y * dq.y + q.z * dq.z + q.w * dq.w, inv = __fdiv_rn(1.0f, q_len);
+                    dq = make_float4((dq.x - q.x * qd) * inv, (dq.y - q.y * qd) * inv, (dq.z - q.z * qd) * inv,
+                                     (dq.w - q.w * qd) * inv);
+                }
                 o_rot[0] = dq.x;
                 o_rot[1] = dq.y;
                 o_rot[2] = dq.z;
@@ -748,7 +793,19 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             pb_flush(a.drots + (size_t)base * 4, sm + PB_O_ROT, n * 4);
         }
     }
-    if (a.dsh && M > 0) {
+    if (RAW && a.dsh && M > 0) {
+        // the gradient blocks of a CTA are contiguous in both arrays: two bulk stores (or two plain loops)
+        if (out_bulk) {
+            if (tid == 0) {
+                bulk_s2g(a.dsh + (size_t)base * 3, sm + PB_SHDC, PB_T * 12);
+                if (M > 1) bulk_s2g(a.dsh_rest + (size_t)base * row_f, sm + PB_SH, PB_T * (uint32_t)row_f * 4);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            pb_flush(a.dsh + (size_t)base * 3, sm + PB_SHDC, n * 3);
+            pb_flush(a.dsh_rest + (size_t)base * row_f, sm + PB_SH, n * row_f);
+        }
+    } else if (a.dsh && M > 0) {
         float *dst = a.dsh + (size_t)base * row_f;
         if (a.shs) {
             if (a.sh_vec) {
@@ -912,7 +969,9 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
                                           (int)BWD_SMEM_BYTES));
             SGR_CUDA(cudaFuncSetAttribute(blend_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)BWD_SMEM_BYTES));
-            SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+            SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           200 * 1024));
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
@@ -966,17 +1025,27 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     a.dscales = dL_dscales;
     a.drots = dL_drotations;
     a.rec11 = rec11;
+    const bool raw = g->activations != 0;
+    a.sh_rest = g->sh_rest;
+    a.rec = geom.rec;
+    a.dsh_rest = plan ? plan->dL_dsh_rest : nullptr;
+    if (raw && g->shs && dL_dsh && g->M > 1 && !a.dsh_rest) {
+        set_error("raw-parameter mode needs SgrBackwardPlan.dL_dsh_rest");
+        return SGR_EINVAL;
+    }
     auto al16 = [](const void *p) { return ((uintptr_t)p & 15u) == 0; };
     a.in_bulk_ok = al16(gacc) && al16(dL_dcolors) && al16(g->means3D) && (!g->scales || al16(g->scales)) &&
-                   (!g->rotations || al16(g->rotations)) && (!g->cov3D_precomp || al16(g->cov3D_precomp));
+                   (!g->rotations || al16(g->rotations)) && (!g->cov3D_precomp || al16(g->cov3D_precomp)) &&
+                   (!raw || !g->shs || (al16(g->shs) && (g->M == 1 || al16(g->sh_rest))));
     a.out_bulk_ok = al16(dL_dmeans2D) && al16(dL_dcov3D) &&
                     (rec11 ? al16(rec11) : (al16(dL_dopacity) && al16(dL_dmeans3D) && al16(dL_dscales) && al16(dL_drotations)));
+    if (raw && g->shs && dL_dsh) a.out_bulk_ok = a.out_bulk_ok && al16(dL_dsh) && (g->M == 1 || al16(a.dsh_rest));
 #ifdef SGR_PB_NO_BULK_STORE
     a.out_bulk_ok = 0;
 #endif
     a.sh_stride = 0;
     a.sh_vec = 0;
-    if (g->shs) {
+    if (g->shs && !raw) {
         const int row_f = g->M * 3;
         if ((row_f % 4) == 0 && al16(g->shs) && al16(dL_dsh)) {
             int s4 = row_f / 4;
@@ -987,7 +1056,7 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
             a.sh_stride = (row_f & 1) ? row_f : row_f + 1;
         }
     }
-    const size_t dyn = (size_t)(PB_SH + PB_T * a.sh_stride) * sizeof(float);
+    const size_t dyn = (size_t)(PB_SH + PB_T * (raw ? (g->M > 0 ? (g->M - 1) * 3 : 0) : a.sh_stride)) * sizeof(float) + 16;
     // the per-Gaussian pass, in `num_chunks` Gaussian ranges (multiples of the CTA size) so that a caller
     // can start reducing a finished range while the next one is computed
     int nchunks = plan && plan->num_chunks > 1 ? plan->num_chunks : 1;
@@ -997,7 +1066,10 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
         const int b0 = (int)((int64_t)blocks * c / nchunks), b1 = (int)((int64_t)blocks * (c + 1) / nchunks);
         a.p0 = b0 * PB_T;
         a.p1 = min(P, b1 * PB_T);
-        if (b1 > b0) SGR_LAUNCH(K_PRE_BWD, st, preprocess_backward_kernel<<<b1 - b0, PB_T, dyn, st>>>(a));
+        if (b1 > b0)
+            SGR_LAUNCH(K_PRE_BWD, st,
+                       if (raw) preprocess_backward_kernel<true><<<b1 - b0, PB_T, dyn, st>>>(a);
+                       else preprocess_backward_kernel<false><<<b1 - b0, PB_T, dyn, st>>>(a));
         if (hook) hook(hook_ctx, SGR_STAGE_CHUNK_DONE + c);
     }
     SGR_CUDA(cudaGetLastError());

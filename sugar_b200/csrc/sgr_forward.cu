@@ -36,6 +36,9 @@ constexpr int PRE_T = SGR_PRE_T;
 struct PreArgs {
     int P;
     const float *means, *scales, *rots, *opac, *shs, *colors, *cov_pre;
+    // raw-parameter mode (SgrGaussians.activations != 0): opac = logits, scales = logs, rots un-normalised, the SH
+    // coefficients in the model's own two arrays: shs = the DC term [P,1,3], sh_rest = the others [P,M-1,3]
+    const float *sh_rest;
     ViewConsts v;
     int bulk_ok;      // all staged arrays 16B-aligned
     int sh_stride;    // padded smem row stride in floats (0 = no SH)
@@ -54,9 +57,11 @@ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 #define SH_C1 0.4886025119029199f
 
 // SH -> RGB for one channel (forward.cu:20-71), operation order as compiled for the reference.
-__device__ __forceinline__ float sh_channel(int deg, const float *sh /* stride 3 */, float x, float y, float z)
+// `dc` points at coefficient 0 of the channel, `rest` at coefficient 1 (stride 3 floats); for one combined row
+// [M][3] rest = dc + 3, in raw-parameter mode they live in two arrays.
+__device__ __forceinline__ float sh_channel(int deg, const float *dc, const float *rest, float x, float y, float z)
 {
-#define SHK(k) sh[(k) * 3]
+#define SHK(k) ((k) == 0 ? dc[0] : rest[((k) - 1) * 3])
     float res = __fmul_rn(SH_C0, SHK(0));
     if (deg > 0) {
         res = __fmaf_rn(-__fmul_rn(y, SH_C1), SHK(1), res);
@@ -95,6 +100,12 @@ __device__ __forceinline__ void stage_plain(float *dst, const float *__restrict_
     for (int i = threadIdx.x; i < n; i += PRE_T) dst[i] = __ldg(src + i);
 }
 
+// RAW: SuGaR's activations (sugar_model.py:400-479: sigmoid of the densities, exp of the scales, normalize of
+// the quaternions) are applied to the staged values here and the SH coefficients come from the model's own
+// (dc, rest) arrays, so a training step needs no elementwise prologue kernels in front of the op.  The rest block
+// of a CTA is one contiguous run -> a single bulk copy into rows of M-1 coefficients (stride 3(M-1) floats: odd
+// for M = 16, conflict-free).
+template <bool RAW>
 __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
 {
     extern __shared__ __align__(16) float s_sh[];  // PRE_T rows x sh_stride floats (only with SH)
@@ -121,7 +132,13 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
             if (a.scales) bytes += PRE_T * 12 + PRE_T * 16;
             if (a.cov_pre) bytes += PRE_T * 24;
             if (a.colors) bytes += PRE_T * 12;
+            if (RAW && a.shs) bytes += PRE_T * 12 + PRE_T * (uint32_t)(a.v.M - 1) * 12;
             mbar_expect_tx(&s_bar, bytes);
+            if (RAW && a.shs) {
+                bulk_g2s(s_col, a.shs + (size_t)base * 3, PRE_T * 12, &s_bar);  // DC terms (colours are absent with SH)
+                if (a.v.M > 1)
+                    bulk_g2s(s_sh, a.sh_rest + (size_t)base * (a.v.M - 1) * 3, PRE_T * (uint32_t)(a.v.M - 1) * 12, &s_bar);
+            }
             bulk_g2s(s_means, a.means + (size_t)base * 3, PRE_T * 12, &s_bar);
             bulk_g2s(s_opac, a.opac + base, PRE_T * 4, &s_bar);
             if (a.scales) {
@@ -140,10 +157,14 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
         }
         if (a.cov_pre) stage_plain(s_cov, a.cov_pre + (size_t)base * 6, n * 6);
         if (a.colors) stage_plain(s_col, a.colors + (size_t)base * 3, n * 3);
+        if (RAW && a.shs) {
+            stage_plain(s_col, a.shs + (size_t)base * 3, n * 3);
+            stage_plain(s_sh, a.sh_rest + (size_t)base * (a.v.M - 1) * 3, n * (a.v.M - 1) * 3);
+        }
     }
     // ---- SH rows: coalesced cp.async into bank-conflict-free padded rows -----------------------
     // (sh_stride == 0 selects the direct path: each surviving thread reads its own row from global)
-    if (a.shs && a.sh_stride) {
+    if (!RAW && a.shs && a.sh_stride) {
         const int row_f = a.v.M * 3;
         const float *src = a.shs + (size_t)base * row_f;
         if (a.sh_vec) {
@@ -194,8 +215,14 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
 #pragma unroll
                 for (int k = 0; k < 6; k++) c3[k] = s_cov[tid * 6 + k];
             } else {
-                cov3d_from_scale_rot(s_scales[tid * 3], s_scales[tid * 3 + 1], s_scales[tid * 3 + 2], a.v.scale_modifier,
-                                     s_rots[tid], c3);
+                float s0 = s_scales[tid * 3], s1 = s_scales[tid * 3 + 1], s2 = s_scales[tid * 3 + 2];
+                float4 q = s_rots[tid];
+                if (RAW) {  // scale_activation = exp, quaternions = F.normalize(_quaternions) (sugar_model.py:417,479)
+                    s0 = expf(s0), s1 = expf(s1), s2 = expf(s2);
+                    const float inv = __fdiv_rn(1.0f, fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f));
+                    q = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+                }
+                cov3d_from_scale_rot(s0, s1, s2, a.v.scale_modifier, q, c3);
             }
             const float tx0 = xf_row(vm, 0, mx, my, mz), ty0 = xf_row(vm, 1, mx, my, mz);
             const Cov2D cv = cov2d_project(tx0, ty0, depth, a.v.focal_x, a.v.focal_y, a.v.tanfovx, a.v.tanfovy, c3, vm);
@@ -214,10 +241,11 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
                 tile_rect(px, py, radius, a.v.gx, a.v.gy, x0, y0, x1, y1);
                 visible = (x1 - x0) * (y1 - y0) != 0;
                 opacity = s_opac[tid];
+                if (RAW) opacity = __fdiv_rn(1.0f, 1.0f + expf(-opacity));  // strengths = sigmoid(all_densities) (:403)
             }
         }
     }
-    if (a.shs && a.sh_stride) {
+    if (!RAW && a.shs && a.sh_stride) {
         cp_async_wait<0>();
         __syncthreads();
     }
@@ -232,10 +260,17 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
                 const float dx = __fsub_rn(mx, cp[0]), dy = __fsub_rn(my, cp[1]), dz = __fsub_rn(mz, cp[2]);
                 const float len = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
                 const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
-                const float *row = a.sh_stride ? s_sh + tid * a.sh_stride : a.shs + (size_t)idx * a.v.M * 3;
-                r = sh_channel(a.v.D, row + 0, x, y, z);
-                g = sh_channel(a.v.D, row + 1, x, y, z);
-                b = sh_channel(a.v.D, row + 2, x, y, z);
+                const float *dc, *rest;
+                if (RAW) {
+                    dc = s_col + tid * 3;
+                    rest = s_sh + tid * (a.v.M - 1) * 3;
+                } else {
+                    dc = a.sh_stride ? s_sh + tid * a.sh_stride : a.shs + (size_t)idx * a.v.M * 3;
+                    rest = dc + 3;
+                }
+                r = sh_channel(a.v.D, dc + 0, rest + 0, x, y, z);
+                g = sh_channel(a.v.D, dc + 1, rest + 1, x, y, z);
+                b = sh_channel(a.v.D, dc + 2, rest + 2, x, y, z);
                 // clamped <=> result + 0.5 < 0 (forward.cu:63-70)
                 clamp_bits = (r < -0.5f ? 1u : 0u) | (g < -0.5f ? 2u : 0u) | (b < -0.5f ? 4u : 0u);
                 r = (clamp_bits & 1u) ? 0.0f : __fadd_rn(r, 0.5f);
@@ -1051,7 +1086,8 @@ static int acquire_slot(DevicePool *pool, CallSlot *slot)
 {
     std::lock_guard<std::mutex> lock(pool->mu);
     if (!pool->attrs_set) {
-        SGR_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SGR_CUDA(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SGR_CUDA(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SGR_CUDA(cudaFuncSetAttribute(tile_sort_merge_kernel<8192, 2048>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
         pool->attrs_set = true;
@@ -1166,16 +1202,21 @@ int launch_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc geom_all
     a.rots = g->rotations;
     a.opac = g->opacities;
     a.shs = g->shs;
+    a.sh_rest = g->sh_rest;
+    const bool raw = g->activations != 0;
     a.colors = g->colors_precomp;
     a.cov_pre = g->cov3D_precomp;
     a.v = v;
     a.bulk_ok = aligned16(g->means3D) && aligned16(g->opacities) && (!g->scales || aligned16(g->scales)) &&
                 (!g->rotations || aligned16(g->rotations)) && (!g->cov3D_precomp || aligned16(g->cov3D_precomp)) &&
-                (!g->colors_precomp || aligned16(g->colors_precomp));
+                (!g->colors_precomp || aligned16(g->colors_precomp)) &&
+                (!raw || !g->shs || (aligned16(g->shs) && (g->M == 1 || aligned16(g->sh_rest))));
     a.sh_stride = 0;
     a.sh_vec = 0;
     size_t dyn = 0;
-    if (g->shs) {
+    if (g->shs && raw) {
+        dyn = (size_t)PRE_T * (g->M - 1) * 3 * sizeof(float) + 16;  // rows of the `rest` block, unpadded
+    } else if (g->shs) {
         const int row_f = g->M * 3;
         if ((row_f % 4) == 0 && aligned16(g->shs)) {
             int s4 = row_f / 4;
@@ -1195,7 +1236,9 @@ int launch_forward(const SgrView *view, const SgrGaussians *g, SgrAlloc geom_all
     a.geom = geom;
     a.radii = radii;
     a.tile_count = img.tile_count;
-    SGR_LAUNCH(K_PREPROCESS, st, preprocess_kernel<<<(P + PRE_T - 1) / PRE_T, PRE_T, dyn, st>>>(a));
+    SGR_LAUNCH(K_PREPROCESS, st,
+               if (raw) preprocess_kernel<true><<<(P + PRE_T - 1) / PRE_T, PRE_T, dyn, st>>>(a);
+               else preprocess_kernel<false><<<(P + PRE_T - 1) / PRE_T, PRE_T, dyn, st>>>(a));
     SGR_LAUNCH(K_TILE_SCAN, st,
                tile_scan_kernel<<<1, 1024, 0, st>>>(img.tile_count, img.tile_start, img.tile_cursor, img.tile_order,
                                                     img.counters, T, nullptr));

@@ -144,11 +144,30 @@ def better_normal_loss(x, gaussian_idx, closest_gaussians_idx, points, scaling, 
 
 def field_values(x, closest_gaussians_idx, points, scaling, quaternions, strengths, density_factor=1.,
                  density_threshold=1., opacity_min_clamp=1e-16, return_sdf=True,
-                 return_closest_gaussian_opacities=False, return_beta=False):
-    """SuGaR.get_field_values for explicit neighbour indices (closest_gaussians_idx = knn_idx[gaussian_idx])."""
+                 return_closest_gaussian_opacities=False, return_beta=False, return_sdf_grad=False,
+                 sdf_grad_max_value=10., beta_mode="average"):
+    """SuGaR.get_field_values for explicit neighbour indices (closest_gaussians_idx = knn_idx[gaussian_idx]).
+
+    beta_mode: only 'average' (the mean of the neighbours' smallest scales, sugar_model.py:1192-1195) -- the one
+    mode every trainer and extractor of the reference constructs its model with; 'learnable' / 'weighted_average'
+    raise.  `return_sdf_grad` adds fields['sdf_grad'] (:1307-1314) as a VALUE (detached, clamped to
+    +-sdf_grad_max_value): it is beta / (rho sqrt(-2 ln rho)) times minus the density's spatial gradient, which the
+    fused backward kernel delivers; no caller of the reference differentiates through it."""
+    if beta_mode != "average":
+        raise NotImplementedError(f"beta_mode={beta_mode!r}: only 'average' is implemented (sugar_model.py:1192-1195)")
     density, nbr, beta, sdf = _Field.apply(x, closest_gaussians_idx, points, scaling, quaternions, strengths,
                                            density_factor, density_threshold, opacity_min_clamp, 1, 7)
     fields = {"density": density}
+    if return_sdf_grad:
+        with torch.enable_grad():
+            xg = x.detach().clone().requires_grad_(True)
+            d = _Field.apply(xg, closest_gaussians_idx, points.detach(), scaling.detach(), quaternions.detach(),
+                             strengths.detach(), density_factor, density_threshold, opacity_min_clamp, 1, 0)[0]
+            (gx,) = torch.autograd.grad(d.sum(), xg)      # d rho / d x = -sum_k o_k Sigma_k^-1 (x - mu_k)
+        with torch.no_grad():
+            rho = torch.where(d >= 1.0, d / (d + 1e-12), d).clamp(min=opacity_min_clamp)   # :1280-1281, :1296
+            coef = beta.detach() / (rho * torch.sqrt(-2.0 * torch.log(rho))).clamp(min=opacity_min_clamp)
+            fields["sdf_grad"] = (coef[:, None] * (-gx)).clamp(min=-sdf_grad_max_value, max=sdf_grad_max_value)
     if return_closest_gaussian_opacities:
         fields["closest_gaussian_opacities"] = nbr
     if return_beta:

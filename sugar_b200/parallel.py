@@ -153,7 +153,7 @@ class ViewParallel:
                 failure.append(e)
 
         cb = stage_hook_type(on_stage)
-        plan = plan_type(cb, None, nchunks, bufs["records"].data_ptr())
+        plan = plan_type(cb, None, nchunks, bufs["records"].data_ptr(), None)
         check(lib.sgr_rasterize_backward_staged(*args, C.byref(plan)))
         if failure:
             raise failure[0]

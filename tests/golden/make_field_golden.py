@@ -68,12 +68,14 @@ def main():
         fields = SuGaR.get_field_values(Fake(), leaf["x"], closest_gaussians_idx=nbr, return_sdf=True,
                                         density_threshold=case["density_threshold"],
                                         density_factor=case["density_factor"], return_closest_gaussian_opacities=True,
-                                        return_beta=True)
+                                        return_beta=True, return_sdf_grad=True, sdf_grad_max_value=10.)
+        sdf_grad = fields.pop("sdf_grad").detach()   # a value-only extra: not part of the scalar loss below
         g = torch.Generator().manual_seed(99)
         w = {k: torch.randn(fields[k].shape, generator=g) for k in ("density", "sdf", "beta", "closest_gaussian_opacities")}
         loss = sum((fields[k] * w[k]).sum() for k in w)
         loss.backward()
         out = {k: v.detach().numpy() for k, v in fields.items()}
+        out["sdf_grad"] = sdf_grad.numpy()
         out.update({"w_" + k: v.numpy() for k, v in w.items()})
         out.update({"grad_" + k: v.grad.numpy() for k, v in leaf.items()})
         np.savez_compressed(os.path.join(HERE, f"field_{name}.npz"), **out)

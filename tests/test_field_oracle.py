@@ -100,3 +100,15 @@ def test_levelset_oracle_matches_reference_code(name):
         assert np.array_equal(t("gaussian_idx")[o["valid"]].numpy(), gold[f"gaussian_idx_{lv}"])
         assert np.allclose(o["intersection_points"].numpy(), gold[f"points_{lv}"], rtol=1e-5, atol=1e-6)
         assert np.allclose(o["normals"].numpy(), gold[f"normals_{lv}"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["c1_1k_2k", "k8"])
+def test_sdf_grad_matches_reference_code(name):
+    """return_sdf_grad (sugar_model.py:1307-1314), a value the reference never differentiates through."""
+    cfg = CASES[name]
+    gold = np.load(os.path.join(HERE, "golden", f"field_{name}.npz"))
+    case = fo.make_case(density_threshold=1.0, **cfg)
+    t = lambda k: torch.from_numpy(case[k])
+    out = fo.field_values_torch(t("x"), t("nbr_idx"), t("points"), t("scaling"), t("quaternions"), t("strengths"),
+                                case["density_factor"], case["density_threshold"], return_sdf_grad=True)
+    assert np.allclose(out["sdf_grad"].numpy(), gold["sdf_grad"], rtol=1e-5, atol=1e-6)

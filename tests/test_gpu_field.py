@@ -119,3 +119,23 @@ def test_normal_loss_matches_oracle(P, N, K):
     # reference itself is only this close to the exact value, so allow 3x its own rounding noise
     assert h.rel_err(loss, l64) < max(2e-5, 3 * h.rel_err(l32, l64))
     assert h.rel_err(gq, g64) < max(1e-4, 3 * h.rel_err(g32, g64))
+
+
+@pytest.mark.parametrize("name", ["c1_1k_2k", "k8"])
+def test_sdf_grad_and_unsupported_modes(name):
+    """fields['sdf_grad'] (sugar_model.py:1307-1314) from the fused backward kernel vs the reference's value;
+    the beta modes no reference caller uses raise instead of silently returning 'average'."""
+    from make_field_golden import CASES
+    from oracle import field_oracle as fo
+    from sugar_b200 import field
+    gold = np.load(os.path.join(HERE, "golden", f"field_{name}.npz"))
+    case = fo.make_case(density_threshold=1.0, **CASES[name])
+    t = lambda k: torch.from_numpy(case[k]).cuda()
+    args = (t("x"), t("nbr_idx"), t("points"), t("scaling"), t("quaternions"), t("strengths"))
+    out = field.field_values(*args, density_factor=case["density_factor"], density_threshold=1.0, return_sdf_grad=True)
+    assert not out["sdf_grad"].requires_grad
+    assert h.rel_err(out["sdf_grad"].cpu().numpy(), gold["sdf_grad"]) < 1e-4
+    assert h.rel_err(out["sdf"].cpu().numpy(), gold["sdf"]) < 2e-5
+    for mode in ("learnable", "weighted_average"):
+        with pytest.raises(NotImplementedError):
+            field.field_values(*args, beta_mode=mode)

@@ -69,3 +69,30 @@ def test_levelset_matches_oracle_large():
     for lv in levels:
         r = ref[lv]
         _compare(ours[lv], r["valid"].numpy(), r["intersection_points"].numpy(), r["normals"].numpy(), 30000)
+
+
+def test_level_surface_points_from_camera_finds_a_rendered_sheet():
+    """The per-view call with the Gaussian-depth front half (sugar_model.py:1898-1962): a dense sheet of flat,
+    opaque Gaussians on the plane z = 5 in front of an identity camera must give level points on that plane,
+    with normals along the view axis, for (nearly) every covered pixel."""
+    from sugar_b200 import levelset, scenes, steps
+    W, H, P = 160, 96, 60_000
+    sc = scenes.make_scene(1000, W, H, seed=0)           # camera only (identity pose)
+    g = torch.Generator().manual_seed(0)
+    xy = (torch.rand(P, 2, generator=g) - 0.5) * torch.tensor([2 * 5 * sc.tanfovx, 2 * 5 * sc.tanfovy]) * 1.1
+    pts = torch.cat([xy, torch.full((P, 1), 5.0)], 1).cuda()
+    scaling = torch.tensor([0.06, 0.06, 0.004]).repeat(P, 1).cuda()     # flat along z
+    quats = torch.tensor([1.0, 0.0, 0.0, 0.0]).repeat(P, 1).cuda()
+    strengths = torch.full((P,), 0.95).cuda()
+    cam = steps.camera_from_scene(sc, "cuda")
+    out = levelset.level_surface_points_from_camera(pts, scaling, quats, strengths, cam, surface_levels=(0.3,),
+                                                    return_normals=True, return_pixel_idx=True)[0.3]
+    n_valid = int(out["valid"].sum())
+    assert n_valid > 0.8 * W * H and out["pixel_idx"].numel() == n_valid
+    z = out["intersection_points"][:, 2]
+    assert float((z - 5.0).abs().quantile(0.99)) < 0.02 and float(z.mean()) < 5.0     # in front of the sheet
+    assert float(out["normals"][:, 2].abs().quantile(0.05)) > 0.95
+    # subsampling keeps the request
+    sub = levelset.level_surface_points_from_camera(pts, scaling, quats, strengths, cam, surface_levels=(0.3,),
+                                                    n_surface_points=1000)[0.3]
+    assert sub["valid"].numel() == 1000

@@ -34,3 +34,20 @@ def test_camera_matrices_match_reference_construction():
         assert np.allclose(wv.numpy(), rwv, atol=1e-5)
         assert np.allclose(fp.numpy(), rfp, atol=1e-4)
         assert np.allclose(cc.numpy(), rcc, atol=1e-6)
+
+
+def test_wrapper_mirror_matches_the_reference_wrapper_golden():
+    """tests/golden/render_wrapper.npz holds what the reference's own render_image_gaussian_rasterizer handed to
+    the rasterizer (make_render_golden.py); the mirror must build the same matrices, camera centre and colours."""
+    import os
+    from sugar_b200 import render
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_wrapper.npz"))
+    wv, fp, cc = render.camera_matrices(torch.from_numpy(g["c2w"]), float(g["fov"][0]), float(g["fov"][1]),
+                                        principal_point=(float(g["pp"][0]), float(g["pp"][1])))
+    assert np.allclose(wv.numpy(), g["viewmatrix"], atol=2e-6)
+    assert np.allclose(fp.numpy(), g["projmatrix"], atol=2e-5)
+    assert np.allclose(cc.numpy(), g["campos"].reshape(3), atol=1e-6)
+    assert abs(math.tan(g["fov"][0] / 2) - g["tanfov"][0]) < 1e-7
+    cols = render.points_rgb(torch.from_numpy(g["points"]), torch.from_numpy(g["sh"]), cc, int(g["sh_degree"]) + 1)
+    assert np.abs(cols.numpy() - g["colors_precomp"]).max() <= 2e-6
+    assert np.array_equal(g["means3D"], g["points"]) and np.array_equal(g["opacities"], g["strengths"])
