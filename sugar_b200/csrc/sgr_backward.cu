@@ -19,7 +19,10 @@
 
 namespace sgr {
 
-constexpr int BWD_B = 128;  // Gaussians per shared-memory batch
+#ifndef SGR_BWD_B
+#define SGR_BWD_B 128
+#endif
+constexpr int BWD_B = SGR_BWD_B;  // Gaussians per shared-memory batch (loader threads: the first BWD_B of the CTA)
 constexpr int BWD_NW = 8;   // warps per CTA (16x16 pixels)
 
 // Blend accumulators (zeroed by a memset before the blend pass):
@@ -506,15 +509,15 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             mbar_fence_init();
             uint32_t bytes = PB_T * 32 + PB_T * 12;
             if (a.shs) bytes += PB_T * 12;  // dL/dRGB is only an input of the SH backward
+            if (RAW && a.shs) bytes += PB_T * 12 + PB_T * (uint32_t)(a.v.M - 1) * 12;
+            if (a.scales) bytes += PB_T * 12 + PB_T * 16;
+            if (a.cov_pre) bytes += PB_T * 24;
+            mbar_expect_tx(&s_bar, bytes);
             if (RAW && a.shs) {
-                bytes += PB_T * 12 + PB_T * (uint32_t)(a.v.M - 1) * 12;
                 bulk_g2s(sm + PB_SHDC, a.shs + (size_t)base * 3, PB_T * 12, &s_bar);
                 if (a.v.M > 1)
                     bulk_g2s(sm + PB_SH, a.sh_rest + (size_t)base * (a.v.M - 1) * 3, PB_T * (uint32_t)(a.v.M - 1) * 12, &s_bar);
             }
-            if (a.scales) bytes += PB_T * 12 + PB_T * 16;
-            if (a.cov_pre) bytes += PB_T * 24;
-            mbar_expect_tx(&s_bar, bytes);
             bulk_g2s(sm + PB_GACC, a.gacc + (size_t)base * 8, PB_T * 32, &s_bar);
             if (a.shs) bulk_g2s(sm + PB_DCOL, a.dcol + (size_t)base * 3, PB_T * 12, &s_bar);
             bulk_g2s(sm + PB_MEANS, a.means + (size_t)base * 3, PB_T * 12, &s_bar);
@@ -547,8 +550,9 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             int r = tid / row_v, c = tid - r * row_v;
             const int dr = PB_T / row_v, dc = PB_T - dr * row_v;
             for (int k = tid; k < total; k += PB_T) {
-                // rows of culled Gaussians are never read (their dL_dsh rows are written as zeros below)
-                if (__ldg(a.radii + base + r) > 0) cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)k * 4);
+                // (skipping the rows of culled Gaussians saves 8 % of this kernel's DRAM bytes but the per-chunk
+                // radius test costs more than that: 0.384 vs 0.333 ms at the headline size, round 2)
+                cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)k * 4);
                 r += dr;
                 c += dc;
                 if (c >= row_v) {

@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
     }
     // ---- SH rows: coalesced cp.async into bank-conflict-free padded rows -----------------------
     // (sh_stride == 0 selects the direct path: each surviving thread reads its own row from global)
-    if (!RAW && a.shs && a.sh_stride) {
+    // SGR_PRE_LATE_SH (A/B knob): issue the row copies only after the cull, for the surviving rows; saves the
+    // bytes of culled Gaussians' coefficients at the price of exposing the copy latency behind the geometry phase.
+    auto stage_sh_rows = [&](const unsigned char *row_live) {
         const int row_f = a.v.M * 3;
         const float *src = a.shs + (size_t)base * row_f;
         if (a.sh_vec) {
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
             int r = tid / row_v, c = tid - r * row_v;  // (row, 16-byte column) advanced without divisions
             const int dr = PRE_T / row_v, dc = PRE_T - dr * row_v;
             for (int i = tid; i < total; i += PRE_T) {
-                cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)i * 4);
+                if (!row_live || row_live[r]) cp_async16(s_sh + r * a.sh_stride + c * 4, src + (size_t)i * 4);
                 r += dr;
                 c += dc;
                 if (c >= row_v) {
@@ -184,11 +186,16 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
             const int total = n * row_f;
             for (int i = tid; i < total; i += PRE_T) {
                 const int r = i / row_f, c = i - r * row_f;
-                cp_async4(s_sh + r * a.sh_stride + c, src + i);
+                if (!row_live || row_live[r]) cp_async4(s_sh + r * a.sh_stride + c, src + i);
             }
         }
         cp_async_commit();
-    }
+    };
+#ifndef SGR_PRE_LATE_SH
+#define SGR_PRE_LATE_SH 0
+#endif
+    __shared__ unsigned char s_live[PRE_T];
+    if (!SGR_PRE_LATE_SH && !RAW && a.shs && a.sh_stride) stage_sh_rows(nullptr);
     __syncthreads();  // barrier init visible / plain staging complete
     if (a.bulk_ok && full) mbar_wait(&s_bar, 0);
 
@@ -246,6 +253,11 @@ __global__ void __launch_bounds__(PRE_T) preprocess_kernel(const PreArgs a)
         }
     }
     if (!RAW && a.shs && a.sh_stride) {
+        if (SGR_PRE_LATE_SH) {
+            s_live[tid] = visible ? 1 : 0;
+            __syncthreads();
+            stage_sh_rows(s_live);
+        }
         cp_async_wait<0>();
         __syncthreads();
     }

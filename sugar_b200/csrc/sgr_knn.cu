@@ -7,11 +7,13 @@
 // distance, int64 indices, a point is its own neighbour 0 when queries == points.  Ties may be
 // returned in a different order than pytorch3d (which does not define one).
 //
-// Method: counting sort of the reference points into an N^3 grid over their bounding box
-// (anisotropic cells), then one thread per query walks Chebyshev shells of cells around its own
-// cell with a K-entry insertion list in local memory; after shell r every unvisited point is
-// farther than r * min(cell size), which bounds the search exactly.  Everything (bounding box,
-// cell sizes) stays on the device: no host synchronisation.
+// Method: counting sort of the reference points into a grid of CUBIC cells over their bounding box
+// (per-axis cell counts nx x ny x nz <= N^3, the edge chosen on the device so that the cell count
+// approaches the budget: a flat or elongated cloud gets a 2-D / 1-D grid instead of N layers of
+// empty or paper-thin cells), then one thread per query walks Chebyshev shells of cells around its
+// own cell with a K-entry insertion list in local memory; after shell r every unvisited point is
+// farther than r * (cell edge), which bounds the search exactly.  Everything (bounding box, cell
+// size) stays on the device: no host synchronisation.
 #include <math.h>
 
 #include "sgr_internal.cuh"
@@ -20,9 +22,9 @@ namespace sgr {
 
 struct KnnGrid {
     float lo[3];
-    float inv_h[3];  // cells per unit length
-    float h_min;     // smallest cell edge
-    int n;           // cells per axis
+    float inv_h;  // cells per unit length (cubic cells)
+    float h;      // cell edge
+    int n[3];     // cells per axis, n[0] * n[1] * n[2] <= the budget N^3
 };
 
 __device__ __forceinline__ int float_flip(float f)
@@ -32,49 +34,93 @@ __device__ __forceinline__ int float_flip(float f)
 }
 __device__ __forceinline__ float float_unflip(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
+// bb: int[6] flipped min / max per axis, then (8-byte aligned) double[6] sum / sum of squares per axis
 __global__ void knn_bbox_init_kernel(int *bb)
 {
     if (threadIdx.x < 3) bb[threadIdx.x] = 0x7fffffff;
     else if (threadIdx.x < 6) bb[threadIdx.x] = (int)0x80000000;
+    else if (threadIdx.x < 12) ((double *)(bb + 8))[threadIdx.x - 6] = 0.0;
 }
 
 __global__ void __launch_bounds__(256) knn_bbox_kernel(int P, const float *__restrict__ pts, int *bb)
 {
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
     for (int i = blockIdx.x * 256 + threadIdx.x; i < P; i += gridDim.x * 256) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             const float v = pts[3 * i + a];
             mn[a] = fminf(mn[a], v);
             mx[a] = fmaxf(mx[a], v);
+            s1[a] += (double)v;
+            s2[a] += (double)v * (double)v;
         }
     }
+    double *mom = (double *)(bb + 8);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         const int lo = __reduce_min_sync(0xffffffffu, float_flip(mn[a]));
         const int hi = __reduce_max_sync(0xffffffffu, float_flip(mx[a]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1[a] += __shfl_xor_sync(0xffffffffu, s1[a], o);
+            s2[a] += __shfl_xor_sync(0xffffffffu, s2[a], o);
+        }
         if ((threadIdx.x & 31) == 0) {
             atomicMin(&bb[a], lo);
             atomicMax(&bb[3 + a], hi);
+            atomicAdd(&mom[a], s1[a]);
+            atomicAdd(&mom[3 + a], s2[a]);
         }
     }
 }
 
-__global__ void knn_grid_setup_kernel(const int *bb, int n, KnnGrid *g)
+// The grid covers the bounding box clipped to mean +- 4 sigma per axis: a few far outliers (floaters) would
+// otherwise stretch the box and leave the bulk of the cloud in a handful of cells.  Points outside the clipped
+// box are clamped into the border cells, which keeps the shell bound valid (they are only farther away than
+// their cell suggests).
+__global__ void knn_grid_setup_kernel(const int *bb, int n, int P, KnnGrid *g)
 {
     if (threadIdx.x != 0) return;
-    float hmin = 3.0e38f;
+    const double *mom = (const double *)(bb + 8);
+    float ext[3], emax = 0.f;
     for (int a = 0; a < 3; a++) {
-        const float lo = float_unflip(bb[a]), hi = float_unflip(bb[3 + a]);
-        float ext = hi - lo;
-        if (!(ext > 1e-30f)) ext = 1e-30f;  // degenerate axis: one layer of cells
-        const float h = ext / (float)n * 1.0001f;
+        float lo = float_unflip(bb[a]), hi = float_unflip(bb[3 + a]);
+        const double mean = mom[a] / (double)P, var = fmax(mom[3 + a] / (double)P - mean * mean, 0.0);
+        const float sd = (float)sqrt(var), m = (float)mean;
+        if (sd > 0.f) {
+            lo = fmaxf(lo, m - 4.0f * sd);
+            hi = fminf(hi, m + 4.0f * sd);
+        }
+        ext[a] = hi - lo;
+        if (!(ext[a] > 0.f)) ext[a] = 0.f;
+        emax = fmaxf(emax, ext[a]);
         g->lo[a] = lo;
-        g->inv_h[a] = 1.0f / h;
-        hmin = fminf(hmin, h);
     }
-    g->h_min = hmin;
-    g->n = n;
+    if (!(emax > 1e-30f)) emax = 1e-30f;  // all points coincide: one cell
+    // smallest cubic edge whose grid fits the budget of n^3 cells: bisection on the edge length
+    // (cells(h) is monotone; h never drops below longest extent / 8 n)
+    const double budget = (double)n * n * n;
+    auto cells = [&](float h, int *c) {
+        double prod = 1.0;
+        for (int a = 0; a < 3; a++) {
+            const float k = floorf(ext[a] / h) + 1.0f;
+            c[a] = (int)fminf(k, 1.0e6f);
+            prod *= (double)c[a];
+        }
+        return prod;
+    };
+    float h_hi = emax * 1.0001f, h_lo = emax / (8.0f * (float)n);
+    int c[3];
+    for (int it = 0; it < 40; it++) {
+        const float mid = 0.5f * (h_lo + h_hi);
+        if (cells(mid, c) <= budget) h_hi = mid;
+        else h_lo = mid;
+    }
+    cells(h_hi, c);
+    g->h = h_hi;
+    g->inv_h = 1.0f / h_hi;
+    for (int a = 0; a < 3; a++) g->n[a] = c[a];
 }
 
 __device__ __forceinline__ int cell_coord(float v, float lo, float inv_h, int n)
@@ -89,10 +135,10 @@ __global__ void __launch_bounds__(256) knn_count_kernel(int P, const float *__re
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= P) return;
     const KnnGrid g = *gp;
-    const int cx = cell_coord(pts[3 * i], g.lo[0], g.inv_h[0], g.n);
-    const int cy = cell_coord(pts[3 * i + 1], g.lo[1], g.inv_h[1], g.n);
-    const int cz = cell_coord(pts[3 * i + 2], g.lo[2], g.inv_h[2], g.n);
-    const uint32_t c = ((uint32_t)cz * g.n + cy) * g.n + cx;
+    const int cx = cell_coord(pts[3 * i], g.lo[0], g.inv_h, g.n[0]);
+    const int cy = cell_coord(pts[3 * i + 1], g.lo[1], g.inv_h, g.n[1]);
+    const int cz = cell_coord(pts[3 * i + 2], g.lo[2], g.inv_h, g.n[2]);
+    const uint32_t c = ((uint32_t)cz * g.n[1] + cy) * g.n[0] + cx;
     cell_of[i] = c;
     atomicAdd(&counts[c], 1u);
 }
@@ -208,10 +254,12 @@ __global__ void __launch_bounds__(128) knn_query_kernel(int Q, int K, int P, con
     const int q = blockIdx.x * 128 + threadIdx.x;
     if (q >= Q) return;
     const KnnGrid g = *gp;
-    const int n = g.n;
+    const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+    const uint32_t ncell = (uint32_t)nx * ny * nz;
     const float qx = qs[3 * q], qy = qs[3 * q + 1], qz = qs[3 * q + 2];
-    const int cx = cell_coord(qx, g.lo[0], g.inv_h[0], n), cy = cell_coord(qy, g.lo[1], g.inv_h[1], n),
-              cz = cell_coord(qz, g.lo[2], g.inv_h[2], n);
+    const int cx = cell_coord(qx, g.lo[0], g.inv_h, nx), cy = cell_coord(qy, g.lo[1], g.inv_h, ny),
+              cz = cell_coord(qz, g.lo[2], g.inv_h, nz);
+    const int rmax = max(nx, max(ny, nz));
     // a query outside the bounding box is first clamped into the border cell; the shell bound below
     // then needs the distance from the query to that cell, which only makes the bound smaller
     float best_d[KNN_MAXK];
@@ -219,10 +267,10 @@ __global__ void __launch_bounds__(128) knn_query_kernel(int Q, int K, int P, con
     int have = 0;
     float kth = 3.0e38f;
     const uint32_t total = (uint32_t)P;
-    for (int r = 0; r < n; r++) {
-        const int z0 = max(cz - r, 0), z1 = min(cz + r, n - 1);
-        const int y0 = max(cy - r, 0), y1 = min(cy + r, n - 1);
-        const int x0 = max(cx - r, 0), x1 = min(cx + r, n - 1);
+    for (int r = 0; r < rmax; r++) {
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
+        const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, nx - 1);
         for (int z = z0; z <= z1; z++) {
             const bool zface = (z == cz - r) || (z == cz + r);
             for (int y = y0; y <= y1; y++) {
@@ -231,9 +279,9 @@ __global__ void __launch_bounds__(128) knn_query_kernel(int Q, int K, int P, con
                 const int step = (zface || yface || r == 0) ? 1 : max(1, 2 * r);
                 for (int x = cx - r; x <= cx + r; x += step) {
                     if (x < x0 || x > x1) continue;
-                    const uint32_t c = ((uint32_t)z * n + y) * n + x;
+                    const uint32_t c = ((uint32_t)z * ny + y) * nx + x;
                     const uint32_t s = starts[c];
-                    const uint32_t e = (c + 1 < (uint32_t)n * n * n) ? starts[c + 1] : total;
+                    const uint32_t e = (c + 1 < ncell) ? starts[c + 1] : total;
                     for (uint32_t k = s; k < e; k++) {
                         const float4 p = __ldg(sorted + k);
                         const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
@@ -254,9 +302,9 @@ __global__ void __launch_bounds__(128) knn_query_kernel(int Q, int K, int P, con
                 }
             }
         }
-        // every unvisited point lies beyond shell r: farther than r * h_min from the query's cell, hence
+        // every unvisited point lies beyond shell r: farther than r cell edges from the query's cell, hence
         // from the query if it is inside the box; outside the box the query is even farther from them
-        const float bound = (float)r * g.h_min;
+        const float bound = (float)r * g.h;
         if (have == K && kth <= bound * bound) break;
     }
     for (int j = 0; j < K; j++) {
@@ -311,7 +359,7 @@ int sgr_knn(int32_t P, const float *points, int32_t Q, const float *queries, int
     float4 *sorted = (float4 *)p;
     SGR_LAUNCH(K_KNN, st, knn_bbox_init_kernel<<<1, 32, 0, st>>>(bb));
     SGR_LAUNCH(K_KNN, st, knn_bbox_kernel<<<148 * 4, 256, 0, st>>>(P, points, bb));
-    SGR_LAUNCH(K_KNN, st, knn_grid_setup_kernel<<<1, 32, 0, st>>>(bb, n, grid));
+    SGR_LAUNCH(K_KNN, st, knn_grid_setup_kernel<<<1, 32, 0, st>>>(bb, n, P, grid));
     SGR_CUDA(cudaMemsetAsync(cursor, 0, ncell * 4, st));  // cursor doubles as the count array first
     SGR_LAUNCH(K_KNN, st, knn_count_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, points, grid, cell_of, cursor));
     SGR_LAUNCH(K_KNN, st, knn_scan_blocks_kernel<<<(unsigned)nblocks, 1024, 0, st>>>((int)ncell, cursor, starts, bsums));

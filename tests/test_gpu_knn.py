@@ -47,3 +47,30 @@ def test_knn_surface_like_and_degenerate_clouds():
     # heavy duplicates
     dup = torch.randn(50, 3, generator=g).repeat(40, 1)
     _check(dup, dup[:300], 16)
+
+
+def test_knn_planar_and_elongated_clouds_stay_fast():
+    """Cubic cells with per-axis counts: a coplanar cloud (what SuGaR's surface-aligned Gaussians look like) or a
+    cloud stretched along one axis by an outlier must not degrade to a linear scan per query (the shell bound was
+    r * the smallest cell edge, i.e. ~0 on a degenerate axis)."""
+    import time
+    from sugar_b200 import knn
+    g = torch.Generator().manual_seed(9)
+    P = 400_000
+    planar = torch.rand(P, 3, generator=g); planar[:, 2] = 0.25
+    line = torch.rand(P, 3, generator=g) * torch.tensor([1.0, 1e-4, 1e-4])
+    outlier = torch.randn(P, 3, generator=g); outlier[0] = torch.tensor([1e4, 0.0, 0.0])
+    for name, pts in (("planar", planar), ("line", line), ("outlier", outlier)):
+        pts = pts.cuda()
+        knn.reset_neighbors(pts[:1000], 4)      # warm-up (context, allocator)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d2, idx = knn.reset_neighbors(pts, 16)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert dt < 2.0, f"{name}: reset_neighbors took {dt:.2f} s for {P} points"
+        assert bool((idx[:, 0] == torch.arange(P, device="cuda")).all()) or float(d2[:, 0].max()) == 0.0
+        sub = torch.randperm(P, generator=g)[:300]
+        D = torch.cdist(pts[sub].double(), pts.double()) ** 2
+        ref = D.topk(16, dim=1, largest=False).values
+        assert torch.allclose(d2[sub].double(), ref, rtol=1e-4, atol=1e-12), name
