@@ -19,8 +19,13 @@
 
 namespace sgr {
 
+// SGR_BWD_PIPE3 (A/B knob): three record stages of 96 with full / empty mbarriers instead of two of 128 with CTA
+// barriers -- a warp only waits for the loader warps' data, so the tile's warps may drift one batch apart.
+#ifndef SGR_BWD_PIPE3
+#define SGR_BWD_PIPE3 0
+#endif
 #ifndef SGR_BWD_B
-#define SGR_BWD_B 128
+#define SGR_BWD_B (SGR_BWD_PIPE3 ? 96 : 128)
 #endif
 constexpr int BWD_B = SGR_BWD_B;  // Gaussians per shared-memory batch (loader threads: the first BWD_B of the CTA)
 constexpr int BWD_NW = 8;   // warps per CTA (16x16 pixels)
@@ -80,10 +85,25 @@ constexpr int CH_PITCH = CH + 1;   // float2 elements per pixel row: odd pitch =
 // (55.4 KB per CTA in total: four CTAs per SM fit, with 64 registers per thread)
 constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 32, CB_BYTES = CB_DP + 32 * 16;
 // CTA shared-memory map (dynamic): records of two batches, membership words, chunk scratch
-constexpr uint32_t SM_A = 0, SM_B = SM_A + 2 * BWD_B * 16, SM_C = SM_B + 2 * BWD_B * 16,
-                   SM_MEMBER = SM_C + 2 * BWD_B * 16, SM_LAST = SM_MEMBER + BWD_NW * (BWD_B / 32) * 4,
-                   SM_CHUNK = SM_LAST + 16, BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
+constexpr uint32_t BWD_NS = SGR_BWD_PIPE3 ? 3 : 2;  // record stages
+constexpr uint32_t SM_A = 0, SM_B = SM_A + BWD_NS * BWD_B * 16, SM_C = SM_B + BWD_NS * BWD_B * 16,
+                   SM_MEMBER = SM_C + BWD_NS * BWD_B * 16,
+                   SM_BAR = SM_MEMBER + (SGR_BWD_PIPE3 ? BWD_NS : 1) * BWD_NW * (BWD_B / 32) * 4,  // PIPE3: full[3], empty[3]
+                   SM_LAST = SM_BAR + (SGR_BWD_PIPE3 ? 6 * 8 : 0), SM_CHUNK = SM_LAST + 16,
+                   BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
+static_assert(SM_BAR % 8 == 0 && BWD_B % 32 == 0, "mbarriers are 8-byte aligned; a batch is whole membership words");
 static_assert(4 * (BWD_SMEM_BYTES + 1024) <= 228 * 1024, "four CTAs of the backward blend must fit one SM's shared memory");
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrives on `bar` when all cp.async copies this thread has issued so far have landed (does not change the
+// barrier's pending count: the expected count must include it)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -232,6 +252,61 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
         }
         cp_async_commit();
     };
+    // membership words of the batch in stage `st` from the loader threads' masks
+    auto publish_members = [&](uint32_t mask, uint32_t(*set)[BWD_B / 32]) {
+#pragma unroll
+        for (int blk = 0; blk < BWD_NW; blk++) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (mask >> blk) & 1u);
+            if (lane == 0) set[blk][wid] = word;
+        }
+    };
+#if SGR_BWD_PIPE3
+    uint64_t *bars = (uint64_t *)(s_raw + SM_BAR);  // full[0..2] then empty[0..2]
+    if (tid == 0) {
+        for (int st = 0; st < 3; st++) {
+            mbar_init(&bars[st], 2 * BWD_B);      // per loader thread: one async arrive (copies landed) + one plain
+            mbar_init(&bars[3 + st], BWD_NW);     // one arrive per warp when it is done with the stage
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int nb = (n + BWD_B - 1) / BWD_B;
+    // loader warps: fill stage b % 3 with batch b (waits until every warp has released the stage's previous batch)
+    auto produce = [&](int b) {
+        const int st = b % 3;
+        if (b >= 3) mbar_wait(&bars[3 + st], (uint32_t)((b / 3 - 1) & 1));
+        const uint32_t w = fetch(b * BWD_B);
+        uint32_t mask = 0;
+        if (w != 0xffffffffu) {
+            const uint32_t id = packed ? (w >> 8) : w;
+            const float4 *r = rec + (size_t)id * 3;
+            const uint32_t e = st * BWD_B + tid;
+            cp_async16_a(sm + SM_A + e * 16, r);
+            cp_async16_a(sm + SM_B + e * 16, r + 1);
+            cp_async16_a(sm + SM_C + e * 16, r + 2);
+            if (packed) mask = w & 0xffu;
+        }
+        if (!packed) {  // the mask needs the landed record
+            cp_async_commit();
+            cp_async_wait<0>();
+            if (w != 0xffffffffu) {
+                const float4 r0 = lds128(sm + SM_A + (st * BWD_B + tid) * 16), r1 = lds128(sm + SM_B + (st * BWD_B + tid) * 16);
+                mask = block_mask_of_record(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
+            }
+        }
+        cp_async_mbar_arrive_noinc(&bars[st]);
+        publish_members(mask, s_member + st * BWD_NW);
+        mbar_arrive(&bars[st]);
+    };
+    if (loader) produce(0);
+    for (int b = 0; b < nb; b++) {
+        const int b0 = b * BWD_B, buf = b % 3;
+        const uint32_t sa = sm + SM_A + buf * (BWD_B * 16), sb = sm + SM_B + buf * (BWD_B * 16),
+                       sc = sm + SM_C + buf * (BWD_B * 16);
+        if (loader && b + 1 < nb) produce(b + 1);
+        mbar_wait(&bars[buf], (uint32_t)((b / 3) & 1));  // batch b has landed and its membership words are visible
+        const uint32_t(*member)[BWD_B / 32] = s_member + buf * BWD_NW;
+#else
     uint32_t w_cur = fetch(0);
     issue(w_cur, 0);
     uint32_t w_next = fetch(BWD_B);
@@ -251,17 +326,15 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
                     mask = block_mask_of_record(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0);
                 }
             }
-#pragma unroll
-            for (int blk = 0; blk < BWD_NW; blk++) {
-                const uint32_t word = __ballot_sync(0xffffffffu, (mask >> blk) & 1u);
-                if (lane == 0) s_member[blk][wid] = word;
-            }
+            publish_members(mask, s_member);
             // next batch's records start moving now; they are not needed before the next barrier
             issue(w_next, buf ^ 1);
             w_cur = w_next;
             w_next = fetch(b0 + 2 * BWD_B);
         }
         __syncthreads();
+        const uint32_t(*member)[BWD_B / 32] = s_member;
+#endif
         const int m = min(BWD_B, n - b0);
 #ifdef SGR_BLEND_STATS
         if (tid == 0) BWD_STAT(6, m);
@@ -271,7 +344,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
         const int jlim = n - 1 - b0 - last_contributor;
 #pragma unroll 1
         for (int c = 0; c * 32 < m; c++) {
-            uint32_t mw = s_member[wid][c];
+            uint32_t mw = member[wid][c];
             const int cut = jmin - c * 32;
             if (cut >= 32) mw = 0;
             else if (cut > 0) mw &= ~((1u << cut) - 1u);
@@ -348,6 +421,10 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
                 }
             }
         }
+#if SGR_BWD_PIPE3
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[3 + buf]);  // this warp no longer reads the stage
+#endif
     }
     if (nfill) chunk_flush(cb, nfill, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc, dcol);
 }

@@ -29,7 +29,7 @@ namespace sgr {
 // preprocess
 // ------------------------------------------------------------------------------------------------
 #ifndef SGR_PRE_T
-#define SGR_PRE_T 256
+#define SGR_PRE_T 128
 #endif
 constexpr int PRE_T = SGR_PRE_T;
 
