@@ -19,10 +19,16 @@
 
 namespace sgr {
 
-// SGR_BWD_PIPE3 (A/B knob): three record stages of 96 with full / empty mbarriers instead of two of 128 with CTA
-// barriers -- a warp only waits for the loader warps' data, so the tile's warps may drift one batch apart.
+// Record pipeline of the backward blend.  SGR_BWD_PIPE3 = 1 (default): SGR_BWD_NS stages of SGR_BWD_B records with
+// full / empty mbarriers -- a warp waits only for the loader warps' data, never for its sibling warps, so the
+// tile's eight warps may drift NS - 2 batches apart and the statistical imbalance between the blocks of one batch
+// (the busiest block of a 128-record batch does 1.32x the mean) is averaged over more records: 1.029 -> 0.973 ms
+// at the headline size against SGR_BWD_PIPE3 = 0 (two stages of 128 records, two CTA barriers per batch).
 #ifndef SGR_BWD_PIPE3
-#define SGR_BWD_PIPE3 0
+#define SGR_BWD_PIPE3 1
+#endif
+#ifndef SGR_BWD_NS
+#define SGR_BWD_NS 3
 #endif
 #ifndef SGR_BWD_B
 #define SGR_BWD_B (SGR_BWD_PIPE3 ? 96 : 128)
@@ -48,8 +54,9 @@ __device__ __forceinline__ void red_add_v2(float *addr, float a, float b)
 // blend backward.  One CTA per 16x16 tile, one thread per pixel, one warp per 8x4 pixel block (the
 // forward's geometry); the tile's list is walked back to front over its first max(n_contrib)
 // positions only, a batch of BWD_B records at a time, with the footprint masks deciding which warp
-// visits which splat (sgr_internal.cuh).  Splat records are double-buffered: the ids of batch b+2 and
-// the cp.async (LDGSTS) copies of batch b+1 are in flight while batch b is processed.
+// visits which splat (sgr_internal.cuh).  Splat records move through a three-stage cp.async (LDGSTS) pipeline
+// with full / empty mbarriers: the copies of batch b+1 are in flight while batch b is processed, and no warp
+// ever waits for a sibling warp, only for data.
 //
 // Reduction.  The 9 per-pair values are NOT reduced across the warp with shuffles.  Phase 1 (lane =
 // pixel) parks S = dL/dG * G and the colour weight alpha*T of every contributing splat in a per-warp
@@ -82,14 +89,14 @@ constexpr int CH_PITCH = CH + 1;   // float2 elements per pixel row: odd pitch =
 // per-warp chunk scratch (bytes from its base): pair[32][CH_PITCH] float2 | meta[CH] x 32 B | dp[32] float4
 //   meta: (x, y, conic a, conic b) (conic c, opacity, clamp bits, id) -- what phase 2 needs of a parked splat
 //   dp:   (dL/dpixel r g b, -T_final <bg, dL/dpixel>) of the block's pixels
-// (55.4 KB per CTA in total: four CTAs per SM fit, with 64 registers per thread)
+// (57.2 KB per CTA in total with three record stages: four CTAs per SM fit, with 64 registers per thread)
 constexpr uint32_t CB_META = 32 * CH_PITCH * 8, CB_DP = CB_META + CH * 32, CB_BYTES = CB_DP + 32 * 16;
-// CTA shared-memory map (dynamic): records of two batches, membership words, chunk scratch
-constexpr uint32_t BWD_NS = SGR_BWD_PIPE3 ? 3 : 2;  // record stages
+// CTA shared-memory map (dynamic): the record stages, their membership words, the mbarriers, chunk scratch
+constexpr uint32_t BWD_NS = SGR_BWD_PIPE3 ? SGR_BWD_NS : 2;  // record stages
 constexpr uint32_t SM_A = 0, SM_B = SM_A + BWD_NS * BWD_B * 16, SM_C = SM_B + BWD_NS * BWD_B * 16,
                    SM_MEMBER = SM_C + BWD_NS * BWD_B * 16,
                    SM_BAR = SM_MEMBER + (SGR_BWD_PIPE3 ? BWD_NS : 1) * BWD_NW * (BWD_B / 32) * 4,  // PIPE3: full[3], empty[3]
-                   SM_LAST = SM_BAR + (SGR_BWD_PIPE3 ? 6 * 8 : 0), SM_CHUNK = SM_LAST + 16,
+                   SM_LAST = SM_BAR + (SGR_BWD_PIPE3 ? 2 * BWD_NS * 8 : 0), SM_CHUNK = SM_LAST + 16,
                    BWD_SMEM_BYTES = SM_CHUNK + BWD_NW * CB_BYTES;
 static_assert(SM_BAR % 8 == 0 && BWD_B % 32 == 0, "mbarriers are 8-byte aligned; a batch is whole membership words");
 static_assert(4 * (BWD_SMEM_BYTES + 1024) <= 228 * 1024, "four CTAs of the backward blend must fit one SM's shared memory");
@@ -261,20 +268,21 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
         }
     };
 #if SGR_BWD_PIPE3
-    uint64_t *bars = (uint64_t *)(s_raw + SM_BAR);  // full[0..2] then empty[0..2]
+    constexpr int NS = (int)BWD_NS;
+    uint64_t *bars = (uint64_t *)(s_raw + SM_BAR);  // full[0..NS) then empty[0..NS)
     if (tid == 0) {
-        for (int st = 0; st < 3; st++) {
+        for (int st = 0; st < NS; st++) {
             mbar_init(&bars[st], 2 * BWD_B);      // per loader thread: one async arrive (copies landed) + one plain
-            mbar_init(&bars[3 + st], BWD_NW);     // one arrive per warp when it is done with the stage
+            mbar_init(&bars[NS + st], BWD_NW);    // one arrive per warp when it is done with the stage
         }
         mbar_fence_init();
     }
     __syncthreads();
     const int nb = (n + BWD_B - 1) / BWD_B;
-    // loader warps: fill stage b % 3 with batch b (waits until every warp has released the stage's previous batch)
+    // loader warps: fill stage b % NS with batch b (waits until every warp has released the stage's previous batch)
     auto produce = [&](int b) {
-        const int st = b % 3;
-        if (b >= 3) mbar_wait(&bars[3 + st], (uint32_t)((b / 3 - 1) & 1));
+        const int st = b % NS;
+        if (b >= NS) mbar_wait(&bars[NS + st], (uint32_t)((b / NS - 1) & 1));
         const uint32_t w = fetch(b * BWD_B);
         uint32_t mask = 0;
         if (w != 0xffffffffu) {
@@ -300,11 +308,11 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
     };
     if (loader) produce(0);
     for (int b = 0; b < nb; b++) {
-        const int b0 = b * BWD_B, buf = b % 3;
+        const int b0 = b * BWD_B, buf = b % NS;
         const uint32_t sa = sm + SM_A + buf * (BWD_B * 16), sb = sm + SM_B + buf * (BWD_B * 16),
                        sc = sm + SM_C + buf * (BWD_B * 16);
         if (loader && b + 1 < nb) produce(b + 1);
-        mbar_wait(&bars[buf], (uint32_t)((b / 3) & 1));  // batch b has landed and its membership words are visible
+        mbar_wait(&bars[buf], (uint32_t)((b / NS) & 1));  // batch b has landed and its membership words are visible
         const uint32_t(*member)[BWD_B / 32] = s_member + buf * BWD_NW;
 #else
     uint32_t w_cur = fetch(0);
@@ -423,7 +431,7 @@ __global__ void __launch_bounds__(256, 4) blend_backward_kernel(
         }
 #if SGR_BWD_PIPE3
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[3 + buf]);  // this warp no longer reads the stage
+        if (lane == 0) mbar_arrive(&bars[NS + buf]);  // this warp no longer reads the stage
 #endif
     }
     if (nfill) chunk_flush(cb, nfill, blk_x0, blk_y0, 0.5f * W, 0.5f * H, gacc, dcol);
