@@ -156,13 +156,16 @@ SGR_API int sgr_backward_chunk_range(int32_t P, int32_t num_chunks, int32_t chun
 
 /* Epilogue of the view-parallel step for the Gaussians [p0, p1), after the exchange (either half optional):
  *  - dL_dsh[P,M,3] rows = sum over views v of basis_k(normalize(mean - campos[v])) * dRGB[v][P,3]  (the SH part of
- *    backward.cu:20-139 is an outer product per view): campos f32[V,3], dRGB f32[V,P,3] = the gathered factors;
+ *    backward.cu:20-139 is an outer product per view): the gathered factors of view v start at dRGB + v * view_stride
+ *    floats (f32[P,3]; view_stride >= 3P) and its camera position at campos + v * campos_stride floats -- the
+ *    exchange appends every view's camera position to its factor block so that one all-gather carries both;
  *  - reduced_records f32[P,11] (all-reduced) are split into dL_dmeans3D / dL_dopacity / dL_dscales / dL_drotations.
  * Every output row of the range is fully written; `scale` (e.g. 1/num_views) multiplies everything. */
 SGR_API int sgr_view_grad_finalize(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree, int32_t num_views,
-                                   const float *means3D, const float *campos, const float *dRGB, float *dL_dsh,
-                                   const float *reduced_records, float scale, float *dL_dmeans3D, float *dL_dopacity,
-                                   float *dL_dscales, float *dL_drotations, void *stream);
+                                   const float *means3D, const float *campos, const float *dRGB, int64_t view_stride,
+                                   int32_t campos_stride, float *dL_dsh, const float *reduced_records, float scale,
+                                   float *dL_dmeans3D, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
+                                   void *stream);
 /* The SH half alone, over all Gaussians (kept for callers that only exchange factors). */
 SGR_API int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float *means3D,
                                      const float *campos, const float *dRGB, float *dL_dsh, void *stream);

@@ -16,6 +16,8 @@ for n in 2 4 8; do
   [ $n -le $N ] || continue
   run $n bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/${tag}_bench_n${n}.json 2> gpurun_out/${tag}_bench_n${n}.err
 done
+run $N bench.py --gpus $N --steps 20 --warmup 5 --chunks 2 --no-cpu-baseline > gpurun_out/${tag}_bench_n${N}_chunks2.json 2> gpurun_out/${tag}_bench_n${N}_chunks2.err
+run $N bench.py --gpus $N --steps 20 --warmup 5 --chunks 8 --no-cpu-baseline > gpurun_out/${tag}_bench_n${N}_chunks8.json 2> gpurun_out/${tag}_bench_n${N}_chunks8.err
 if [ $N -ge 8 ]; then
   run 8 scripts/check_view_parallel.py > gpurun_out/${tag}_check_n8.json 2> gpurun_out/${tag}_check_n8.err
   run 8 bench.py --gpus 8 --steps 20 --warmup 5 --no-sh-factors > gpurun_out/${tag}_bench_n8_plain.json 2> gpurun_out/${tag}_bench_n8_plain.err

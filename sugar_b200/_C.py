@@ -250,7 +250,9 @@ def _alloc_backward(P: int, M: int, dev, with_records: bool, split_sh: bool = Fa
     offs, o = {}, 0
     for name, w in widths:
         offs[name] = o
-        o = _round_up(o + P * w, _PART_ALIGN)
+        # dL_dcolors is followed by 4 spare floats: the view-parallel exchange appends the camera position there,
+        # so that one all-gather carries a view's SH factors and its camera
+        o = _round_up(o + P * w + (4 if name == "colors" else 0), _PART_ALIGN)
     total = o + n_scratch + 64
     flat = _big_empty(_round_up(4 * total, _ROUND) // 4, torch.float32, dev)
     skew = (-(flat.data_ptr() // 4)) % _PART_ALIGN  # the allocator aligns to 512 B; be explicit anyway
@@ -259,6 +261,7 @@ def _alloc_backward(P: int, M: int, dev, with_records: bool, split_sh: bool = Fa
               "cov3D": (P, 6), "records": (P, 11)}
     bufs = {name: flat[skew + offs[name]:skew + offs[name] + P * w].view(shapes[name]) for name, w in widths}
     bufs["scratch"] = flat[skew + o:skew + o + n_scratch]
+    bufs["colors_block"] = flat[skew + offs["colors"]:skew + offs["colors"] + 3 * P + 4]
     return bufs
 
 

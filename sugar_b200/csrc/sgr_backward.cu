@@ -934,19 +934,112 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
 //    the four gradient arrays autograd expects.
 // Either half is optional.
 // ------------------------------------------------------------------------------------------------
-constexpr int SF_T = 128;
+constexpr int SF_T = 256;  // 64 Gaussians per CTA, four threads each
 
-__global__ void __launch_bounds__(SF_T) view_grad_finalize_kernel(int p0, int p1, int P, int M, int deg, int nviews,
+// Four threads per Gaussian: thread q owns SH coefficients 4q .. 4q+3, i.e. 48 contiguous bytes of the row
+// (three 16-byte stores; the four threads of a Gaussian cover its 192-byte row, a warp 1.5 KB without gaps), and
+// evaluates only those four basis functions per view -- 12 accumulators instead of 48 per thread, no shared-memory
+// transpose, 4x the threads in flight.  Rows with M != 16 use the generic path below (one thread per Gaussian).
+// `view_stride` is the distance in floats between two views' factor blocks (>= 3P: the exchange appends each view's
+// camera position to its block); campos[v] may live there too.
+__global__ void __launch_bounds__(SF_T) view_grad_finalize_m16_kernel(int p0, int p1, int deg, int nviews,
+                                                                       const float *__restrict__ means,
+                                                                       const float *__restrict__ campos, int campos_stride,
+                                                                       const float *__restrict__ dRGB, size_t view_stride,
+                                                                       float *__restrict__ dsh,
+                                                                       const float *__restrict__ rec11, float scale,
+                                                                       float *__restrict__ dmeans3D,
+                                                                       float *__restrict__ dopacity,
+                                                                       float *__restrict__ dscales, float *__restrict__ drots)
+{
+    const int t = blockIdx.x * SF_T + threadIdx.x;
+    const int i = p0 + (t >> 2), q = t & 3;
+    if (i >= p1) return;
+    if (rec11) {
+        // the 11 reduced floats of a Gaussian, split over its four threads: means3D | opacity + scales | rotations
+        const float *r = rec11 + (size_t)i * 11;
+        if (q == 0) {
+            dmeans3D[3 * (size_t)i] = r[0] * scale;
+            dmeans3D[3 * (size_t)i + 1] = r[1] * scale;
+            dmeans3D[3 * (size_t)i + 2] = r[2] * scale;
+        } else if (q == 1) {
+            dopacity[i] = r[3] * scale;
+            dscales[3 * (size_t)i] = r[4] * scale;
+            dscales[3 * (size_t)i + 1] = r[5] * scale;
+            dscales[3 * (size_t)i + 2] = r[6] * scale;
+        } else if (q == 2) {
+            *(float4 *)(drots + 4 * (size_t)i) = make_float4(r[7] * scale, r[8] * scale, r[9] * scale, r[10] * scale);
+        }
+    }
+    if (!dsh) return;
+    float acc[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+    const float mx = means[3 * (size_t)i], my = means[3 * (size_t)i + 1], mz = means[3 * (size_t)i + 2];
+    for (int v = 0; v < nviews; v++) {
+        const float *g = dRGB + (size_t)v * view_stride + (size_t)i * 3;
+        const float gr = g[0] * scale, gg = g[1] * scale, gb = g[2] * scale;
+        if (gr == 0.f && gg == 0.f && gb == 0.f) continue;  // not visible in this view
+        const float *cp = campos + (size_t)v * campos_stride;
+        const float ox = mx - cp[0], oy = my - cp[1], oz = mz - cp[2];
+        const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
+        const float x = ox * inv, y = oy * inv, z = oz * inv;
+        const float xx = x * x, yy = y * y, zz = z * z;
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        if (q == 0) {
+            w[0] = SH_C0;
+            if (deg > 0) {
+                w[1] = -SH_C1 * y;
+                w[2] = SH_C1 * z;
+                w[3] = -SH_C1 * x;
+            }
+        } else if (q == 1) {
+            if (deg > 1) {
+                w[0] = b_SH_C2[0] * x * y;
+                w[1] = b_SH_C2[1] * y * z;
+                w[2] = b_SH_C2[2] * (2.f * zz - xx - yy);
+                w[3] = b_SH_C2[3] * x * z;
+            }
+        } else if (q == 2) {
+            if (deg > 1) w[0] = b_SH_C2[4] * (xx - yy);
+            if (deg > 2) {
+                w[1] = b_SH_C3[0] * y * (3.f * xx - yy);
+                w[2] = b_SH_C3[1] * x * y * z;
+                w[3] = b_SH_C3[2] * y * (4.f * zz - xx - yy);
+            }
+        } else if (deg > 2) {
+            w[0] = b_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+            w[1] = b_SH_C3[4] * x * (4.f * zz - xx - yy);
+            w[2] = b_SH_C3[5] * z * (xx - yy);
+            w[3] = b_SH_C3[6] * x * (xx - 3.f * yy);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            acc[k][0] = fmaf(w[k], gr, acc[k][0]);
+            acc[k][1] = fmaf(w[k], gg, acc[k][1]);
+            acc[k][2] = fmaf(w[k], gb, acc[k][2]);
+        }
+    }
+    float4 *dst = (float4 *)(dsh + (size_t)i * 48 + q * 12);
+    dst[0] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[1][0]);
+    dst[1] = make_float4(acc[1][1], acc[1][2], acc[2][0], acc[2][1]);
+    dst[2] = make_float4(acc[2][2], acc[3][0], acc[3][1], acc[3][2]);
+}
+
+constexpr int SFG_T = 128;
+
+__global__ void __launch_bounds__(SFG_T) view_grad_finalize_kernel(int p0, int p1, int P, int M, int deg, int nviews,
                                                                    const float *__restrict__ means,
-                                                                   const float *__restrict__ campos,
-                                                                   const float *__restrict__ dRGB, float *__restrict__ dsh,
+                                                                   const float *__restrict__ campos, int campos_stride,
+                                                                   const float *__restrict__ dRGB, size_t view_stride,
+                                                                   float *__restrict__ dsh,
                                                                    const float *__restrict__ rec11, float scale,
                                                                    float *__restrict__ dmeans3D, float *__restrict__ dopacity,
                                                                    float *__restrict__ dscales, float *__restrict__ drots)
 {
-    extern __shared__ __align__(16) float s_rows[];  // SF_T rows x stride floats (SH half only)
-    const int tid = threadIdx.x, base = p0 + blockIdx.x * SF_T, i = base + tid;
-    const int n = min(SF_T, p1 - base);
+    extern __shared__ __align__(16) float s_rows[];  // SFG_T rows x stride floats (SH half only)
+    const int tid = threadIdx.x, base = p0 + blockIdx.x * SFG_T, i = base + tid;
+    const int n = min(SFG_T, p1 - base);
     if (rec11 && tid < n) {
         const float *r = rec11 + (size_t)i * 11;
         float v[11];
@@ -973,10 +1066,11 @@ __global__ void __launch_bounds__(SF_T) view_grad_finalize_kernel(int p0, int p1
     if (tid < n) {
         const float mx = means[3 * (size_t)i], my = means[3 * (size_t)i + 1], mz = means[3 * (size_t)i + 2];
         for (int v = 0; v < nviews; v++) {
-            const float *g = dRGB + ((size_t)v * P + i) * 3;
+            const float *g = dRGB + (size_t)v * view_stride + (size_t)i * 3;
             const float gr = g[0] * scale, gg = g[1] * scale, gb = g[2] * scale;
             if (gr == 0.f && gg == 0.f && gb == 0.f) continue;  // not visible in this view
-            const float ox = mx - campos[3 * v], oy = my - campos[3 * v + 1], oz = mz - campos[3 * v + 2];
+            const float *cp = campos + (size_t)v * campos_stride;
+            const float ox = mx - cp[0], oy = my - cp[1], oz = mz - cp[2];
             const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
             const float x = ox * inv, y = oy * inv, z = oz * inv;
             float w[16];
@@ -1024,7 +1118,7 @@ __global__ void __launch_bounds__(SF_T) view_grad_finalize_kernel(int p0, int p1
     }
     __syncthreads();
     float *dst = dsh + (size_t)base * row_f;
-    for (int k = tid; k < n * row_f; k += SF_T) {
+    for (int k = tid; k < n * row_f; k += SFG_T) {
         const int r = k / row_f, c = k - r * row_f;
         dst[k] = s_rows[r * stride + c];
     }
@@ -1189,27 +1283,37 @@ extern "C" int sgr_backward_chunk_range(int32_t P, int32_t num_chunks, int32_t c
 }
 
 extern "C" int sgr_view_grad_finalize(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree, int32_t num_views,
-                                      const float *means3D, const float *campos, const float *dRGB, float *dL_dsh,
-                                      const float *reduced_records, float scale, float *dL_dmeans3D, float *dL_dopacity,
-                                      float *dL_dscales, float *dL_drotations, void *stream)
+                                      const float *means3D, const float *campos, const float *dRGB, int64_t view_stride,
+                                      int32_t campos_stride, float *dL_dsh, const float *reduced_records, float scale,
+                                      float *dL_dmeans3D, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
+                                      void *stream)
 {
     using namespace sgr;
     const bool sh = dL_dsh != nullptr, rec = reduced_records != nullptr;
     if (P < 0 || p0 < 0 || p1 < p0 || p1 > P || (!sh && !rec) ||
         (sh && (M <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M || num_views <= 0 ||
-                !means3D || !campos || !dRGB)) ||
+                !means3D || !campos || !dRGB || view_stride < (int64_t)3 * P || campos_stride < 3)) ||
         (rec && (!dL_dmeans3D || !dL_dopacity || !dL_dscales || !dL_drotations))) {
         set_error("bad arguments to sgr_view_grad_finalize");
         return SGR_EINVAL;
     }
     if (p1 == p0) return SGR_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int row_f = M * 3, stride = (row_f & 1) ? row_f : row_f + 1;
-    const size_t dyn = sh ? (size_t)SF_T * stride * sizeof(float) : 0;
-    SGR_LAUNCH(K_MISC, st,
-               view_grad_finalize_kernel<<<(p1 - p0 + SF_T - 1) / SF_T, SF_T, dyn, st>>>(
-                   p0, p1, P, M, sh_degree, num_views, means3D, campos, dRGB, dL_dsh, reduced_records, scale, dL_dmeans3D,
-                   dL_dopacity, dL_dscales, dL_drotations));
+    const bool al16 = (((uintptr_t)dL_dsh | (uintptr_t)dL_drotations) & 15u) == 0;
+    if ((!sh || M == 16) && al16) {
+        const int threads = (p1 - p0) * 4;
+        SGR_LAUNCH(K_MISC, st,
+                   view_grad_finalize_m16_kernel<<<(threads + SF_T - 1) / SF_T, SF_T, 0, st>>>(
+                       p0, p1, sh_degree, num_views, means3D, campos, campos_stride, dRGB, (size_t)view_stride, dL_dsh,
+                       reduced_records, scale, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations));
+    } else {
+        const int row_f = M * 3, stride = (row_f & 1) ? row_f : row_f + 1;
+        const size_t dyn = sh ? (size_t)SFG_T * stride * sizeof(float) : 0;
+        SGR_LAUNCH(K_MISC, st,
+                   view_grad_finalize_kernel<<<(p1 - p0 + SFG_T - 1) / SFG_T, SFG_T, dyn, st>>>(
+                       p0, p1, P, M, sh_degree, num_views, means3D, campos, campos_stride, dRGB, (size_t)view_stride, dL_dsh,
+                       reduced_records, scale, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations));
+    }
     SGR_CUDA(cudaGetLastError());
     return SGR_OK;
 }
@@ -1221,6 +1325,6 @@ extern "C" int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree,
         sgr::set_error("bad arguments to sgr_sh_grad_from_factors");
         return SGR_EINVAL;
     }
-    return sgr_view_grad_finalize(P, 0, P, M, sh_degree, num_views, means3D, campos, dRGB, dL_dsh, nullptr, 1.0f, nullptr,
-                                  nullptr, nullptr, nullptr, stream);
+    return sgr_view_grad_finalize(P, 0, P, M, sh_degree, num_views, means3D, campos, dRGB, (int64_t)3 * P, 3, dL_dsh, nullptr,
+                                  1.0f, nullptr, nullptr, nullptr, nullptr, stream);
 }

@@ -114,35 +114,30 @@ class ViewParallel:
         dev = means3D.device
         factor = bool(M) and self.sh_factors
         nchunks = max(1, self.chunks)
-        rng = lambda c: self._range(lib, check, P, nchunks, c)
+        if getattr(self, "_ranges_key", None) != (P, nchunks):
+            self._ranges_key, self._ranges = (P, nchunks), [self._range(lib, check, P, nchunks, c) for c in range(nchunks)]
+        ranges = self._ranges
         pending = {c: [] for c in range(nchunks)}
         early = []
-        state = {"d_all": None}
         failure = []
-        # every view's camera position (tiny; long done when the finalize needs it)
+        stride = 3 * P + 4   # a view's factor block: dL/dRGB [P,3] followed by its camera position (+ 1 pad)
+        d_all = None
         if factor:
-            c_all = torch.empty((world, 3), dtype=torch.float32, device=dev)
-            if multi:
-                early.append(dist.all_gather_into_tensor(c_all, campos.reshape(3).float().contiguous(), group=self.group,
-                                                         async_op=True))
-            else:
-                c_all.copy_(campos.reshape(1, 3))
+            block = bufs["colors_block"]
+            block[3 * P:3 * P + 3].copy_(campos.reshape(3))   # rides in the same all-gather as the factors
+            d_all = self._gather_buffer(world, stride, dev) if multi else block.view(1, stride)
 
         def on_stage(_ctx, stage):
             try:
                 if stage == 1:  # SGR_STAGE_BLEND_DONE: dL_dcolors is final
-                    if factor:
-                        if multi:
-                            state["d_all"] = torch.empty((world, P, 3), dtype=torch.float32, device=dev)
-                            early.append(dist.all_gather_into_tensor(state["d_all"], bufs["colors"], group=self.group,
-                                                                     async_op=True))
-                        else:
-                            state["d_all"] = bufs["colors"].view(1, P, 3)
+                    if factor and multi:
+                        early.append(dist.all_gather_into_tensor(d_all, bufs["colors_block"], group=self.group,
+                                                                 async_op=True))
                     elif not M and multi:  # colours were precomputed: their gradient is an ordinary sum
                         early.append(dist.all_reduce(bufs["colors"], group=self.group, async_op=True))
                 elif stage >= 16 and multi:  # SGR_STAGE_CHUNK_DONE + c
                     c = stage - 16
-                    p0, p1 = rng(c)
+                    p0, p1 = ranges[c]
                     if p1 > p0:
                         pending[c].append(dist.all_reduce(bufs["records"][p0:p1], group=self.group, async_op=True))
                         if M and not factor:
@@ -160,17 +155,17 @@ class ViewParallel:
         for h in early:
             h.wait()  # stream-ordered: the host does not block
         stream = torch.cuda.current_stream(dev).cuda_stream
-        d_all = state["d_all"]
+        d_ptr = d_all.data_ptr() if factor else None
         for c in range(nchunks):
-            p0, p1 = rng(c)
+            p0, p1 = ranges[c]
             for h in pending[c]:
                 h.wait()
             if p1 > p0:
                 check(lib.sgr_view_grad_finalize(
-                    P, p0, p1, M, degree, world, means3D.data_ptr(), c_all.data_ptr() if factor else None,
-                    d_all.data_ptr() if factor else None, bufs["sh"].data_ptr() if factor else None,
-                    bufs["records"].data_ptr(), self.scale, bufs["means3D"].data_ptr(), bufs["opacity"].data_ptr(),
-                    bufs["scales"].data_ptr(), bufs["rotations"].data_ptr(), stream))
+                    P, p0, p1, M, degree, world, means3D.data_ptr(), (d_ptr + 12 * P) if factor else None, d_ptr,
+                    stride, stride, bufs["sh"].data_ptr() if factor else None, bufs["records"].data_ptr(), self.scale,
+                    bufs["means3D"].data_ptr(), bufs["opacity"].data_ptr(), bufs["scales"].data_ptr(),
+                    bufs["rotations"].data_ptr(), stream))
         if self.scale != 1.0:  # what the finalize kernel did not touch
             if M and not factor:
                 bufs["sh"].mul_(self.scale)
@@ -180,6 +175,14 @@ class ViewParallel:
                 bufs["cov3D"].mul_(self.scale)
         self.stats["backwards"] += 1
         self.stats["collectives"] += len(early) + sum(len(v) for v in pending.values())
+
+    def _gather_buffer(self, world, stride, dev):
+        """[world, 3P+4] receive buffer of the factor all-gather, kept across backwards (its readers, the finalize
+        kernels, are enqueued on the compute stream before the next backward's gather is)."""
+        key = (world, stride, dev)
+        if getattr(self, "_gather_key", None) != key:
+            self._gather_key, self._gather = key, torch.empty((world, stride), dtype=torch.float32, device=dev)
+        return self._gather
 
     @staticmethod
     def _range(lib, check, P, nchunks, c):
