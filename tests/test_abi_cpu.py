@@ -91,4 +91,4 @@ def test_new_entry_points_validate_arguments_without_gpu():
             prev, seen = p1.value, seen + (p1.value - p0.value)
         assert seen == P and prev == P
     assert L.sgr_backward_chunk_range(10, 2, 2, ctypes.byref(p0), ctypes.byref(p1)) == -1
-    assert L.sgr_view_grad_finalize(10, 0, 10, 16, 3, 1, None, None, None, 30, 3, None, None, 1.0, *([None] * 4)) == -1
+    assert L.sgr_view_grad_finalize(10, 0, 10, 16, 3, 1, None, None, None, 30, 3, None, None, 1.0, *([None] * 5)) == -1
