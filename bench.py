@@ -68,6 +68,10 @@ def parse():
                     help="N>1: all-reduce the full dL_dsh instead of all-gathering the SH factors")
     ap.add_argument("--chunks", type=int, default=4,
                     help="N>1: Gaussian ranges of the per-Gaussian backward pass; each range's all-reduce overlaps the next")
+    ap.add_argument("--side-stream", action="store_true",
+                    help="N>1: finalize each range on a second stream as soon as its collective is done (parallel.ViewParallel)")
+    ap.add_argument("--force-exchange", action="store_true",
+                    help="diagnostic, N=1: run the exchange path's kernels (factor-mode backward + finalize) without NCCL")
     return ap.parse_args()
 
 
@@ -233,7 +237,7 @@ def cpu_baseline_density(args):
                       f"({cores} threads), {dt*1e3:.0f} ms per call"}
 
 
-def verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D, sh_factors, chunks):
+def verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D, sh_factors, chunks, side_stream=False):
     """N > 1, before any timing: on a small scene every rank renders its own view twice -- once with the
     exchange inside the backward, once plainly followed by an ordinary all-reduce of each gradient -- and the
     two sets of summed gradients must agree.  Returns the largest |a-b|_inf / |b|_inf over tensors and ranks."""
@@ -258,7 +262,7 @@ def verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D, sh_
     plain = run()
     for k in names:
         dist.all_reduce(plain[k].grad)
-    vp = parallel.ViewParallel(sh_factors=sh_factors, chunks=chunks)
+    vp = parallel.ViewParallel(sh_factors=sh_factors, chunks=chunks, side_stream=side_stream)
     with vp.context():
         ex = run()
     worst = 0.0
@@ -358,14 +362,17 @@ def main():
                                                  campos=cp, prefiltered=False, debug=False)
 
     exchange_check = None
-    if dist is not None:
+    if dist is not None or (args.force_exchange and not use_ref):
         # view-parallel exchange inside the op's backward (sugar_b200/parallel.py): SH factors all-gathered,
         # the other 44 B/Gaussian all-reduced chunk by chunk underneath the per-Gaussian pass
         import contextlib
         from sugar_b200 import parallel
-        vp = parallel.ViewParallel(sh_factors=not args.no_sh_factors, chunks=args.chunks)
-        exchange_check = verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D,
-                                         sh_factors=not args.no_sh_factors, chunks=args.chunks)
+        vp = parallel.ViewParallel(sh_factors=not args.no_sh_factors, chunks=args.chunks, side_stream=args.side_stream,
+                                   force=args.force_exchange)
+        if dist is not None:
+            exchange_check = verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D,
+                                             sh_factors=not args.no_sh_factors, chunks=args.chunks,
+                                             side_stream=args.side_stream)
         stack = contextlib.ExitStack()
         stack.enter_context(vp.context())  # the autograd node keeps the context for the backward thread
 
@@ -506,6 +513,7 @@ def main():
                                     "1 view per GPU per step") + ", fwd+bwd"),
                       "visible": V_vis, "l2_policy": "inputs (708 MB of Gaussian parameters) larger than L2; no flush"},
            "parallelism": {"mode": f"view-dp{world}" if world > 1 else "single",
+                           "side_stream_finalize": bool(args.side_stream), "forced_exchange": bool(args.force_exchange),
                            "exchange": ("none" if world == 1 else "all-reduce 236 B/Gaussian" if args.no_sh_factors else
                                         f"inside the backward: all-gather 12 B/Gaussian/view SH factors under the "
                                         f"per-Gaussian pass + all-reduce 44 B/Gaussian in {args.chunks} overlapped chunks"),

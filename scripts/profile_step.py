@@ -1,4 +1,6 @@
-"""Two fwd+bwd steps of the bench workload (for ncu): python scripts/profile_step.py [P W H]"""
+"""Two fwd+bwd steps of the bench workload (for ncu): python scripts/profile_step.py [P W H [steps]]
+SGR_PROFILE_EXCHANGE=<views>: run the view-parallel exchange path on this one rank (parallel.ViewParallel(force=True)): the
+same kernels as a multi-GPU step (factor-mode per-Gaussian backward + finalize) without NCCL, so ncu can capture them."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,11 +17,18 @@ means2D = torch.zeros_like(params["means3D"], requires_grad=True)
 dL = t(scenes.upstream_grad(W, H))
 st = mod.GaussianRasterizationSettings(H, W, sc.tanfovx, sc.tanfovy, torch.zeros(3, device=dev), 1.0, t(sc.viewmatrix),
                                        t(sc.projmatrix), 3, t(sc.campos), False, False)
-for _ in range(steps):
-    color, radii = mod.GaussianRasterizer(st)(means3D=params["means3D"], means2D=means2D, opacities=params["opacities"],
-                                              shs=params["shs"], scales=params["scales"], rotations=params["rotations"])
-    torch.autograd.backward(color, dL)
-    for p in params.values():
-        p.grad = None
+import contextlib
+ctx = contextlib.nullcontext()
+if os.environ.get("SGR_PROFILE_EXCHANGE"):
+    from sugar_b200 import parallel
+    ctx = parallel.ViewParallel(force=True, chunks=int(os.environ.get("SGR_PROFILE_CHUNKS", "4"))).context()
+with ctx:
+    for _ in range(steps):
+        color, radii = mod.GaussianRasterizer(st)(means3D=params["means3D"], means2D=means2D,
+                                                  opacities=params["opacities"], shs=params["shs"],
+                                                  scales=params["scales"], rotations=params["rotations"])
+        torch.autograd.backward(color, dL)
+        for p in params.values():
+            p.grad = None
 torch.cuda.synchronize()
 print("done", int((radii > 0).sum()))

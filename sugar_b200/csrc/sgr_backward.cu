@@ -935,6 +935,10 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
 // Either half is optional.
 // ------------------------------------------------------------------------------------------------
 constexpr int SF_T = 256;  // 64 Gaussians per CTA, four threads each
+#ifndef SGR_SF_VB
+#define SGR_SF_VB 4
+#endif
+constexpr int SF_VB = SGR_SF_VB;  // views whose factors a thread fetches before it uses any
 
 // Four threads per Gaussian: thread q owns SH coefficients 4q .. 4q+3, i.e. 48 contiguous bytes of the row
 // (three 16-byte stores; the four threads of a Gaussian cover its 192-byte row, a warp 1.5 KB without gaps), and
@@ -955,75 +959,113 @@ __global__ void __launch_bounds__(SF_T) view_grad_finalize_m16_kernel(int p0, in
     const int t = blockIdx.x * SF_T + threadIdx.x;
     const int i = p0 + (t >> 2), q = t & 3;
     if (i >= p1) return;
-    if (rec11) {
+    // Every load of the thread is issued before its first store or use: the kernel is a latency chain per thread
+    // (records -> stores, mean + factors -> rows), and what hides DRAM latency here is bytes in flight per thread.
+    float rv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rec11 && q < 3) {
         // the 11 reduced floats of a Gaussian, split over its four threads: means3D | opacity + scales | rotations
-        const float *r = rec11 + (size_t)i * 11;
+        const float *r = rec11 + (size_t)i * 11 + (q == 0 ? 0 : q == 1 ? 3 : 7);
+        rv[0] = __ldcs(r);
+        rv[1] = __ldcs(r + 1);
+        rv[2] = __ldcs(r + 2);
+        if (q) rv[3] = __ldcs(r + 3);
+    }
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    float gv[SF_VB][3];
+    if (dsh) {
+        mx = __ldg(means + 3 * (size_t)i);
+        my = __ldg(means + 3 * (size_t)i + 1);
+        mz = __ldg(means + 3 * (size_t)i + 2);
+#pragma unroll
+        for (int u = 0; u < SF_VB; u++) {
+            const bool on = u < nviews;
+            const float *g = dRGB + (size_t)(on ? u : 0) * view_stride + (size_t)i * 3;
+            gv[u][0] = on ? __ldcs(g) : 0.f;
+            gv[u][1] = on ? __ldcs(g + 1) : 0.f;
+            gv[u][2] = on ? __ldcs(g + 2) : 0.f;
+        }
+    }
+    if (rec11) {
         if (q == 0) {
-            dmeans3D[3 * (size_t)i] = r[0] * scale;
-            dmeans3D[3 * (size_t)i + 1] = r[1] * scale;
-            dmeans3D[3 * (size_t)i + 2] = r[2] * scale;
+            __stcs(dmeans3D + 3 * (size_t)i, rv[0] * scale);
+            __stcs(dmeans3D + 3 * (size_t)i + 1, rv[1] * scale);
+            __stcs(dmeans3D + 3 * (size_t)i + 2, rv[2] * scale);
         } else if (q == 1) {
-            dopacity[i] = r[3] * scale;
-            dscales[3 * (size_t)i] = r[4] * scale;
-            dscales[3 * (size_t)i + 1] = r[5] * scale;
-            dscales[3 * (size_t)i + 2] = r[6] * scale;
+            __stcs(dopacity + i, rv[0] * scale);
+            __stcs(dscales + 3 * (size_t)i, rv[1] * scale);
+            __stcs(dscales + 3 * (size_t)i + 1, rv[2] * scale);
+            __stcs(dscales + 3 * (size_t)i + 2, rv[3] * scale);
         } else if (q == 2) {
-            *(float4 *)(drots + 4 * (size_t)i) = make_float4(r[7] * scale, r[8] * scale, r[9] * scale, r[10] * scale);
+            __stcs((float4 *)(drots + 4 * (size_t)i), make_float4(rv[0] * scale, rv[1] * scale, rv[2] * scale, rv[3] * scale));
         }
     }
     if (!dsh) return;
     float acc[4][3];
 #pragma unroll
     for (int k = 0; k < 4; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
-    const float mx = means[3 * (size_t)i], my = means[3 * (size_t)i + 1], mz = means[3 * (size_t)i + 2];
-    for (int v = 0; v < nviews; v++) {
-        const float *g = dRGB + (size_t)v * view_stride + (size_t)i * 3;
-        const float gr = g[0] * scale, gg = g[1] * scale, gb = g[2] * scale;
-        if (gr == 0.f && gg == 0.f && gb == 0.f) continue;  // not visible in this view
-        const float *cp = campos + (size_t)v * campos_stride;
-        const float ox = mx - cp[0], oy = my - cp[1], oz = mz - cp[2];
-        const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
-        const float x = ox * inv, y = oy * inv, z = oz * inv;
-        const float xx = x * x, yy = y * y, zz = z * z;
-        float w[4] = {0.f, 0.f, 0.f, 0.f};
-        if (q == 0) {
-            w[0] = SH_C0;
-            if (deg > 0) {
-                w[1] = -SH_C1 * y;
-                w[2] = SH_C1 * z;
-                w[3] = -SH_C1 * x;
+    // The views' factors are independent 12-byte reads 3P floats apart: a thread fetches SF_VB views' worth at a time
+    // (the first batch above, with everything else), so 8 views cost 2 dependent DRAM round trips, not 8.
+    for (int v0 = 0; v0 < nviews; v0 += SF_VB) {
+        if (v0) {
+#pragma unroll
+            for (int u = 0; u < SF_VB; u++) {
+                const bool on = v0 + u < nviews;
+                const float *g = dRGB + (size_t)(on ? v0 + u : v0) * view_stride + (size_t)i * 3;
+                gv[u][0] = on ? __ldcs(g) : 0.f;
+                gv[u][1] = on ? __ldcs(g + 1) : 0.f;
+                gv[u][2] = on ? __ldcs(g + 2) : 0.f;
             }
-        } else if (q == 1) {
-            if (deg > 1) {
-                w[0] = b_SH_C2[0] * x * y;
-                w[1] = b_SH_C2[1] * y * z;
-                w[2] = b_SH_C2[2] * (2.f * zz - xx - yy);
-                w[3] = b_SH_C2[3] * x * z;
-            }
-        } else if (q == 2) {
-            if (deg > 1) w[0] = b_SH_C2[4] * (xx - yy);
-            if (deg > 2) {
-                w[1] = b_SH_C3[0] * y * (3.f * xx - yy);
-                w[2] = b_SH_C3[1] * x * y * z;
-                w[3] = b_SH_C3[2] * y * (4.f * zz - xx - yy);
-            }
-        } else if (deg > 2) {
-            w[0] = b_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-            w[1] = b_SH_C3[4] * x * (4.f * zz - xx - yy);
-            w[2] = b_SH_C3[5] * z * (xx - yy);
-            w[3] = b_SH_C3[6] * x * (xx - 3.f * yy);
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            acc[k][0] = fmaf(w[k], gr, acc[k][0]);
-            acc[k][1] = fmaf(w[k], gg, acc[k][1]);
-            acc[k][2] = fmaf(w[k], gb, acc[k][2]);
+        for (int u = 0; u < SF_VB; u++) {
+            const float gr = gv[u][0] * scale, gg = gv[u][1] * scale, gb = gv[u][2] * scale;
+            if (gr == 0.f && gg == 0.f && gb == 0.f) continue;  // not visible in this view (or past the last view)
+            const float *cp = campos + (size_t)(v0 + u) * campos_stride;
+            const float ox = mx - __ldg(cp), oy = my - __ldg(cp + 1), oz = mz - __ldg(cp + 2);
+            const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
+            const float x = ox * inv, y = oy * inv, z = oz * inv;
+            const float xx = x * x, yy = y * y, zz = z * z;
+            float w[4] = {0.f, 0.f, 0.f, 0.f};
+            if (q == 0) {
+                w[0] = SH_C0;
+                if (deg > 0) {
+                    w[1] = -SH_C1 * y;
+                    w[2] = SH_C1 * z;
+                    w[3] = -SH_C1 * x;
+                }
+            } else if (q == 1) {
+                if (deg > 1) {
+                    w[0] = b_SH_C2[0] * x * y;
+                    w[1] = b_SH_C2[1] * y * z;
+                    w[2] = b_SH_C2[2] * (2.f * zz - xx - yy);
+                    w[3] = b_SH_C2[3] * x * z;
+                }
+            } else if (q == 2) {
+                if (deg > 1) w[0] = b_SH_C2[4] * (xx - yy);
+                if (deg > 2) {
+                    w[1] = b_SH_C3[0] * y * (3.f * xx - yy);
+                    w[2] = b_SH_C3[1] * x * y * z;
+                    w[3] = b_SH_C3[2] * y * (4.f * zz - xx - yy);
+                }
+            } else if (deg > 2) {
+                w[0] = b_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                w[1] = b_SH_C3[4] * x * (4.f * zz - xx - yy);
+                w[2] = b_SH_C3[5] * z * (xx - yy);
+                w[3] = b_SH_C3[6] * x * (xx - 3.f * yy);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                acc[k][0] = fmaf(w[k], gr, acc[k][0]);
+                acc[k][1] = fmaf(w[k], gg, acc[k][1]);
+                acc[k][2] = fmaf(w[k], gb, acc[k][2]);
+            }
         }
     }
+    // written once, 576 MB per backward at 3M Gaussians: streaming stores keep them from displacing the L2's contents
     float4 *dst = (float4 *)(dsh + (size_t)i * 48 + q * 12);
-    dst[0] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[1][0]);
-    dst[1] = make_float4(acc[1][1], acc[1][2], acc[2][0], acc[2][1]);
-    dst[2] = make_float4(acc[2][2], acc[3][0], acc[3][1], acc[3][2]);
+    __stcs(dst, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[1][0]));
+    __stcs(dst + 1, make_float4(acc[1][1], acc[1][2], acc[2][0], acc[2][1]));
+    __stcs(dst + 2, make_float4(acc[2][2], acc[3][0], acc[3][1], acc[3][2]));
 }
 
 constexpr int SFG_T = 128;

@@ -917,6 +917,9 @@ __global__ void __launch_bounds__(BK_T) tile_sort_bucket_kernel(const uint32_t *
 // Tiles are taken heaviest first (tile_order).
 // ------------------------------------------------------------------------------------------------
 constexpr int BLEND_T = 256;
+#ifndef SGR_FWD_MIN_BLOCKS
+#define SGR_FWD_MIN_BLOCKS 1   // A/B knob: resident CTAs/SM the register allocation must allow
+#endif
 
 // -DSGR_BLEND_STATS: count what the blend loops do (scripts/blend_stats.py); never in the shipped build
 #ifdef SGR_BLEND_STATS
@@ -925,7 +928,7 @@ __device__ unsigned long long g_fwd_stats[8];
 #endif
 
 template <bool packed>
-__global__ void __launch_bounds__(BLEND_T) blend_forward_kernel(const uint32_t *__restrict__ tile_order,
+__global__ void __launch_bounds__(BLEND_T, SGR_FWD_MIN_BLOCKS) blend_forward_kernel(const uint32_t *__restrict__ tile_order,
                                                                 const uint32_t *__restrict__ tile_start,
                                                                 const uint32_t *__restrict__ plist,
                                                                 const float4 *__restrict__ rec,

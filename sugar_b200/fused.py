@@ -38,10 +38,13 @@ class _RasterizeRaw(torch.autograd.Function):
         ctx.raster_settings, ctx.num_rendered = rs, num_rendered
         ctx.save_for_backward(points, scales_raw, quats_raw, radii, sh_dc, sh_rest, geom, binning, img)
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)   # no [P] zeros tensor for radii's absent gradient on every backward
         return color, radii
 
     @staticmethod
     def backward(ctx, grad_color, _grad_radii):
+        if grad_color is None:
+            return (None,) * 8
         rs = ctx.raster_settings
         points, scales_raw, quats_raw, radii, sh_dc, sh_rest, geom, binning, img = ctx.saved_tensors
         absent = torch.Tensor([])

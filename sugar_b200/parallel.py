@@ -84,11 +84,16 @@ class ViewParallel:
     chunks      Gaussian ranges of the per-Gaussian pass; each range's all-reduce overlaps the next range
     scale       multiplies every summed gradient (1/num_views for a mean over the batch)
     force       run the record / finalize path even with a single rank (tests; no collectives are issued)
+    side_stream finalize range c on a second (high-priority) stream as soon as its collective is done, concurrently
+                with the per-Gaussian pass of the ranges behind it, instead of after the whole pass on the caller's stream
     """
 
-    def __init__(self, sh_factors: bool = True, chunks: int = 4, scale: float = 1.0, group=None, force: bool = False):
+    def __init__(self, sh_factors: bool = True, chunks: int = 4, scale: float = 1.0, group=None, force: bool = False,
+                 side_stream: bool = False):
         from . import _C
         self.sh_factors, self.chunks, self.scale, self.group, self.force = bool(sh_factors), int(chunks), float(scale), group, force
+        self.side_stream = bool(side_stream)
+        self._side = {}     # device -> (stream, [events])
         self.ctx = _C.Context()
         self.ctx.exchange = self
         self.stats = {"backwards": 0, "collectives": 0}
@@ -120,6 +125,13 @@ class ViewParallel:
         pending = {c: [] for c in range(nchunks)}
         early = []
         failure = []
+        side = chunk_done = None
+        if self.side_stream:
+            if dev not in self._side:
+                self._side[dev] = (torch.cuda.Stream(device=dev, priority=-1), [])
+            side, chunk_done = self._side[dev]
+            while len(chunk_done) < nchunks:
+                chunk_done.append(torch.cuda.Event())
         stride = 3 * P + 4   # a view's factor block: dL/dRGB [P,3] followed by its camera position (+ 1 pad)
         d_all = None
         if factor:
@@ -135,6 +147,8 @@ class ViewParallel:
                                                                  async_op=True))
                     elif not M and multi:  # colours were precomputed: their gradient is an ordinary sum
                         early.append(dist.all_reduce(bufs["colors"], group=self.group, async_op=True))
+                elif stage >= 16 and side is not None and not multi:
+                    chunk_done[stage - 16].record()   # what the side stream's finalize of this range waits for
                 elif stage >= 16 and multi:  # SGR_STAGE_CHUNK_DONE + c
                     c = stage - 16
                     p0, p1 = ranges[c]
@@ -152,20 +166,28 @@ class ViewParallel:
         check(lib.sgr_rasterize_backward_staged(*args, C.byref(plan)))
         if failure:
             raise failure[0]
-        for h in early:
-            h.wait()  # stream-ordered: the host does not block
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        main = torch.cuda.current_stream(dev)
         d_ptr = d_all.data_ptr() if factor else None
-        for c in range(nchunks):
-            p0, p1 = ranges[c]
-            for h in pending[c]:
+        # stream-ordered waits: the host never blocks.  With a side stream every range is finalized as soon as ITS
+        # collective is done, while the caller's stream is still in the per-Gaussian pass of later ranges.
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            cur = side if side is not None else main
+            for h in early:
                 h.wait()
-            if p1 > p0:
-                check(lib.sgr_view_grad_finalize(
-                    P, p0, p1, M, degree, world, means3D.data_ptr(), (d_ptr + 12 * P) if factor else None, d_ptr,
-                    stride, stride, bufs["sh"].data_ptr() if factor else None, bufs["records"].data_ptr(), self.scale,
-                    bufs["means3D"].data_ptr(), bufs["opacity"].data_ptr(), bufs["scales"].data_ptr(),
-                    bufs["rotations"].data_ptr(), stream))
+            for c in range(nchunks):
+                p0, p1 = ranges[c]
+                for h in pending[c]:
+                    h.wait()
+                if side is not None and not multi:
+                    side.wait_event(chunk_done[c])   # single rank: the range's producer is the caller's stream itself
+                if p1 > p0:
+                    check(lib.sgr_view_grad_finalize(
+                        P, p0, p1, M, degree, world, means3D.data_ptr(), (d_ptr + 12 * P) if factor else None, d_ptr,
+                        stride, stride, bufs["sh"].data_ptr() if factor else None, bufs["records"].data_ptr(), self.scale,
+                        bufs["means3D"].data_ptr(), bufs["opacity"].data_ptr(), bufs["scales"].data_ptr(),
+                        bufs["rotations"].data_ptr(), cur.cuda_stream))
+        if side is not None:
+            main.wait_stream(side)   # everything after the backward (and the allocator's reuse of bufs) is ordered behind
         if self.scale != 1.0:  # what the finalize kernel did not touch
             if M and not factor:
                 bufs["sh"].mul_(self.scale)

@@ -27,8 +27,10 @@ def _render_loss(mod, t, sc, dL, deg, ps, bg=(0.1, 0.2, 0.3), colors=None):
     return (color * dL).sum(), means2D
 
 
-@pytest.mark.parametrize("deg,chunks,factors", [(3, 4, True), (1, 3, True), (0, 1, True), (3, 4, False), (2, 7, True)])
-def test_forced_exchange_matches_plain_backward(deg, chunks, factors):
+@pytest.mark.parametrize("deg,chunks,factors,side", [(3, 4, True, False), (1, 3, True, False), (0, 1, True, False),
+                                                     (3, 4, False, False), (2, 7, True, False), (3, 4, True, True),
+                                                     (2, 3, False, True)])
+def test_forced_exchange_matches_plain_backward(deg, chunks, factors, side):
     import torch
     from sugar_b200 import diff_gaussian_rasterization as mod
     from sugar_b200 import parallel, scenes
@@ -41,7 +43,7 @@ def test_forced_exchange_matches_plain_backward(deg, chunks, factors):
     ps_a = {k: leaf(t[k]) for k in names}
     loss, m2a = _render_loss(mod, t, sc, dL, deg, ps_a)
     loss.backward()
-    vp = parallel.ViewParallel(sh_factors=factors, chunks=chunks, scale=0.5, force=True)
+    vp = parallel.ViewParallel(sh_factors=factors, chunks=chunks, scale=0.5, force=True, side_stream=side)
     ps_b = {k: leaf(t[k]) for k in names}
     with vp.context():
         loss, m2b = _render_loss(mod, t, sc, dL, deg, ps_b)
