@@ -549,14 +549,18 @@ def main():
         stages = {}
         for name, (tot, cnt) in prof.items():
             avg_ms = tot / cnt
+            # a view's pass of this kernel may be split into several launches (the per-Gaussian backward runs in
+            # Gaussian-range chunks under the view-parallel exchange): rates are per VIEW PASS, i.e. the byte /
+            # instruction model of one view over the summed duration of that view's launches
+            pass_ms = tot / (args.steps * len(views))
             b = alg.get(name)
-            st = {"ms": round(avg_ms, 4), "launches_per_step": cnt / args.steps,
-                  "gbs": round(b / (avg_ms * 1e-3) / 1e9, 1) if b else None,
-                  "hbm_frac": round(b / (avg_ms * 1e-3) / 1e9 / peak, 4) if b else None,
+            st = {"ms": round(avg_ms, 4), "launches_per_step": cnt / args.steps, "ms_per_view_pass": round(pass_ms, 4),
+                  "gbs": round(b / (pass_ms * 1e-3) / 1e9, 1) if b else None,
+                  "hbm_frac": round(b / (pass_ms * 1e-3) / 1e9 / peak, 4) if b else None,
                   "bound": KERNEL_BOUND.get(name, "latency")}
             inst = (ncu.get(name) or {}).get("warp_instructions")
             if inst:
-                st["issue_frac"] = round(inst / (avg_ms * 1e-3) / issue_peak, 4)
+                st["issue_frac"] = round(inst / (pass_ms * 1e-3) / issue_peak, 4)
             stages[name] = st
         dom = max(stages, key=lambda k: stages[k]["ms"] * stages[k]["launches_per_step"]) if stages else None
         if dom:
@@ -569,7 +573,7 @@ def main():
                 # the blend kernels are FP32-issue bound (~256 pair evaluations per 40 bytes): their roofline
                 # is the issue rate, warp-instructions (ncu smsp__inst_executed.sum) / duration vs SMs x 4 x clock
                 out["roofline"]["issue"] = {
-                    "achieved": round(facts["warp_instructions"] / (stages[dom]["ms"] * 1e-3) / 1e9, 1),
+                    "achieved": round(facts["warp_instructions"] / (stages[dom]["ms_per_view_pass"] * 1e-3) / 1e9, 1),
                     "peak": round(issue_peak / 1e9, 1), "unit": "G warp-inst/s", "frac": stages[dom].get("issue_frac"),
                     "warp_instructions": facts["warp_instructions"], "source": facts.get("source")}
             # the HBM-bound stages BASELINE.md holds to >= 60 % of peak
