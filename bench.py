@@ -70,6 +70,11 @@ def parse():
                     help="N>1: Gaussian ranges of the per-Gaussian backward pass; each range's all-reduce overlaps the next")
     ap.add_argument("--side-stream", action="store_true",
                     help="N>1: finalize each range on a second stream as soon as its collective is done (parallel.ViewParallel)")
+    ap.add_argument("--peer", action="store_true",
+                    help="N>1: exchange through the peer-memory kernels (csrc/sgr_peer.cu: CUDA IPC mappings, flags, "
+                         "P2P loads / stores over NVLink) instead of NCCL collectives (all-gather + chunked all-reduce)")
+    ap.add_argument("--no-taper", action="store_true",
+                    help="N>1, peer exchange: equal chunks instead of halving ones")
     ap.add_argument("--force-exchange", action="store_true",
                     help="diagnostic, N=1: run the exchange path's kernels (factor-mode backward + finalize) without NCCL")
     return ap.parse_args()
@@ -237,7 +242,8 @@ def cpu_baseline_density(args):
                       f"({cores} threads), {dt*1e3:.0f} ms per call"}
 
 
-def verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D, sh_factors, chunks, side_stream=False):
+def verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D, sh_factors, chunks, side_stream=False,
+                    peer="auto"):
     """N > 1, before any timing: on a small scene every rank renders its own view twice -- once with the
     exchange inside the backward, once plainly followed by an ordinary all-reduce of each gradient -- and the
     two sets of summed gradients must agree.  Returns the largest |a-b|_inf / |b|_inf over tensors and ranks."""
@@ -262,20 +268,25 @@ def verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D, sh_
     plain = run()
     for k in names:
         dist.all_reduce(plain[k].grad)
-    vp = parallel.ViewParallel(sh_factors=sh_factors, chunks=chunks, side_stream=side_stream)
-    with vp.context():
-        ex = run()
+    vp = parallel.ViewParallel(sh_factors=sh_factors, chunks=chunks, side_stream=side_stream, peer=peer)
     worst = 0.0
-    for k in names:
-        a, b = ex[k].grad, plain[k].grad
-        worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+    with vp.context():
+        for _ in range(3):   # three backwards: the peer exchange alternates its factor blocks by step parity
+            ex = run()
+            for k in names:
+                a, b = ex[k].grad, plain[k].grad
+                worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
     w = torch.tensor([worst], device=dev)
     dist.all_reduce(w, op=dist.ReduceOp.MAX)
     worst = float(w.item())
     if not worst <= 1e-4:
         raise RuntimeError(f"view-parallel exchange disagrees with a plain all-reduce: rel err {worst:.3e}")
-    return {"max_rel_err": worst, "tolerance": 1e-4, "scene": f"{P} Gaussians {W}x{H}, one view per rank",
-            "collectives_per_backward": vp.stats["collectives"]}
+    used_peer = bool(vp.peer) and any(v is not None for v in vp._peer_states.values())
+    out = {"max_rel_err": worst, "tolerance": 1e-4, "scene": f"{P} Gaussians {W}x{H}, one view per rank, 3 backwards",
+           "nccl_collectives_per_backward": vp.stats["collectives"] // 3, "peer_memory": used_peer,
+           "peer_fallback_reason": vp.peer_error}
+    vp.close()
+    return out
 
 
 def main():
@@ -368,11 +379,12 @@ def main():
         import contextlib
         from sugar_b200 import parallel
         vp = parallel.ViewParallel(sh_factors=not args.no_sh_factors, chunks=args.chunks, side_stream=args.side_stream,
-                                   force=args.force_exchange)
+                                   force=args.force_exchange, peer="auto" if args.peer else False,
+                                   taper=not args.no_taper)
         if dist is not None:
             exchange_check = verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D,
                                              sh_factors=not args.no_sh_factors, chunks=args.chunks,
-                                             side_stream=args.side_stream)
+                                             side_stream=args.side_stream, peer="auto" if args.peer else False)
         stack = contextlib.ExitStack()
         stack.enter_context(vp.context())  # the autograd node keeps the context for the backward thread
 
@@ -473,7 +485,12 @@ def main():
     for _ in range(PRE_ROLL):
         step_device()
 
-    if not use_ref:
+    # per-kernel durations: every launch bracketed by CUDA events on its own stream.  One GPU: inside the timed region
+    # itself (a dozen launches per step).  N > 1: the exchange adds dozens of microsecond-sized launches on side
+    # streams whose bracketing would distort the step, so the timed region runs plain and the SAME steps are repeated
+    # right after it with the bracketing on (same count on every rank: the steps contain collectives / peer flags).
+    profile_in_timed = not use_ref and dist is None
+    if profile_in_timed:
         _lib.profile(True)   # allocates the event pool
         step_device()
         torch.cuda.synchronize()
@@ -482,11 +499,21 @@ def main():
     t_timed0 = time.perf_counter()
     ms = timed(step_device, args.steps)
     t_timed1 = time.perf_counter()
+    launches = 0 if use_ref else int(_lib.lib.sgr_launch_count() - launches0)
     prof = {}
-    if not use_ref:
+    if profile_in_timed:
         prof = _lib.profile_read()
         _lib.profile(False)
-    launches = 0 if use_ref else int(_lib.lib.sgr_launch_count() - launches0)
+    elif not use_ref:
+        _lib.profile(True)
+        step_device()
+        torch.cuda.synchronize()
+        _lib.profile_read()
+        for _ in range(args.steps):
+            step_device()
+        torch.cuda.synchronize()
+        prof = _lib.profile_read()
+        _lib.profile(False)
     for _ in range(POST_ROLL):
         step_device()
     torch.cuda.synchronize()
@@ -515,10 +542,18 @@ def main():
            "parallelism": {"mode": f"view-dp{world}" if world > 1 else "single",
                            "side_stream_finalize": bool(args.side_stream), "forced_exchange": bool(args.force_exchange),
                            "exchange": ("none" if world == 1 else "all-reduce 236 B/Gaussian" if args.no_sh_factors else
-                                        f"inside the backward: all-gather 12 B/Gaussian/view SH factors under the "
-                                        f"per-Gaussian pass + all-reduce 44 B/Gaussian in {args.chunks} overlapped chunks"),
+                                        f"inside the backward, NCCL: all-gather 12 B/Gaussian/view SH factors under the "
+                                        f"per-Gaussian pass + all-reduce 44 B/Gaussian in {args.chunks} overlapped chunks"
+                                        if (not args.peer or not (exchange_check or {}).get("peer_memory")) else
+                                        f"inside the backward, over peer memory (CUDA IPC, no NCCL call): the finalize "
+                                        f"kernel loads every view's 12 B/Gaussian SH factors from its owner GPU; the "
+                                        f"44 B/Gaussian records are reduced by a two-shot P2P kernel in {args.chunks} "
+                                        f"chunks under the per-Gaussian pass; flags in peer memory order the ranks"),
                            "exchange_check": exchange_check},
            "clocks": clk}
+    if not use_ref:
+        out["stage_timing"] = ("CUDA events around every launch inside the timed region" if profile_in_timed else
+                               "CUDA events around every launch in a repeat of the timed steps right after the timed region")
     n_e2e = 1 if use_ref else views_total
     out["e2e"] = {"value": n_e2e / (ms_e2e * 1e-3), "unit": "views/s",
                   "h2d_bytes_per_step": int((dL_h.numel() * 4 + (16 + 16 + 3 + 3) * 4) * len(views)),

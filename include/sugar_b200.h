@@ -145,6 +145,24 @@ typedef struct SgrBackwardPlan {
     int32_t num_chunks;
     float *reduce_records; /* may be NULL */
     float *dL_dsh_rest;    /* raw-parameter mode (SgrGaussians.activations): f32[P,M-1,3], fully written */
+    /* Peer mode (sgr_peer_* below).  When peer_flag_tab is non-NULL the backward signals the peer ranks itself, on
+     * `stream`, with sequence number peer_seq: slot peer_slot_blend once the blend pass is enqueued (dL_dcolors, which
+     * the caller placed in its peer-visible factor block, is final), slot peer_slot_chunk0 + c after chunk c of the
+     * per-Gaussian pass (reduce_records, placed in the peer-visible record array, holds the chunk's rows). */
+    void *const *peer_flag_tab; /* DEVICE array of peer_nranks pointers: every rank's flag words, see sgr_peer_signal */
+    int32_t peer_nranks, peer_rank, peer_slot_blend, peer_slot_chunk0;
+    uint32_t peer_seq;
+    /* With SH colours and dL_dsh non-NULL: peer_view_blocks is a DEVICE array of peer_nranks pointers to the ranks'
+     * factor blocks (f32[3P] dL/dRGB followed by the rank's camera position; entry peer_rank is dL_dcolors itself).
+     * The backward then waits (on `stream`, through peer_flags = this rank's own flag words) until every rank has
+     * signalled peer_slot_blend, and the per-Gaussian pass writes dL_dsh = peer_dsh_scale * SUM over all ranks' views
+     * of their SH gradients, loading the other ranks' factors straight from their memory -- the all-gather of the
+     * factors is fused into the kernel and no separate SH epilogue runs. */
+    const float *const *peer_view_blocks;
+    const void *peer_flags;
+    float peer_dsh_scale;
+    double peer_timeout_s;
+    int32_t chunk_taper; /* 0: equal chunks; else every chunk half the size of the one before it */
 } SgrBackwardPlan;
 SGR_API int sgr_rasterize_backward_staged(const SgrView *view, const SgrGaussians *g, const int32_t *radii,
                                           const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
@@ -153,6 +171,8 @@ SGR_API int sgr_rasterize_backward_staged(const SgrView *view, const SgrGaussian
                                           float *dL_dsh, float *dL_dscales, float *dL_drotations, void *grad_scratch,
                                           void *stream, const SgrBackwardPlan *plan);
 SGR_API int sgr_backward_chunk_range(int32_t P, int32_t num_chunks, int32_t chunk, int32_t *p0, int32_t *p1);
+SGR_API int sgr_backward_chunk_range_tapered(int32_t P, int32_t num_chunks, int32_t chunk, int32_t taper, int32_t *p0,
+                                             int32_t *p1); /* SgrBackwardPlan.chunk_taper */
 
 /* Epilogue of the view-parallel step for the Gaussians [p0, p1), after the exchange (either half optional):
  *  - dL_dsh[P,M,3] rows = sum over views v of basis_k(normalize(mean - campos[v])) * dRGB[v][P,3]  (the SH part of
@@ -166,6 +186,44 @@ SGR_API int sgr_view_grad_finalize(int32_t P, int32_t p0, int32_t p1, int32_t M,
                                    int32_t campos_stride, float *dL_dsh, const float *reduced_records, float scale,
                                    float *dL_dmeans3D, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
                                    void *stream);
+/* The same epilogue reading every view's factor block through a DEVICE-resident table of num_views pointers
+ * (view_blocks[v] -> f32[3P] factors followed by that view's camera position, 3 floats).  The entries may point into
+ * other GPUs' memory mapped with sgr_peer_import: the all-gather of the factors is then fused into this kernel's loads
+ * over NVLink and no gathered copy exists. */
+SGR_API int sgr_view_grad_finalize_peers(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree,
+                                         int32_t num_views, const float *means3D, const float *const *view_blocks,
+                                         float *dL_dsh, const float *reduced_records, float scale, float *dL_dmeans3D,
+                                         float *dL_dopacity, float *dL_dscales, float *dL_drotations, void *stream);
+
+/* ---- View-parallel exchange over peer memory (NVLink / NVSwitch): csrc/sgr_peer.cu.  No counterpart in the reference.
+ * sgr_peer_alloc     one zero-filled device allocation on the current device whose CUDA IPC handle (sgr_peer_export,
+ *                    64 bytes, to be sent to the other ranks by any means) maps it at offset 0;
+ * sgr_peer_import    maps a peer's allocation into this process (lazy peer access); sgr_peer_close unmaps it.
+ * Flag words: the first sgr_peer_flag_bytes() of an allocation used with signal / wait are u32
+ * [SGR_PEER_MAX_SLOTS][SGR_PEER_MAX_RANKS]; word [slot][j] is written by rank j only.
+ * sgr_peer_signal    (on `stream`) writes `seq` into word [slot][my_rank] of EVERY rank's flags (flag_tab: device array
+ *                    of nranks pointers to the ranks' flag words), after a system-scope fence;
+ * sgr_peer_wait      (on `stream`) spins until words [slot0 .. slot0+nslots)[0 .. nranks) of the LOCAL flags have all
+ *                    reached seq (wrap-safe); traps after timeout_s seconds (<= 0: 20 s) instead of hanging;
+ * sgr_peer_reduce_records  two-shot all-reduce of the 44-byte records of the Gaussians [p0, p1) (p0 * 11 floats a
+ *                    multiple of 16 bytes): this rank sums ITS slice of the range over all ranks' record arrays
+ *                    (rec_tab, device array of nranks pointers to f32[11P + 4]) in rank order and stores the sums into
+ *                    every rank's sum array (sum_tab, likewise). */
+#define SGR_PEER_MAX_RANKS 64
+#define SGR_PEER_MAX_SLOTS 64
+SGR_API int sgr_peer_alloc(size_t bytes, void **ptr);
+SGR_API int sgr_peer_free(void *ptr);
+SGR_API int sgr_peer_export(const void *ptr, void *handle64);
+SGR_API int sgr_peer_import(const void *handle64, void **ptr);
+SGR_API int sgr_peer_close(void *ptr);
+SGR_API size_t sgr_peer_flag_bytes(void);
+SGR_API int sgr_peer_signal(void *const *flag_tab, int32_t nranks, int32_t slot, int32_t my_rank, uint32_t seq,
+                            void *stream);
+SGR_API int sgr_peer_wait(const void *flags, int32_t nranks, int32_t slot0, int32_t nslots, uint32_t seq,
+                          double timeout_s, void *stream);
+SGR_API int sgr_peer_reduce_records(const void *const *rec_tab, void *const *sum_tab, int32_t nranks, int32_t my_rank,
+                                    int32_t p0, int32_t p1, void *stream);
+
 /* The SH half alone, over all Gaussians (kept for callers that only exchange factors). */
 SGR_API int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float *means3D,
                                      const float *campos, const float *dRGB, float *dL_dsh, void *stream);

@@ -24,10 +24,11 @@ dist.init_process_group("nccl", device_id=dev)
 from sugar_b200 import diff_gaussian_rasterization as mod, parallel
 scenes = bench.load_scenes()
 res = {}
-for factors in (True, False):
+for factors, peer in ((True, "auto"), (True, False), (False, False)):
     for chunks in (1, 4, 7):
-        r = bench.verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, 3, sh_factors=factors, chunks=chunks)
-        res[f"factors={factors},chunks={chunks}"] = r["max_rel_err"]
+        r = bench.verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, 3, sh_factors=factors, chunks=chunks,
+                                  peer=peer)
+        res[f"factors={factors},peer={r['peer_memory']},chunks={chunks}"] = r["max_rel_err"]
 if rank == 0:
     print(json.dumps({"world": world, "max_rel_err": res}))
 dist.destroy_process_group()

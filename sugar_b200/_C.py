@@ -286,7 +286,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         raise NotImplementedError("raw-parameter mode under a view-parallel exchange: activate in PyTorch instead "
                                   "(the exchange acts on the op's output gradients either way)")
     with torch.cuda.device(dev):
-        b = _alloc_backward(P, M, dev, with_records=ex is not None, split_sh=raw)
+        has_cov = cov3D_precomp is not None and cov3D_precomp.numel() != 0
+        # the peer-memory exchange keeps its records in its own peer-visible buffer
+        b = _alloc_backward(P, M, dev, with_records=ex is not None and not ex.uses_peer_memory(M, has_cov), split_sh=raw)
         if P != 0:
             means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color = map(
                 _c, (means3D, colors, scales, rotations, cov3D_precomp, sh, dL_dout_color))
@@ -309,7 +311,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                 check(lib.sgr_rasterize_backward(*args))
             else:
                 ex.run_backward(lib, check, _lib.STAGE_HOOK, _lib.SgrBackwardPlan, args, b, P, M, int(degree), means3D,
-                                campos, has_cov_precomp=cov3D_precomp is not None and cov3D_precomp.numel() != 0)
+                                campos, has_cov_precomp=has_cov)
     out = (b["means2D"], b["colors"], b["opacity"], b["means3D"], b["cov3D"], b["sh"], b["scales"], b["rotations"])
     return out + (b["sh_rest"],) if raw else out
 

@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char *what)
 static const char *const g_kind_names[K_NUM_KINDS] = {
     "preprocess", "tile_scan", "scatter", "tile_sort_smem", "tile_sort_global", "blend_forward", "blend_backward",
     "preprocess_backward", "field_pack", "field_forward", "field_backward", "field_unpack", "knn_build", "knn_query",
-    "misc"};
+    "misc", "view_finalize", "peer_reduce", "peer_sync"};
 struct ProfRec {
     cudaEvent_t a, b;
     int kind;

@@ -461,6 +461,14 @@ struct PreBwdArgs {
     const float *sh_rest;
     const float4 *rec;  // splat records of the forward: rec[3i+1].z = the activated opacity
     float *dsh_rest;
+    // view-parallel peer mode (csrc/sgr_peer.cu): dsh rows leave as the sum over ALL views' SH gradients.  view_tab is a
+    // device table of nviews pointers to the views' factor blocks (f32[3P] dL/dRGB + the view's camera position at
+    // campos_off), entries of other ranks pointing into THEIR memory over NVLink; view my_view is this launch's own
+    // (its factor is `dcol`).  dsh_scale multiplies every dsh row (1/num_views for a mean over the batch).
+    const float *const *view_tab;
+    int nviews, my_view;
+    size_t campos_off;
+    float dsh_scale;
 };
 
 #define SH_C0 0.28209479177387814f
@@ -479,9 +487,11 @@ struct f3 {
 // (t_k = <sh_k, dL/dRGB> feeds the view-direction gradient) and then overwritten by dL/dsh_k.
 // `dc` is coefficient 0's row of three, `rest` coefficient 1's (one combined row: rest = dc + 3; raw-parameter
 // mode: two arrays).
+template <bool OTHERS = false>
 __device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *dc, float *rest, f3 dir_orig, f3 dRGB,
-                                                    f3 &dmean)
+                                                    f3 &dmean, float out_scale = 1.0f, const float *oacc = nullptr)
 {
+    const f3 dS = {dRGB.x * out_scale, dRGB.y * out_scale, dRGB.z * out_scale};  // x 1.0f is exact
     const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
     const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;
@@ -493,9 +503,15 @@ __device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *dc, f
         ddy += (cy) * t_;                                                              \
         ddz += (cz) * t_;                                                              \
         const float w_ = (w);                                                          \
-        q_[0] = w_ * dRGB.x;                                                           \
-        q_[1] = w_ * dRGB.y;                                                           \
-        q_[2] = w_ * dRGB.z;                                                           \
+        if (OTHERS) { /* the other views' SH gradients of this Gaussian (registers) join the row here */ \
+            q_[0] = fmaf(w_, dS.x, oacc[(k) * 3]);                                     \
+            q_[1] = fmaf(w_, dS.y, oacc[(k) * 3 + 1]);                                 \
+            q_[2] = fmaf(w_, dS.z, oacc[(k) * 3 + 2]);                                 \
+        } else {                                                                       \
+            q_[0] = w_ * dS.x;                                                         \
+            q_[1] = w_ * dS.y;                                                         \
+            q_[2] = w_ * dS.z;                                                         \
+        }                                                                              \
     }
     SHB(0, SH_C0, 0.f, 0.f, 0.f);
     if (deg > 0) {
@@ -535,9 +551,49 @@ __device__ __forceinline__ void sh_backward_inplace(int deg, int M, float *dc, f
     dmean.z += (-o.x * o.z * ddx - o.y * o.z * ddy + (sum2 - o.z * o.z) * ddz) * invsum32;
 }
 
+// Another view's SH gradient of one Gaussian, accumulated in registers: acc[3k + c] += basis_k(normalize(dir)) * g_c
+// (the dL_dsh part of backward.cu:20-139 is this outer product per view).
+__device__ __forceinline__ void sh_accumulate(int deg, float *acc, f3 dir_orig, f3 g)
+{
+    const float inv = 1.0f / sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+    const float x = dir_orig.x * inv, y = dir_orig.y * inv, z = dir_orig.z * inv;
+#define SHA(k, w)                                           \
+    {                                                       \
+        const float w_ = (w);                               \
+        acc[(k) * 3] = fmaf(w_, g.x, acc[(k) * 3]);         \
+        acc[(k) * 3 + 1] = fmaf(w_, g.y, acc[(k) * 3 + 1]); \
+        acc[(k) * 3 + 2] = fmaf(w_, g.z, acc[(k) * 3 + 2]); \
+    }
+    SHA(0, SH_C0);
+    if (deg > 0) {
+        SHA(1, -SH_C1 * y);
+        SHA(2, SH_C1 * z);
+        SHA(3, -SH_C1 * x);
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            SHA(4, b_SH_C2[0] * xy);
+            SHA(5, b_SH_C2[1] * yz);
+            SHA(6, b_SH_C2[2] * (2.f * zz - xx - yy));
+            SHA(7, b_SH_C2[3] * xz);
+            SHA(8, b_SH_C2[4] * (xx - yy));
+            if (deg > 2) {
+                SHA(9, b_SH_C3[0] * y * (3.f * xx - yy));
+                SHA(10, b_SH_C3[1] * xy * z);
+                SHA(11, b_SH_C3[2] * y * (4.f * zz - xx - yy));
+                SHA(12, b_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
+                SHA(13, b_SH_C3[4] * x * (4.f * zz - xx - yy));
+                SHA(14, b_SH_C3[5] * z * (xx - yy));
+                SHA(15, b_SH_C3[6] * x * (xx - 3.f * yy));
+            }
+        }
+    }
+#undef SHA
+}
+
 #ifndef SGR_PB_T
 #define SGR_PB_T 64
 #endif
+constexpr int PB_VB = 7;  // other views whose factors a thread fetches at the top of the kernel (8 ranks: all of them)
 constexpr int PB_T = SGR_PB_T;
 // dynamic shared memory carve-up (floats): inputs, outputs, then the SH block
 constexpr int PB_GACC = 0;                     // PB_T*8
@@ -576,7 +632,8 @@ __device__ __forceinline__ void pb_flush(float *__restrict__ dst, const float *s
     for (int i = threadIdx.x; i < n; i += PB_T) dst[i] = src[i];
 }
 
-template <bool RAW>
+// MULTI (view-parallel peer mode, never with RAW): dsh rows leave as the sum over all views, see PreBwdArgs::view_tab
+template <bool RAW, bool MULTI = false>
 __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdArgs a)
 {
     extern __shared__ __align__(16) float sm[];
@@ -656,6 +713,21 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
     }
     int radius = 0;
     if (tid < n) radius = a.radii[i];
+    // peer mode: the other views' factors of this Gaussian, fetched from their owners' memory (NVLink) while the local
+    // staging is in flight; views beyond the first PB_VB are fetched when they are used
+    float pf[MULTI ? PB_VB : 1][3];
+    const int others = MULTI ? a.nviews - 1 : 0;
+    if (MULTI && tid < n) {
+#pragma unroll
+        for (int u = 0; u < PB_VB; u++) {
+            const int v = u + (u >= a.my_view ? 1 : 0);  // skip this launch's own view
+            const bool on = u < others;
+            const float *g = a.view_tab[on ? v : a.my_view] + (size_t)i * 3;
+            pf[u][0] = on ? __ldcg(g) : 0.f;
+            pf[u][1] = on ? __ldcg(g + 1) : 0.f;
+            pf[u][2] = on ? __ldcg(g + 2) : 0.f;
+        }
+    }
     __syncthreads();
     if (a.in_bulk_ok && full) mbar_wait(&s_bar, 0);
     if (!RAW && a.shs) {
@@ -663,6 +735,35 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
         __syncthreads();
     }
 
+    // peer mode: the other views' SH gradients of this Gaussian, summed in registers (48 accumulators); they join the
+    // row when this view's gradient is written into it (or make up the whole row if the Gaussian is culled here)
+    float oacc[MULTI ? 48 : 1];
+    if (MULTI && tid < n) {
+#pragma unroll
+        for (int k = 0; k < 48; k++) oacc[k] = 0.f;
+        const float mx = sm[PB_MEANS + tid * 3], my = sm[PB_MEANS + tid * 3 + 1], mz = sm[PB_MEANS + tid * 3 + 2];
+        for (int u0 = 0; u0 < others; u0 += PB_VB) {
+            if (u0) {
+#pragma unroll
+                for (int u = 0; u < PB_VB; u++) {
+                    const int uu = u0 + u, v = uu + (uu >= a.my_view ? 1 : 0);
+                    const bool on = uu < others;
+                    const float *g = a.view_tab[on ? v : a.my_view] + (size_t)i * 3;
+                    pf[u][0] = on ? __ldcg(g) : 0.f;
+                    pf[u][1] = on ? __ldcg(g + 1) : 0.f;
+                    pf[u][2] = on ? __ldcg(g + 2) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PB_VB; u++) {
+                const f3 g = {pf[u][0] * a.dsh_scale, pf[u][1] * a.dsh_scale, pf[u][2] * a.dsh_scale};
+                if (g.x == 0.f && g.y == 0.f && g.z == 0.f) continue;  // not visible in that view (or past the last view)
+                const int uu = u0 + u, v = uu + (uu >= a.my_view ? 1 : 0);
+                const float *cp = a.view_tab[v] + a.campos_off;
+                sh_accumulate(a.v.D, oacc, {mx - __ldg(cp), my - __ldg(cp + 1), mz - __ldg(cp + 2)}, g);
+            }
+        }
+    }
     if (tid < n) {
         const bool vis = radius > 0;
         // the 11 all-reduce-bound outputs: four arrays, or one 44-byte record per Gaussian (stride 11: conflict-free)
@@ -682,7 +783,14 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             o_scl[0] = o_scl[1] = o_scl[2] = 0.f;
             o_rot[0] = o_rot[1] = o_rot[2] = o_rot[3] = 0.f;
             if (a.shs && a.dsh) {
-                for (int k = 0; k < row_f; k++) row[k] = 0.f;
+                if (MULTI) {
+#pragma unroll
+                    for (int k = 0; k < 48; k++)
+                        if (k < row_f) row[k] = oacc[k];
+                    for (int k = 48; k < row_f; k++) row[k] = 0.f;
+                } else {
+                    for (int k = 0; k < row_f; k++) row[k] = 0.f;
+                }
                 if (RAW) sm[PB_SHDC + tid * 3] = sm[PB_SHDC + tid * 3 + 1] = sm[PB_SHDC + tid * 3 + 2] = 0.f;
             }
         } else {
@@ -795,8 +903,9 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
                 // accumulated dL/dRGB, already masked where the forward clamped the colour
                 const f3 dRGB = {sm[PB_DCOL + tid * 3], sm[PB_DCOL + tid * 3 + 1], sm[PB_DCOL + tid * 3 + 2]};
                 const float *cp = a.v.campos;
-                sh_backward_inplace(a.v.D, M, RAW ? sm + PB_SHDC + tid * 3 : row, RAW ? row : row + 3,
-                                    {mx - cp[0], my - cp[1], mz - cp[2]}, dRGB, dmean);
+                sh_backward_inplace<MULTI>(a.v.D, M, RAW ? sm + PB_SHDC + tid * 3 : row, RAW ? row : row + 3,
+                                           {mx - cp[0], my - cp[1], mz - cp[2]}, dRGB, dmean,
+                                           MULTI ? a.dsh_scale : 1.0f, oacc);
             }
             o_m3d[0] = dmean.x;
             o_m3d[1] = dmean.y;
@@ -934,6 +1043,14 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
 //    the four gradient arrays autograd expects.
 // Either half is optional.
 // ------------------------------------------------------------------------------------------------
+// Where view v's factor block [P,3] starts: a slice of one gathered buffer (base + v * stride), or -- peer mode -- an
+// entry of a device-resident pointer table whose entries may point into OTHER GPUs' memory (CUDA IPC mappings over
+// NVLink): the all-gather is then fused into this kernel's loads and no gathered copy exists.
+__device__ __forceinline__ const float *view_block(const float *base, size_t stride, const float *const *tab, int v)
+{
+    return tab ? tab[v] : base + (size_t)v * stride;
+}
+
 constexpr int SF_T = 256;  // 64 Gaussians per CTA, four threads each
 #ifndef SGR_SF_VB
 #define SGR_SF_VB 4
@@ -950,7 +1067,8 @@ __global__ void __launch_bounds__(SF_T) view_grad_finalize_m16_kernel(int p0, in
                                                                        const float *__restrict__ means,
                                                                        const float *__restrict__ campos, int campos_stride,
                                                                        const float *__restrict__ dRGB, size_t view_stride,
-                                                                       float *__restrict__ dsh,
+                                                                       const float *const *__restrict__ view_tab,
+                                                                       size_t campos_off, float *__restrict__ dsh,
                                                                        const float *__restrict__ rec11, float scale,
                                                                        float *__restrict__ dmeans3D,
                                                                        float *__restrict__ dopacity,
@@ -979,7 +1097,7 @@ __global__ void __launch_bounds__(SF_T) view_grad_finalize_m16_kernel(int p0, in
 #pragma unroll
         for (int u = 0; u < SF_VB; u++) {
             const bool on = u < nviews;
-            const float *g = dRGB + (size_t)(on ? u : 0) * view_stride + (size_t)i * 3;
+            const float *g = view_block(dRGB, view_stride, view_tab, on ? u : 0) + (size_t)i * 3;
             gv[u][0] = on ? __ldcs(g) : 0.f;
             gv[u][1] = on ? __ldcs(g + 1) : 0.f;
             gv[u][2] = on ? __ldcs(g + 2) : 0.f;
@@ -1010,7 +1128,7 @@ __global__ void __launch_bounds__(SF_T) view_grad_finalize_m16_kernel(int p0, in
 #pragma unroll
             for (int u = 0; u < SF_VB; u++) {
                 const bool on = v0 + u < nviews;
-                const float *g = dRGB + (size_t)(on ? v0 + u : v0) * view_stride + (size_t)i * 3;
+                const float *g = view_block(dRGB, view_stride, view_tab, on ? v0 + u : v0) + (size_t)i * 3;
                 gv[u][0] = on ? __ldcs(g) : 0.f;
                 gv[u][1] = on ? __ldcs(g + 1) : 0.f;
                 gv[u][2] = on ? __ldcs(g + 2) : 0.f;
@@ -1020,7 +1138,7 @@ __global__ void __launch_bounds__(SF_T) view_grad_finalize_m16_kernel(int p0, in
         for (int u = 0; u < SF_VB; u++) {
             const float gr = gv[u][0] * scale, gg = gv[u][1] * scale, gb = gv[u][2] * scale;
             if (gr == 0.f && gg == 0.f && gb == 0.f) continue;  // not visible in this view (or past the last view)
-            const float *cp = campos + (size_t)(v0 + u) * campos_stride;
+            const float *cp = view_tab ? view_tab[v0 + u] + campos_off : campos + (size_t)(v0 + u) * campos_stride;
             const float ox = mx - __ldg(cp), oy = my - __ldg(cp + 1), oz = mz - __ldg(cp + 2);
             const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
             const float x = ox * inv, y = oy * inv, z = oz * inv;
@@ -1074,7 +1192,8 @@ __global__ void __launch_bounds__(SFG_T) view_grad_finalize_kernel(int p0, int p
                                                                    const float *__restrict__ means,
                                                                    const float *__restrict__ campos, int campos_stride,
                                                                    const float *__restrict__ dRGB, size_t view_stride,
-                                                                   float *__restrict__ dsh,
+                                                                   const float *const *__restrict__ view_tab,
+                                                                   size_t campos_off, float *__restrict__ dsh,
                                                                    const float *__restrict__ rec11, float scale,
                                                                    float *__restrict__ dmeans3D, float *__restrict__ dopacity,
                                                                    float *__restrict__ dscales, float *__restrict__ drots)
@@ -1108,10 +1227,10 @@ __global__ void __launch_bounds__(SFG_T) view_grad_finalize_kernel(int p0, int p
     if (tid < n) {
         const float mx = means[3 * (size_t)i], my = means[3 * (size_t)i + 1], mz = means[3 * (size_t)i + 2];
         for (int v = 0; v < nviews; v++) {
-            const float *g = dRGB + (size_t)v * view_stride + (size_t)i * 3;
+            const float *g = view_block(dRGB, view_stride, view_tab, v) + (size_t)i * 3;
             const float gr = g[0] * scale, gg = g[1] * scale, gb = g[2] * scale;
             if (gr == 0.f && gg == 0.f && gb == 0.f) continue;  // not visible in this view
-            const float *cp = campos + (size_t)v * campos_stride;
+            const float *cp = view_tab ? view_tab[v] + campos_off : campos + (size_t)v * campos_stride;
             const float ox = mx - cp[0], oy = my - cp[1], oz = mz - cp[2];
             const float inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
             const float x = ox * inv, y = oy * inv, z = oz * inv;
@@ -1166,6 +1285,23 @@ __global__ void __launch_bounds__(SFG_T) view_grad_finalize_kernel(int p0, int p
     }
 }
 
+// CTA range [b0, b1) of chunk c of the per-Gaussian pass.  taper == 0: equal chunks.  taper != 0: every chunk half the size
+// of the one before it (weights 2^(n-1-c)), so that what a caller does with a finished chunk while the next one is
+// computed (the peer exchange: reduce + split) is matched by that next chunk's shorter run, and little is left after the
+// last, smallest chunk.
+static void chunk_blocks(int blocks, int nchunks, int c, int taper, int *b0, int *b1)
+{
+    if (!taper || nchunks > 30) {
+        *b0 = (int)((int64_t)blocks * c / nchunks);
+        *b1 = (int)((int64_t)blocks * (c + 1) / nchunks);
+        return;
+    }
+    const int64_t full = ((int64_t)1 << nchunks) - 1;
+    auto edge = [&](int k) { return (int)((int64_t)blocks * ((((int64_t)1 << nchunks) - ((int64_t)1 << (nchunks - k)))) / full); };
+    *b0 = edge(c);
+    *b1 = c + 1 == nchunks ? blocks : edge(c + 1);
+}
+
 int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *radii, const void *geom_buffer,
                     const void *binning_buffer, const void *image_buffer, int64_t num_rendered,
                     const float *dL_dout_color, float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity,
@@ -1198,6 +1334,8 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
                                           200 * 1024));
             SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           200 * 1024));
+            SGR_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<false, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
     }
@@ -1217,6 +1355,22 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     }
     // dL_dcolors is final here (with SH colours: the clamp-masked dL/dRGB, i.e. this view's SH factor)
     if (hook) hook(hook_ctx, SGR_STAGE_BLEND_DONE);
+    const bool peer = plan && plan->peer_flag_tab;
+    if (peer) {
+        int rc = sgr_peer_signal(plan->peer_flag_tab, plan->peer_nranks, plan->peer_slot_blend, plan->peer_rank,
+                                 plan->peer_seq, st);
+        if (rc) return rc;
+        if (plan->peer_view_blocks && dL_dsh && g->shs) {
+            // the per-Gaussian pass sums every view's SH gradient into dL_dsh: the peers' factor blocks must be final
+            if (g->activations != 0 || !plan->peer_flags) {
+                set_error("peer_view_blocks: needs peer_flags and activated (not raw) parameters");
+                return SGR_EINVAL;
+            }
+            rc = sgr_peer_wait(plan->peer_flags, plan->peer_nranks, plan->peer_slot_blend, 1, plan->peer_seq,
+                               plan->peer_timeout_s, st);
+            if (rc) return rc;
+        }
+    }
     PreBwdArgs a;
     a.means = g->means3D;
     a.scales = g->scales;
@@ -1250,7 +1404,18 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     a.dscales = dL_dscales;
     a.drots = dL_drotations;
     a.rec11 = rec11;
+    a.view_tab = nullptr;
+    a.nviews = 1;
+    a.my_view = 0;
+    a.campos_off = (size_t)3 * P;
+    a.dsh_scale = 1.0f;
     const bool raw = g->activations != 0;
+    if (peer && plan->peer_view_blocks && dL_dsh && g->shs) {
+        a.view_tab = (const float *const *)plan->peer_view_blocks;
+        a.nviews = plan->peer_nranks;
+        a.my_view = plan->peer_rank;
+        a.dsh_scale = plan->peer_dsh_scale;
+    }
     a.sh_rest = g->sh_rest;
     a.rec = geom.rec;
     a.dsh_rest = plan ? plan->dL_dsh_rest : nullptr;
@@ -1288,14 +1453,21 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     const int blocks = (P + PB_T - 1) / PB_T;
     if (nchunks > blocks) nchunks = blocks;
     for (int c = 0; c < nchunks; c++) {
-        const int b0 = (int)((int64_t)blocks * c / nchunks), b1 = (int)((int64_t)blocks * (c + 1) / nchunks);
+        int b0, b1;
+        chunk_blocks(blocks, nchunks, c, plan ? plan->chunk_taper : 0, &b0, &b1);
         a.p0 = b0 * PB_T;
         a.p1 = min(P, b1 * PB_T);
         if (b1 > b0)
             SGR_LAUNCH(K_PRE_BWD, st,
                        if (raw) preprocess_backward_kernel<true><<<b1 - b0, PB_T, dyn, st>>>(a);
+                       else if (a.view_tab) preprocess_backward_kernel<false, true><<<b1 - b0, PB_T, dyn, st>>>(a);
                        else preprocess_backward_kernel<false><<<b1 - b0, PB_T, dyn, st>>>(a));
         if (hook) hook(hook_ctx, SGR_STAGE_CHUNK_DONE + c);
+        if (peer) {
+            const int rc = sgr_peer_signal(plan->peer_flag_tab, plan->peer_nranks, plan->peer_slot_chunk0 + c,
+                                           plan->peer_rank, plan->peer_seq, st);
+            if (rc) return rc;
+        }
     }
     SGR_CUDA(cudaGetLastError());
     if (view->debug) SGR_CUDA(cudaStreamSynchronize(st));
@@ -1304,7 +1476,8 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
 
 }  // namespace sgr
 
-extern "C" int sgr_backward_chunk_range(int32_t P, int32_t num_chunks, int32_t chunk, int32_t *p0, int32_t *p1)
+extern "C" int sgr_backward_chunk_range_tapered(int32_t P, int32_t num_chunks, int32_t chunk, int32_t taper, int32_t *p0,
+                                                int32_t *p1)
 {
     using namespace sgr;
     if (P < 0 || num_chunks < 1 || chunk < 0 || chunk >= num_chunks || !p0 || !p1) {
@@ -1317,12 +1490,59 @@ extern "C" int sgr_backward_chunk_range(int32_t P, int32_t num_chunks, int32_t c
         *p0 = *p1 = P;
         return SGR_OK;
     }
-    *p0 = (int)((int64_t)blocks * chunk / nchunks) * PB_T;
-    *p1 = (int)((int64_t)blocks * (chunk + 1) / nchunks) * PB_T;
+    int b0, b1;
+    chunk_blocks(blocks, nchunks, chunk, taper, &b0, &b1);
+    *p0 = b0 * PB_T;
+    *p1 = b1 * PB_T;
     if (*p1 > P) *p1 = P;
     if (*p0 > P) *p0 = P;
     return SGR_OK;
 }
+
+extern "C" int sgr_backward_chunk_range(int32_t P, int32_t num_chunks, int32_t chunk, int32_t *p0, int32_t *p1)
+{
+    return sgr_backward_chunk_range_tapered(P, num_chunks, chunk, 0, p0, p1);
+}
+
+namespace sgr {
+static int finalize_impl(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree, int32_t num_views,
+                         const float *means3D, const float *campos, const float *dRGB, int64_t view_stride,
+                         int32_t campos_stride, const float *const *view_tab, float *dL_dsh, const float *reduced_records,
+                         float scale, float *dL_dmeans3D, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
+                         void *stream, const char *who)
+{
+    const bool sh = dL_dsh != nullptr, rec = reduced_records != nullptr;
+    const bool src_ok = view_tab ? true : (campos && dRGB && view_stride >= (int64_t)3 * P && campos_stride >= 3);
+    if (P < 0 || p0 < 0 || p1 < p0 || p1 > P || (!sh && !rec) ||
+        (sh && (M <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M || num_views <= 0 ||
+                !means3D || !src_ok)) ||
+        (rec && (!dL_dmeans3D || !dL_dopacity || !dL_dscales || !dL_drotations))) {
+        set_error(who);
+        return SGR_EINVAL;
+    }
+    if (p1 == p0) return SGR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t campos_off = (size_t)3 * P;  // peer mode: a view's camera position follows its [P,3] factors
+    const bool al16 = (((uintptr_t)dL_dsh | (uintptr_t)dL_drotations) & 15u) == 0;
+    if ((!sh || M == 16) && al16) {
+        const int threads = (p1 - p0) * 4;
+        SGR_LAUNCH(K_FINALIZE, st,
+                   view_grad_finalize_m16_kernel<<<(threads + SF_T - 1) / SF_T, SF_T, 0, st>>>(
+                       p0, p1, sh_degree, num_views, means3D, campos, campos_stride, dRGB, (size_t)view_stride, view_tab,
+                       campos_off, dL_dsh, reduced_records, scale, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations));
+    } else {
+        const int row_f = M * 3, stride = (row_f & 1) ? row_f : row_f + 1;
+        const size_t dyn = sh ? (size_t)SFG_T * stride * sizeof(float) : 0;
+        SGR_LAUNCH(K_FINALIZE, st,
+                   view_grad_finalize_kernel<<<(p1 - p0 + SFG_T - 1) / SFG_T, SFG_T, dyn, st>>>(
+                       p0, p1, P, M, sh_degree, num_views, means3D, campos, campos_stride, dRGB, (size_t)view_stride,
+                       view_tab, campos_off, dL_dsh, reduced_records, scale, dL_dmeans3D, dL_dopacity, dL_dscales,
+                       dL_drotations));
+    }
+    SGR_CUDA(cudaGetLastError());
+    return SGR_OK;
+}
+}  // namespace sgr
 
 extern "C" int sgr_view_grad_finalize(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree, int32_t num_views,
                                       const float *means3D, const float *campos, const float *dRGB, int64_t view_stride,
@@ -1330,34 +1550,23 @@ extern "C" int sgr_view_grad_finalize(int32_t P, int32_t p0, int32_t p1, int32_t
                                       float *dL_dmeans3D, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
                                       void *stream)
 {
-    using namespace sgr;
-    const bool sh = dL_dsh != nullptr, rec = reduced_records != nullptr;
-    if (P < 0 || p0 < 0 || p1 < p0 || p1 > P || (!sh && !rec) ||
-        (sh && (M <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M || num_views <= 0 ||
-                !means3D || !campos || !dRGB || view_stride < (int64_t)3 * P || campos_stride < 3)) ||
-        (rec && (!dL_dmeans3D || !dL_dopacity || !dL_dscales || !dL_drotations))) {
-        set_error("bad arguments to sgr_view_grad_finalize");
+    return sgr::finalize_impl(P, p0, p1, M, sh_degree, num_views, means3D, campos, dRGB, view_stride, campos_stride, nullptr,
+                              dL_dsh, reduced_records, scale, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations, stream,
+                              "bad arguments to sgr_view_grad_finalize");
+}
+
+extern "C" int sgr_view_grad_finalize_peers(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree,
+                                            int32_t num_views, const float *means3D, const float *const *view_blocks,
+                                            float *dL_dsh, const float *reduced_records, float scale, float *dL_dmeans3D,
+                                            float *dL_dopacity, float *dL_dscales, float *dL_drotations, void *stream)
+{
+    if (dL_dsh && !view_blocks) {
+        sgr::set_error("bad arguments to sgr_view_grad_finalize_peers");
         return SGR_EINVAL;
     }
-    if (p1 == p0) return SGR_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool al16 = (((uintptr_t)dL_dsh | (uintptr_t)dL_drotations) & 15u) == 0;
-    if ((!sh || M == 16) && al16) {
-        const int threads = (p1 - p0) * 4;
-        SGR_LAUNCH(K_MISC, st,
-                   view_grad_finalize_m16_kernel<<<(threads + SF_T - 1) / SF_T, SF_T, 0, st>>>(
-                       p0, p1, sh_degree, num_views, means3D, campos, campos_stride, dRGB, (size_t)view_stride, dL_dsh,
-                       reduced_records, scale, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations));
-    } else {
-        const int row_f = M * 3, stride = (row_f & 1) ? row_f : row_f + 1;
-        const size_t dyn = sh ? (size_t)SFG_T * stride * sizeof(float) : 0;
-        SGR_LAUNCH(K_MISC, st,
-                   view_grad_finalize_kernel<<<(p1 - p0 + SFG_T - 1) / SFG_T, SFG_T, dyn, st>>>(
-                       p0, p1, P, M, sh_degree, num_views, means3D, campos, campos_stride, dRGB, (size_t)view_stride, dL_dsh,
-                       reduced_records, scale, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations));
-    }
-    SGR_CUDA(cudaGetLastError());
-    return SGR_OK;
+    return sgr::finalize_impl(P, p0, p1, M, sh_degree, num_views, means3D, nullptr, nullptr, 0, 0, view_blocks, dL_dsh,
+                              reduced_records, scale, dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations, stream,
+                              "bad arguments to sgr_view_grad_finalize_peers");
 }
 
 extern "C" int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float *means3D,

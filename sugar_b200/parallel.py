@@ -38,6 +38,7 @@ of leaf gradients after the backward (236 B/Gaussian, not overlapped).
 """
 import contextlib
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -77,6 +78,76 @@ def reduce_grad(t: torch.Tensor, scale: float = 1.0, group=None) -> torch.Tensor
     return _ReduceGrad.apply(t, scale, group)
 
 
+_SLOT_BLEND, _SLOT_CHUNK0, _SLOT_REDUCED0, _PEER_MAX_CHUNKS = 0, 1, 17, 16   # flag slots (csrc/sgr_peer.cu)
+_PEER_SERIAL = os.environ.get("SGR_PEER_SERIAL", "0") == "1"                 # diagnostics (scripts/timeline_peer.py)
+_PEER_LOCAL_FACTORS = os.environ.get("SGR_PEER_LOCAL_FACTORS", "0") == "1"
+
+
+class _DevMem:
+    """A raw device range as seen by torch.as_tensor (the CUDA array interface)."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class _PeerState:
+    """One rank's peer-visible exchange buffer for P Gaussians and the mappings of the other ranks' buffers
+    (layout: csrc/sgr_peer.cu).  Building it is collective (the IPC handles travel in one all-gather)."""
+
+    def __init__(self, lib, check, P, rank, world, group, dev):
+        self.P, self.rank, self.world, self.dev, self.seq = P, rank, world, dev, 0
+        up = lambda n: (n + 255) // 256 * 256
+        fl, fb, rb = int(lib.sgr_peer_flag_bytes()), up(4 * (3 * P + 4)), up(4 * 11 * P + 64)
+        off = {"flags": 0, "F0": fl, "F1": fl + fb, "R": fl + 2 * fb, "S": fl + 2 * fb + rb}
+        total = fl + 2 * fb + 2 * rb
+        self.imported = []
+        with torch.cuda.device(dev):
+            base = C.c_void_p()
+            check(lib.sgr_peer_alloc(total, C.byref(base)))
+            self.base = base.value
+            handle = (C.c_ubyte * 64)()
+            check(lib.sgr_peer_export(self.base, handle))
+            bases = [self.base]
+            if world > 1:
+                mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+                every = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(every, mine, group=group)
+                every = every.cpu()
+                bases = []
+                for j in range(world):
+                    if j == rank:
+                        bases.append(self.base)
+                        continue
+                    h = (C.c_ubyte * 64)(*every[j].tolist())
+                    q = C.c_void_p()
+                    check(lib.sgr_peer_import(h, C.byref(q)))
+                    self.imported.append(q.value)
+                    bases.append(q.value)
+            tab = lambda name: torch.tensor([b + off[name] for b in bases], dtype=torch.int64, device=dev)
+            self.flag_tab, self.R_tab, self.S_tab = tab("flags"), tab("R"), tab("S")
+            self.F_tab = [tab("F0"), tab("F1")]
+            if _PEER_LOCAL_FACTORS:   # diagnostic (WRONG gradients): every "peer" factor block is this rank's own
+                self.F_tab = [torch.tensor([self.base + off[k]] * world, dtype=torch.int64, device=dev) for k in ("F0", "F1")]
+            self.flags_ptr, self.R_ptr, self.S_ptr = self.base, self.base + off["R"], self.base + off["S"]
+            self.F_local = [torch.as_tensor(_DevMem(self.base + off[k], 3 * P + 4), device=dev) for k in ("F0", "F1")]
+            torch.cuda.synchronize(dev)
+        self._streams = None
+
+    def streams(self, dev):
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Event())
+        return self._streams
+
+    def close(self, lib):
+        for q in self.imported:
+            lib.sgr_peer_close(q)
+        self.imported = []
+        self.F_local = []
+        if self.base:
+            lib.sgr_peer_free(self.base)
+            self.base = 0
+
+
 class ViewParallel:
     """Exchange state of one model's view-parallel step (see the module docstring).
 
@@ -89,10 +160,14 @@ class ViewParallel:
     """
 
     def __init__(self, sh_factors: bool = True, chunks: int = 4, scale: float = 1.0, group=None, force: bool = False,
-                 side_stream: bool = False):
+                 side_stream: bool = False, peer=False, peer_timeout_s: float = 20.0, taper: bool = True):
         from . import _C
         self.sh_factors, self.chunks, self.scale, self.group, self.force = bool(sh_factors), int(chunks), float(scale), group, force
         self.side_stream = bool(side_stream)
+        self.peer, self.peer_timeout_s, self.taper = peer, float(peer_timeout_s), bool(taper)
+        self.peer_error = None   # why "auto" fell back to the NCCL exchange, if it did
+        self._peer_states = {}   # (P, device) -> _PeerState
+        self._emulated = ()      # tests: other ranks whose record slices this process reduces as well (see tests/test_gpu_parallel.py)
         self._side = {}     # device -> (stream, [events])
         self.ctx = _C.Context()
         self.ctx.exchange = self
@@ -108,19 +183,30 @@ class ViewParallel:
     def enabled(self) -> bool:
         return self.force or _world(self.group) > 1
 
+    def uses_peer_memory(self, M: int, has_cov_precomp: bool) -> bool:
+        """Peer mode serves the common case: SH colours exchanged as factors, covariances computed in the op."""
+        return bool(self.peer) and bool(M) and self.sh_factors and not has_cov_precomp and self.chunks <= _PEER_MAX_CHUNKS
+
     # -- the exchange, driven from _C.rasterize_gaussians_backward ------------------------------------------
     def run_backward(self, lib, check, stage_hook_type, plan_type, args, bufs, P, M, degree, means3D, campos,
                      has_cov_precomp):
         """`args`: the positional arguments of sgr_rasterize_backward_staged without the trailing plan;
         `bufs`: dict of the gradient tensors + "records" f32[P,11].  Returns nothing: bufs hold the reduced
         gradients when the enqueued work completes."""
+        if self.uses_peer_memory(M, has_cov_precomp):
+            st = self._peer_state(lib, check, P, means3D.device)
+            if st is not None:
+                return self._run_backward_peer(st, lib, check, stage_hook_type, plan_type, args, bufs, P, M, degree,
+                                               means3D, campos)
+        if "records" not in bufs:   # "auto" just fell back to the NCCL exchange: the arena was sized for peer mode
+            bufs["records"] = torch.empty((P, 11), dtype=torch.float32, device=means3D.device)
         world = _world(self.group)
         multi = world > 1
         dev = means3D.device
         factor = bool(M) and self.sh_factors
         nchunks = max(1, self.chunks)
-        if getattr(self, "_ranges_key", None) != (P, nchunks):
-            self._ranges_key, self._ranges = (P, nchunks), [self._range(lib, check, P, nchunks, c) for c in range(nchunks)]
+        if getattr(self, "_ranges_key", None) != (P, nchunks, 0):
+            self._ranges_key, self._ranges = (P, nchunks, 0), [self._range(lib, check, P, nchunks, c) for c in range(nchunks)]
         ranges = self._ranges
         pending = {c: [] for c in range(nchunks)}
         early = []
@@ -198,6 +284,95 @@ class ViewParallel:
         self.stats["backwards"] += 1
         self.stats["collectives"] += len(early) + sum(len(v) for v in pending.values())
 
+    # -- the exchange over peer memory (csrc/sgr_peer.cu): no NCCL call, no host callback in a backward ---------
+    def _peer_state(self, lib, check, P, dev):
+        key = (P, dev)
+        if key not in self._peer_states:
+            world = _world(self.group)
+            rank = dist.get_rank(self.group) if world > 1 else 0
+            st, err = None, None
+            try:
+                st = _PeerState(lib, check, P, rank, world, self.group, dev)
+            except Exception as e:  # no IPC / no peer access on this box: every rank must take the same branch
+                err = e
+            if world > 1:
+                ok = torch.tensor([0 if st is None else 1], device=dev, dtype=torch.int32)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+                if int(ok.item()) == 0:
+                    if st is not None:
+                        st.close(lib)
+                    st = None
+            if st is None:
+                if self.peer != "auto":
+                    raise RuntimeError(f"peer-memory exchange unavailable: {err!r}")
+                self.peer, self.peer_error = False, repr(err) if err else "a peer rank could not map the buffers"
+            self._peer_states[key] = st
+        return self._peer_states[key]
+
+    def _run_backward_peer(self, st, lib, check, stage_hook_type, plan_type, args, bufs, P, M, degree, means3D, campos):
+        dev = means3D.device
+        world, rank = st.world, st.rank
+        nchunks = max(1, self.chunks)
+        taper = int(self.taper)
+        if getattr(self, "_ranges_key", None) != (P, nchunks, taper):
+            self._ranges_key = (P, nchunks, taper)
+            self._ranges = [self._range(lib, check, P, nchunks, c, taper) for c in range(nchunks)]
+        ranges = [(c, r) for c, r in enumerate(self._ranges) if r[1] > r[0]]   # the chunks the op really launches
+        st.seq += 1
+        seq, par = st.seq, st.seq & 1
+        main = torch.cuda.current_stream(dev)
+        B, ev = st.streams(dev)
+        if _PEER_SERIAL:     # diagnostic: everything on the caller's stream (isolated kernel durations)
+            B = main
+        F = st.F_local[par]
+        F[3 * P:3 * P + 3].copy_(campos.reshape(3))     # the camera position rides behind the factors
+        ev.record(main)                                  # the side stream starts no earlier than this backward
+        args = list(args)
+        args[9] = F.data_ptr()       # dL_dcolors: the blend pass accumulates straight into the peer-visible factor block
+        args[13] = bufs["sh"].data_ptr()                 # dL_dsh: written by the per-Gaussian pass, summed over ALL views
+        # main stream, all inside the C call: blend -> signal(BLEND) -> wait(BLEND, every rank) -> per-Gaussian pass in
+        # chunks, which loads the other ranks' factors over NVLink and writes the summed dL_dsh and this rank's 44-byte
+        # records (into the peer-visible R) -> signal(CHUNK c) after each chunk
+        plan = plan_type(stage_hook_type(0), None, nchunks, st.R_ptr, None, st.flag_tab.data_ptr(), world, rank,
+                         _SLOT_BLEND, _SLOT_CHUNK0, seq, st.F_tab[par].data_ptr(), st.flags_ptr, self.scale,
+                         self.peer_timeout_s, taper)
+        check(lib.sgr_rasterize_backward_staged(*args, C.byref(plan)))
+        tmo, flags, mp = self.peer_timeout_s, st.flags_ptr, means3D.data_ptr()
+        # side stream: two-shot all-reduce of the records chunk by chunk, underneath the per-Gaussian pass of the later
+        # chunks; the split of chunk c-1 runs behind the reduce of chunk c, so the peers' slices of c-1 have landed by
+        # then and only the last chunk's reduce + split is exposed
+        B.wait_event(ev)
+
+        def split(c, p0, p1):
+            check(lib.sgr_peer_wait(flags, world, _SLOT_REDUCED0 + c, 1, seq, tmo, B.cuda_stream))
+            check(lib.sgr_view_grad_finalize_peers(P, p0, p1, M, degree, world, mp, None, None, st.S_ptr, self.scale,
+                                                   bufs["means3D"].data_ptr(), bufs["opacity"].data_ptr(),
+                                                   bufs["scales"].data_ptr(), bufs["rotations"].data_ptr(), B.cuda_stream))
+        prev = None
+        for c, (p0, p1) in ranges:
+            check(lib.sgr_peer_wait(flags, world, _SLOT_CHUNK0 + c, 1, seq, tmo, B.cuda_stream))
+            for r in (rank,) + tuple(self._emulated):
+                check(lib.sgr_peer_reduce_records(st.R_tab.data_ptr(), st.S_tab.data_ptr(), world, r, p0, p1, B.cuda_stream))
+            check(lib.sgr_peer_signal(st.flag_tab.data_ptr(), world, _SLOT_REDUCED0 + c, rank, seq, B.cuda_stream))
+            if prev is not None:
+                split(*prev)
+            prev = (c, p0, p1)
+        if prev is not None:
+            split(*prev)
+        main.wait_stream(B)
+        self.stats["backwards"] += 1
+
+    def close(self):
+        """Unmap / free the peer buffers (collective: every rank calls it).  Optional -- process exit does the same."""
+        from ._lib import lib
+        for st in self._peer_states.values():
+            if st is not None:
+                torch.cuda.synchronize(st.dev)
+                if st.world > 1:
+                    dist.barrier(group=self.group)
+                st.close(lib)
+        self._peer_states = {}
+
     def _gather_buffer(self, world, stride, dev):
         """[world, 3P+4] receive buffer of the factor all-gather, kept across backwards (its readers, the finalize
         kernels, are enqueued on the compute stream before the next backward's gather is)."""
@@ -207,9 +382,9 @@ class ViewParallel:
         return self._gather
 
     @staticmethod
-    def _range(lib, check, P, nchunks, c):
+    def _range(lib, check, P, nchunks, c, taper=0):
         p0, p1 = C.c_int32(0), C.c_int32(0)
-        check(lib.sgr_backward_chunk_range(P, nchunks, c, C.byref(p0), C.byref(p1)))
+        check(lib.sgr_backward_chunk_range_tapered(P, nchunks, c, taper, C.byref(p0), C.byref(p1)))
         return p0.value, p1.value
 
 

@@ -30,7 +30,8 @@ def _render_loss(mod, t, sc, dL, deg, ps, bg=(0.1, 0.2, 0.3), colors=None):
 @pytest.mark.parametrize("deg,chunks,factors,side", [(3, 4, True, False), (1, 3, True, False), (0, 1, True, False),
                                                      (3, 4, False, False), (2, 7, True, False), (3, 4, True, True),
                                                      (2, 3, False, True)])
-def test_forced_exchange_matches_plain_backward(deg, chunks, factors, side):
+@pytest.mark.parametrize("peer", [True, False])
+def test_forced_exchange_matches_plain_backward(deg, chunks, factors, side, peer):
     import torch
     from sugar_b200 import diff_gaussian_rasterization as mod
     from sugar_b200 import parallel, scenes
@@ -43,12 +44,17 @@ def test_forced_exchange_matches_plain_backward(deg, chunks, factors, side):
     ps_a = {k: leaf(t[k]) for k in names}
     loss, m2a = _render_loss(mod, t, sc, dL, deg, ps_a)
     loss.backward()
-    vp = parallel.ViewParallel(sh_factors=factors, chunks=chunks, scale=0.5, force=True, side_stream=side)
-    ps_b = {k: leaf(t[k]) for k in names}
-    with vp.context():
-        loss, m2b = _render_loss(mod, t, sc, dL, deg, ps_b)
-        loss.backward()
-    assert vp.stats["backwards"] == 1
+    # peer=True: the peer-memory exchange (csrc/sgr_peer.cu) with this GPU as its only rank -- flags, two-shot
+    # record reduce, pointer-table finalize, both side streams
+    vp = parallel.ViewParallel(sh_factors=factors, chunks=chunks, scale=0.5, force=True, side_stream=side, peer=peer)
+    for _ in range(3 if peer else 1):      # step parity alternates the factor blocks
+        ps_b = {k: leaf(t[k]) for k in names}
+        with vp.context():
+            loss, m2b = _render_loss(mod, t, sc, dL, deg, ps_b)
+            loss.backward()
+    assert vp.stats["backwards"] == (3 if peer else 1)
+    assert any(v is not None for v in vp._peer_states.values()) == (peer and factors)
+    vp.close()
     for k in names:
         assert _err(ps_b[k].grad, 0.5 * ps_a[k].grad) <= 1e-4, k   # fp32 atomics: run-to-run order differs
     assert _err(m2b.grad, m2a.grad) <= 1e-4                        # per-view statistic: neither summed nor scaled
@@ -144,3 +150,67 @@ def test_sh_factors_of_three_views_rebuild_the_summed_dsh():
     got = parallel.sh_grad_from_factors(torch.from_numpy(base.means3D).cuda(), torch.stack(campos).contiguous(),
                                         torch.stack(factors).contiguous(), 16, deg)
     assert _err(got, want) <= 1e-4
+
+
+def test_peer_exchange_with_three_emulated_ranks():
+    """The peer-memory exchange (csrc/sgr_peer.cu) as rank 0 of THREE, on one GPU: ranks 1 and 2 are static stand-ins --
+    their factor blocks and record arrays are filled from plain backwards of their views, their flag words are preset,
+    and this process reduces their record slices as well.  Everything the real multi-rank run executes runs here: the
+    flag waits, the per-Gaussian pass summing three views' SH gradients through the pointer table, the two-shot reduce
+    over three record arrays, the split.  The result must be scale x (sum of the three views' plain gradients)."""
+    import ctypes as C
+    import torch
+    from sugar_b200 import _C, _lib, diff_gaussian_rasterization as mod
+    from sugar_b200 import parallel, scenes
+    P, W, H, deg, scale = 6001, 160, 96, 3, 0.25
+    base = scenes.make_scene(P, W, H, seed=41, camera="posed")
+    views = [base, scenes.with_camera_offset(base, 0.15, (0.3, -0.1, 0.2)),
+             scenes.with_camera_offset(base, -0.2, (-0.4, 0.2, 0.5))]
+    names = ("means3D", "opacities", "shs", "scales", "rotations")
+    E = torch.Tensor([])
+    plain, factors, records = [], [], []
+    for v, sc in enumerate(views):
+        t = h.to_torch(sc)
+        dL = torch.from_numpy(scenes.upstream_grad(W, H, seed=5 + v)).cuda()
+        bg = torch.zeros(3, device="cuda")
+        R, color, radii, geom, binning, img = _C.rasterize_gaussians(
+            bg, t["means3D"], E, t["opacities"], t["scales"], t["rotations"], 1.0, E, t["viewmatrix"], t["projmatrix"],
+            sc.tanfovx, sc.tanfovy, H, W, t["shs"], deg, t["campos"], False, False)
+        g = _C.rasterize_gaussians_backward(bg, t["means3D"], radii, E, t["scales"], t["rotations"], 1.0, E,
+                                            t["viewmatrix"], t["projmatrix"], sc.tanfovx, sc.tanfovy, dL, t["shs"], deg,
+                                            t["campos"], geom, R, binning, img, False)
+        plain.append({"means3D": g[3].double(), "opacities": g[2].double(), "shs": g[5].double(), "scales": g[6].double(),
+                      "rotations": g[7].double()})
+        factors.append(torch.cat([g[1].reshape(-1), t["campos"].reshape(3), torch.zeros(1, device="cuda")]).contiguous())
+        records.append(torch.cat([g[3], g[2], g[6], g[7]], dim=1).contiguous())     # the 44-byte record layout
+    want = {k: scale * sum(p[k] for p in plain) for k in names}
+
+    vp = parallel.ViewParallel(chunks=3, scale=scale, force=True, peer=True)
+    st = vp._peer_state(_lib.lib, _lib.check, P, torch.device("cuda", torch.cuda.current_device()))
+    # stand-ins for ranks 1 and 2: padded record / sum arrays and their (static) factor blocks
+    pad = lambda r: torch.cat([r.reshape(-1), torch.zeros(16, device="cuda")]).contiguous()
+    R_fake = [pad(records[1]), pad(records[2])]
+    S_fake = [torch.zeros(11 * P + 16, device="cuda"), torch.zeros(11 * P + 16, device="cuda")]
+    tab = lambda own, others: torch.tensor([int(own)] + [o.data_ptr() for o in others], dtype=torch.int64, device="cuda")
+    st.world = 3
+    st.F_tab = [tab(st.F_tab[0][0], factors[1:]), tab(st.F_tab[1][0], factors[1:])]
+    st.R_tab, st.S_tab = tab(st.R_tab[0], R_fake), tab(st.S_tab[0], S_fake)
+    st.flag_tab = torch.tensor([st.base] * 3, dtype=torch.int64, device="cuda")   # "every rank's flags" = ours
+    flags = torch.as_tensor(type("M", (), {"__cuda_array_interface__": {
+        "shape": (64, 64), "typestr": "<i4", "data": (st.base, False), "version": 2}})(), device="cuda")
+    flags[:, 1:3] = 1 << 30     # ranks 1 and 2 have "already signalled" every slot of every step
+    vp._emulated = (1, 2)
+    t0, sc0 = h.to_torch(views[0]), views[0]
+    dL0 = torch.from_numpy(scenes.upstream_grad(W, H, seed=5)).cuda()
+    for step in range(2):       # both factor-block parities
+        ps = {k: t0[k].clone().requires_grad_(True) for k in names}
+        with vp.context():
+            loss, _ = _render_loss(mod, t0, sc0, dL0, deg, ps, bg=(0.0, 0.0, 0.0))
+            loss.backward()
+        for k in names:
+            assert _err(ps[k].grad, want[k].float()) <= 1e-4, (step, k)
+        for S in S_fake:        # every rank's sum array received every slice
+            assert _err(S[:11 * P], (records[0].double() + records[1].double() + records[2].double()).float().reshape(-1)) <= 1e-4
+    torch.cuda.synchronize()
+    st.world = 1
+    vp.close()
