@@ -70,14 +70,20 @@ def parse():
                     help="N>1: Gaussian ranges of the per-Gaussian backward pass; each range's all-reduce overlaps the next")
     ap.add_argument("--side-stream", action="store_true",
                     help="N>1: finalize each range on a second stream as soon as its collective is done (parallel.ViewParallel)")
-    ap.add_argument("--peer", action="store_true",
-                    help="N>1: exchange through the peer-memory kernels (csrc/sgr_peer.cu: CUDA IPC mappings, flags, "
-                         "P2P loads / stores over NVLink) instead of NCCL collectives (all-gather + chunked all-reduce)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: how the ranks' gradients meet inside the backward.  peer: the peer-memory kernels "
+                         "(csrc/sgr_peer.cu: CUDA IPC mappings, flags, TMA loads / stores over NVLink); nccl: all-gather + "
+                         "chunked all-reduce; auto (default): peer on the world sizes it was measured faster on "
+                         "(sugar_b200.parallel.PEER_AUTO_WORLDS), else nccl")
+    ap.add_argument("--peer", action="store_true", help="same as --exchange peer")
     ap.add_argument("--no-taper", action="store_true",
                     help="N>1, peer exchange: equal chunks instead of halving ones")
     ap.add_argument("--force-exchange", action="store_true",
                     help="diagnostic, N=1: run the exchange path's kernels (factor-mode backward + finalize) without NCCL")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.peer:
+        args.exchange = "peer"
+    return args
 
 
 # ---------------------------------------------------------------------------------------------
@@ -379,12 +385,13 @@ def main():
         import contextlib
         from sugar_b200 import parallel
         vp = parallel.ViewParallel(sh_factors=not args.no_sh_factors, chunks=args.chunks, side_stream=args.side_stream,
-                                   force=args.force_exchange, peer="auto" if args.peer else False,
+                                   force=args.force_exchange, peer={"auto": "auto", "peer": True, "nccl": False}[args.exchange],
                                    taper=not args.no_taper)
         if dist is not None:
             exchange_check = verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, D,
                                              sh_factors=not args.no_sh_factors, chunks=args.chunks,
-                                             side_stream=args.side_stream, peer="auto" if args.peer else False)
+                                             side_stream=args.side_stream,
+                                             peer={"auto": "auto", "peer": True, "nccl": False}[args.exchange])
         stack = contextlib.ExitStack()
         stack.enter_context(vp.context())  # the autograd node keeps the context for the backward thread
 
@@ -544,7 +551,7 @@ def main():
                            "exchange": ("none" if world == 1 else "all-reduce 236 B/Gaussian" if args.no_sh_factors else
                                         f"inside the backward, NCCL: all-gather 12 B/Gaussian/view SH factors under the "
                                         f"per-Gaussian pass + all-reduce 44 B/Gaussian in {args.chunks} overlapped chunks"
-                                        if (not args.peer or not (exchange_check or {}).get("peer_memory")) else
+                                        if not (exchange_check or {}).get("peer_memory") else
                                         f"inside the backward, over peer memory (CUDA IPC, no NCCL call): the finalize "
                                         f"kernel loads every view's 12 B/Gaussian SH factors from its owner GPU; the "
                                         f"44 B/Gaussian records are reduced by a two-shot P2P kernel in {args.chunks} "

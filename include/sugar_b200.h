@@ -163,6 +163,30 @@ typedef struct SgrBackwardPlan {
     float peer_dsh_scale;
     double peer_timeout_s;
     int32_t chunk_taper; /* 0: equal chunks; else every chunk half the size of the one before it */
+    /* With peer_view_blocks: DEVICE array of peer_nranks pointers, entry j = rank j's staging array (f32[11P + 4]) for
+     * records COMING FROM this rank (entry peer_rank = reduce_records itself).  CTA b of a chunk's launch then stores its
+     * 64 records into the array of the rank that owns them (owner = b * nranks / CTAs of the chunk; what
+     * sgr_peer_reduce_records assumes) with a TMA bulk store over NVLink -- the reduce-scatter half of the records'
+     * all-reduce is fused into the pass.  NULL: all records go to reduce_records. */
+    float *const *peer_record_stages;
+    /* Optional second stream for the backward's own signals: each signal kernel then runs there, behind an event
+     * recorded on `stream`, and the per-Gaussian chunks follow one another on `stream` without the signals' launches
+     * in between.  The caller orders whatever must see the signals' completion behind this stream. */
+    void *peer_signal_stream;
+    /* Optional: the backward also drives the records' exchange, on this side stream, chunk by chunk underneath the
+     * per-Gaussian pass of the later chunks: once this rank's CHUNK c signal is out (an event behind the signal kernel;
+     * a spinning kernel must never sit in front of a signal another rank waits for) it enqueues
+     * sgr_peer_reduce_records_synced (wait CHUNK c of every rank, sum the owned slice over peer_rec_tab into every rank's
+     * peer_sum_tab, signal peer_slot_reduced0 + c) and, behind the NEXT chunk's reduce, sgr_peer_wait(REDUCED c) + the
+     * split of peer_sums (this rank's sum array) into dL_dmeans3D / dL_dopacity / dL_dscales / dL_drotations scaled by
+     * peer_dsh_scale.  The caller orders its stream behind peer_side_stream (and peer_signal_stream) afterwards.
+     * peer_emulate_ranks (tests): bit r set = also reduce rank r's slices here. */
+    void *peer_side_stream;
+    const void *const *peer_rec_tab;
+    void *const *peer_sum_tab;
+    const float *peer_sums;
+    int32_t peer_slot_reduced0;
+    uint64_t peer_emulate_ranks;
 } SgrBackwardPlan;
 SGR_API int sgr_rasterize_backward_staged(const SgrView *view, const SgrGaussians *g, const int32_t *radii,
                                           const void *geom_buffer, const void *binning_buffer, const void *image_buffer,
@@ -205,10 +229,12 @@ SGR_API int sgr_view_grad_finalize_peers(int32_t P, int32_t p0, int32_t p1, int3
  *                    of nranks pointers to the ranks' flag words), after a system-scope fence;
  * sgr_peer_wait      (on `stream`) spins until words [slot0 .. slot0+nslots)[0 .. nranks) of the LOCAL flags have all
  *                    reached seq (wrap-safe); traps after timeout_s seconds (<= 0: 20 s) instead of hanging;
- * sgr_peer_reduce_records  two-shot all-reduce of the 44-byte records of the Gaussians [p0, p1) (p0 * 11 floats a
- *                    multiple of 16 bytes): this rank sums ITS slice of the range over all ranks' record arrays
- *                    (rec_tab, device array of nranks pointers to f32[11P + 4]) in rank order and stores the sums into
- *                    every rank's sum array (sum_tab, likewise). */
+ * sgr_peer_reduce_records  second half of the records' all-reduce for the chunk of Gaussians [p0, p1) (p0 a multiple of
+ *                    64): this rank sums the slice of the chunk it OWNS -- the 64-record blocks b with
+ *                    b * nranks / blocks == my_rank, the ones the per-Gaussian pass stored here
+ *                    (SgrBackwardPlan.peer_record_stages) -- over the nranks staging arrays rec_tab points to (device
+ *                    array of pointers to f32[11P + 4]; normally all LOCAL), in rank order, and stores the sums into
+ *                    every rank's sum array (sum_tab, likewise; remote entries are posted NVLink writes). */
 #define SGR_PEER_MAX_RANKS 64
 #define SGR_PEER_MAX_SLOTS 64
 SGR_API int sgr_peer_alloc(size_t bytes, void **ptr);
@@ -223,6 +249,14 @@ SGR_API int sgr_peer_wait(const void *flags, int32_t nranks, int32_t slot0, int3
                           double timeout_s, void *stream);
 SGR_API int sgr_peer_reduce_records(const void *const *rec_tab, void *const *sum_tab, int32_t nranks, int32_t my_rank,
                                     int32_t p0, int32_t p1, void *stream);
+/* The same with the flag handshake folded into the kernel: it first waits until every rank's word of wait_slot in the
+ * LOCAL flags has reached seq (flags NULL: no wait), and its last CTA to finish writes seq into word
+ * [signal_slot][my_rank] of every rank's flags (flag_tab NULL: no signal; `counter`: a zero-initialised u32 in local
+ * device memory that the kernel re-arms, one per concurrently running launch). */
+SGR_API int sgr_peer_reduce_records_synced(const void *const *rec_tab, void *const *sum_tab, int32_t nranks,
+                                           int32_t my_rank, int32_t p0, int32_t p1, const void *flags, int32_t wait_slot,
+                                           void *const *flag_tab, int32_t signal_slot, uint32_t seq, void *counter,
+                                           double timeout_s, void *stream);
 
 /* The SH half alone, over all Gaussians (kept for callers that only exchange factors). */
 SGR_API int sgr_sh_grad_from_factors(int32_t P, int32_t M, int32_t sh_degree, int32_t num_views, const float *means3D,

@@ -24,7 +24,7 @@ dist.init_process_group("nccl", device_id=dev)
 from sugar_b200 import diff_gaussian_rasterization as mod, parallel
 scenes = bench.load_scenes()
 res = {}
-for factors, peer in ((True, "auto"), (True, False), (False, False)):
+for factors, peer in ((True, True), (True, False), (False, False)):
     for chunks in (1, 4, 7):
         r = bench.verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, 3, sh_factors=factors, chunks=chunks,
                                   peer=peer)

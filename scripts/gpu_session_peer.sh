@@ -13,14 +13,15 @@ run $N scripts/check_view_parallel.py > gpurun_out/${tag}_check_n${N}.json 2> gp
 tail -1 gpurun_out/${tag}_check_n${N}.json; tail -5 gpurun_out/${tag}_check_n${N}.err
 B="--steps 20 --warmup 5 --no-cpu-baseline"
 timeout 300 python bench.py $B > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err
-run $N bench.py --gpus $N $B --peer > gpurun_out/${tag}_bench_n${N}_peer.json 2> gpurun_out/${tag}_bench_n${N}_peer.err
-run $N bench.py --gpus $N $B > gpurun_out/${tag}_bench_n${N}_nccl.json 2> gpurun_out/${tag}_bench_n${N}_nccl.err
+run $N bench.py --gpus $N $B --exchange peer > gpurun_out/${tag}_bench_n${N}_peer.json 2> gpurun_out/${tag}_bench_n${N}_peer.err
+run $N bench.py --gpus $N $B --exchange nccl > gpurun_out/${tag}_bench_n${N}_nccl.json 2> gpurun_out/${tag}_bench_n${N}_nccl.err
+grep -q '"value"' gpurun_out/${tag}_bench_n${N}_peer.json || { echo "peer bench failed; stopping"; tail -5 gpurun_out/${tag}_bench_n${N}_peer.err; head -c 300 gpurun_out/${tag}_bench_n${N}_peer.json; exit 1; }
 if [ "${3:-}" != "quick" ]; then
-run $N bench.py --gpus $N $B --peer --chunks 3 > gpurun_out/${tag}_bench_n${N}_peer_chunks3.json 2> gpurun_out/${tag}_bench_n${N}_peer_chunks3.err
-run $N bench.py --gpus $N $B --peer --chunks 5 > gpurun_out/${tag}_bench_n${N}_peer_chunks5.json 2> gpurun_out/${tag}_bench_n${N}_peer_chunks5.err
-run $N bench.py --gpus $N $B --peer --no-taper > gpurun_out/${tag}_bench_n${N}_peer_notaper.json 2> gpurun_out/${tag}_bench_n${N}_peer_notaper.err
-run $N scripts/timeline_peer.py --peer > gpurun_out/${tag}_timeline_n${N}.txt 2> gpurun_out/${tag}_timeline_n${N}.err
+run $N bench.py --gpus $N $B --exchange peer --chunks 3 > gpurun_out/${tag}_bench_n${N}_peer_chunks3.json 2> gpurun_out/${tag}_bench_n${N}_peer_chunks3.err
+run $N bench.py --gpus $N $B --exchange peer --chunks 5 > gpurun_out/${tag}_bench_n${N}_peer_chunks5.json 2> gpurun_out/${tag}_bench_n${N}_peer_chunks5.err
+run $N bench.py --gpus $N $B --exchange peer --no-taper > gpurun_out/${tag}_bench_n${N}_peer_notaper.json 2> gpurun_out/${tag}_bench_n${N}_peer_notaper.err
 fi
+run $N scripts/timeline_peer.py --peer > gpurun_out/${tag}_timeline_n${N}.txt 2> gpurun_out/${tag}_timeline_n${N}.err
 python - <<PY
 import glob, json
 for f in sorted(glob.glob("gpurun_out/${tag}_*.json")):

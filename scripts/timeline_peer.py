@@ -23,7 +23,7 @@ means2D = torch.zeros_like(params["means3D"], requires_grad=True)
 dL = t(scenes.upstream_grad(W, H, seed=1 + rank))
 st = mod.GaussianRasterizationSettings(H, W, sc.tanfovx, sc.tanfovy, torch.zeros(3, device=dev), 1.0, t(sc.viewmatrix),
                                        t(sc.projmatrix), 3, t(sc.campos), False, False)
-vp = parallel.ViewParallel(chunks=int(os.environ.get("CHUNKS", "4")), peer="auto" if "--peer" in sys.argv else False,
+vp = parallel.ViewParallel(chunks=int(os.environ.get("CHUNKS", "4")), peer=True if "--peer" in sys.argv else False,
                            taper="--no-taper" not in sys.argv)
 def step():
     with vp.context():

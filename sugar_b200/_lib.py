@@ -49,7 +49,10 @@ class SgrBackwardPlan(C.Structure):
                 ("peer_flag_tab", C.c_void_p), ("peer_nranks", C.c_int32), ("peer_rank", C.c_int32),
                 ("peer_slot_blend", C.c_int32), ("peer_slot_chunk0", C.c_int32), ("peer_seq", C.c_uint32),
                 ("peer_view_blocks", C.c_void_p), ("peer_flags", C.c_void_p), ("peer_dsh_scale", C.c_float),
-                ("peer_timeout_s", C.c_double), ("chunk_taper", C.c_int32)]
+                ("peer_timeout_s", C.c_double), ("chunk_taper", C.c_int32),
+                ("peer_record_stages", C.c_void_p), ("peer_signal_stream", C.c_void_p),
+                ("peer_side_stream", C.c_void_p), ("peer_rec_tab", C.c_void_p), ("peer_sum_tab", C.c_void_p),
+                ("peer_sums", C.c_void_p), ("peer_slot_reduced0", C.c_int32), ("peer_emulate_ranks", C.c_uint64)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
@@ -75,6 +78,9 @@ PROTOTYPES = {
     "sgr_peer_signal": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
     "sgr_peer_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_double, C.c_void_p]),
     "sgr_peer_reduce_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "sgr_peer_reduce_records_synced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p,
+                                                 C.c_double, C.c_void_p]),
     "sgr_mark_visible": (C.c_int, [C.c_int32] + [C.c_void_p] * 5),
     "sgr_sh_grad_from_factors": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "sgr_geometry_bytes": (C.c_size_t, [C.c_int32]),

@@ -469,6 +469,12 @@ struct PreBwdArgs {
     int nviews, my_view;
     size_t campos_off;
     float dsh_scale;
+    // peer mode, records: CTA b of this launch (a chunk of the pass) stores its 64 records into the staging array of the
+    // rank that OWNS them -- owner = b * nviews / gridDim.x, stage_tab[owner] = that rank's array for records coming
+    // from this rank -- with one TMA bulk store (a posted write over NVLink): the reduce-scatter half of the records'
+    // all-reduce is fused into this kernel's write-out.  NULL: records go to rec11.
+    float *const *stage_tab;
+    int pf_off;  // floats: where the other views' factor blocks land in shared memory (MULTI)
 };
 
 #define SH_C0 0.28209479177387814f
@@ -654,7 +660,16 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             if (RAW && a.shs) bytes += PB_T * 12 + PB_T * (uint32_t)(a.v.M - 1) * 12;
             if (a.scales) bytes += PB_T * 12 + PB_T * 16;
             if (a.cov_pre) bytes += PB_T * 24;
+            // peer mode: the other views' factor blocks of these 64 Gaussians, one bulk copy per view straight out of
+            // its owner GPU's memory (TMA over NVLink): the factors' all-gather is fused into this kernel's staging.
+            // (A separate, later-waited barrier for them measured slower: 0.308 vs 0.257 ms for 1.6 M Gaussians.)
+            const int pulled = MULTI ? min(a.nviews - 1, PB_VB) : 0;
+            bytes += (uint32_t)pulled * PB_T * 12;
             mbar_expect_tx(&s_bar, bytes);
+            for (int u = 0; u < pulled; u++) {
+                const int v = u + (u >= a.my_view ? 1 : 0);
+                bulk_g2s(sm + a.pf_off + u * PB_T * 3, a.view_tab[v] + (size_t)base * 3, PB_T * 12, &s_bar);
+            }
             if (RAW && a.shs) {
                 bulk_g2s(sm + PB_SHDC, a.shs + (size_t)base * 3, PB_T * 12, &s_bar);
                 if (a.v.M > 1)
@@ -681,6 +696,13 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
         if (RAW && a.shs) {
             pb_stage(sm + PB_SHDC, a.shs + (size_t)base * 3, n * 3);
             pb_stage(sm + PB_SH, a.sh_rest + (size_t)base * (M - 1) * 3, n * (M - 1) * 3);
+        }
+        if (MULTI) {
+            const int pulled = min(a.nviews - 1, PB_VB);
+            for (int u = 0; u < pulled; u++) {
+                const int v = u + (u >= a.my_view ? 1 : 0);
+                pb_stage(sm + a.pf_off + u * PB_T * 3, a.view_tab[v] + (size_t)base * 3, n * 3);
+            }
         }
     }
     float *s_sh = sm + PB_SH;
@@ -713,21 +735,7 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
     }
     int radius = 0;
     if (tid < n) radius = a.radii[i];
-    // peer mode: the other views' factors of this Gaussian, fetched from their owners' memory (NVLink) while the local
-    // staging is in flight; views beyond the first PB_VB are fetched when they are used
-    float pf[MULTI ? PB_VB : 1][3];
     const int others = MULTI ? a.nviews - 1 : 0;
-    if (MULTI && tid < n) {
-#pragma unroll
-        for (int u = 0; u < PB_VB; u++) {
-            const int v = u + (u >= a.my_view ? 1 : 0);  // skip this launch's own view
-            const bool on = u < others;
-            const float *g = a.view_tab[on ? v : a.my_view] + (size_t)i * 3;
-            pf[u][0] = on ? __ldcg(g) : 0.f;
-            pf[u][1] = on ? __ldcg(g + 1) : 0.f;
-            pf[u][2] = on ? __ldcg(g + 2) : 0.f;
-        }
-    }
     __syncthreads();
     if (a.in_bulk_ok && full) mbar_wait(&s_bar, 0);
     if (!RAW && a.shs) {
@@ -738,16 +746,24 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
     // peer mode: the other views' SH gradients of this Gaussian, summed in registers (48 accumulators); they join the
     // row when this view's gradient is written into it (or make up the whole row if the Gaussian is culled here)
     float oacc[MULTI ? 48 : 1];
-    if (MULTI && tid < n) {
+    auto sum_other_views = [&]() {
+        if (!MULTI) return;
 #pragma unroll
-        for (int k = 0; k < 48; k++) oacc[k] = 0.f;
+        for (int k = 0; k < (MULTI ? 48 : 1); k++) oacc[k] = 0.f;
+        if (others <= 0) return;
         const float mx = sm[PB_MEANS + tid * 3], my = sm[PB_MEANS + tid * 3 + 1], mz = sm[PB_MEANS + tid * 3 + 2];
         for (int u0 = 0; u0 < others; u0 += PB_VB) {
-            if (u0) {
+            float pf[PB_VB][3];
 #pragma unroll
-                for (int u = 0; u < PB_VB; u++) {
-                    const int uu = u0 + u, v = uu + (uu >= a.my_view ? 1 : 0);
-                    const bool on = uu < others;
+            for (int u = 0; u < PB_VB; u++) {
+                const int uu = u0 + u, v = uu + (uu >= a.my_view ? 1 : 0);
+                const bool on = uu < others;
+                if (u0 == 0) {  // staged in shared memory by the bulk copies above
+                    const float *g = sm + a.pf_off + u * PB_T * 3 + tid * 3;
+                    pf[u][0] = on ? g[0] : 0.f;
+                    pf[u][1] = on ? g[1] : 0.f;
+                    pf[u][2] = on ? g[2] : 0.f;
+                } else {        // more than PB_VB + 1 views: the rest straight from global / peer memory
                     const float *g = a.view_tab[on ? v : a.my_view] + (size_t)i * 3;
                     pf[u][0] = on ? __ldcg(g) : 0.f;
                     pf[u][1] = on ? __ldcg(g + 1) : 0.f;
@@ -763,7 +779,8 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
                 sh_accumulate(a.v.D, oacc, {mx - __ldg(cp), my - __ldg(cp + 1), mz - __ldg(cp + 2)}, g);
             }
         }
-    }
+    };
+    if (MULTI && tid < n) sum_other_views();
     if (tid < n) {
         const bool vis = radius > 0;
         // the 11 all-reduce-bound outputs: four arrays, or one 44-byte record per Gaussian (stride 11: conflict-free)
@@ -963,6 +980,8 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
     // ---- write-out: the small arrays leave as 1-D bulk copies (TMA stores issued by one thread) when the
     // block is full and everything is 16-byte aligned, else through coalesced loops
     const bool out_bulk = a.out_bulk_ok && full;
+    float *rec_out = a.rec11;
+    if (a.stage_tab) rec_out = a.stage_tab[(int)((long long)blockIdx.x * a.nviews / gridDim.x)];
     if (out_bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (out_bulk) {
@@ -970,7 +989,7 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
             bulk_s2g(a.dmeans2D + (size_t)base * 3, sm + PB_O_M2D, PB_T * 12);
             bulk_s2g(a.dcov3D + (size_t)base * 6, sm + PB_O_COV, PB_T * 24);
             if (a.rec11) {
-                bulk_s2g(a.rec11 + (size_t)base * 11, sm + PB_O_R11, PB_T * 44);
+                bulk_s2g(rec_out + (size_t)base * 11, sm + PB_O_R11, PB_T * 44);
             } else {
                 bulk_s2g(a.dopacity + base, sm + PB_O_OPA, PB_T * 4);
                 bulk_s2g(a.dmeans3D + (size_t)base * 3, sm + PB_O_M3D, PB_T * 12);
@@ -983,7 +1002,7 @@ __global__ void __launch_bounds__(PB_T) preprocess_backward_kernel(const PreBwdA
         pb_flush(a.dmeans2D + (size_t)base * 3, sm + PB_O_M2D, n * 3);
         pb_flush(a.dcov3D + (size_t)base * 6, sm + PB_O_COV, n * 6);
         if (a.rec11) {
-            pb_flush(a.rec11 + (size_t)base * 11, sm + PB_O_R11, n * 11);
+            pb_flush(rec_out + (size_t)base * 11, sm + PB_O_R11, n * 11);
         } else {
             pb_flush(a.dopacity + base, sm + PB_O_OPA, n);
             pb_flush(a.dmeans3D + (size_t)base * 3, sm + PB_O_M3D, n * 3);
@@ -1285,6 +1304,12 @@ __global__ void __launch_bounds__(SFG_T) view_grad_finalize_kernel(int p0, int p
     }
 }
 
+static int finalize_impl(int32_t P, int32_t p0, int32_t p1, int32_t M, int32_t sh_degree, int32_t num_views,
+                         const float *means3D, const float *campos, const float *dRGB, int64_t view_stride,
+                         int32_t campos_stride, const float *const *view_tab, float *dL_dsh, const float *reduced_records,
+                         float scale, float *dL_dmeans3D, float *dL_dopacity, float *dL_dscales, float *dL_drotations,
+                         void *stream, const char *who);
+
 // CTA range [b0, b1) of chunk c of the per-Gaussian pass.  taper == 0: equal chunks.  taper != 0: every chunk half the size
 // of the one before it (weights 2^(n-1-c)), so that what a caller does with a finished chunk while the next one is
 // computed (the peer exchange: reduce + split) is matched by that next chunk's shorter run, and little is left after the
@@ -1356,9 +1381,31 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     // dL_dcolors is final here (with SH colours: the clamp-masked dL/dRGB, i.e. this view's SH factor)
     if (hook) hook(hook_ctx, SGR_STAGE_BLEND_DONE);
     const bool peer = plan && plan->peer_flag_tab;
+    // this backward's own signals: on `st`, or on the plan's signal stream behind an event recorded on `st` (so that the
+    // next kernel on `st` does not queue behind the signal's launch)
+    auto signal = [&](int slot, int ev_index, bool on_main = false) -> int {
+        cudaStream_t sig = st;
+        if (plan->peer_signal_stream && !on_main) {
+            static std::mutex mu;
+            static cudaEvent_t evs[64][20] = {};
+            int dev = 0;
+            SGR_CUDA(cudaGetDevice(&dev));
+            if (dev < 0 || dev >= 64 || ev_index < 0 || ev_index >= 20) {
+                set_error("peer_signal_stream: device / chunk index out of range");
+                return SGR_EINVAL;
+            }
+            std::lock_guard<std::mutex> lock(mu);
+            if (!evs[dev][ev_index]) SGR_CUDA(cudaEventCreateWithFlags(&evs[dev][ev_index], cudaEventDisableTiming));
+            sig = (cudaStream_t)plan->peer_signal_stream;
+            SGR_CUDA(cudaEventRecord(evs[dev][ev_index], st));
+            SGR_CUDA(cudaStreamWaitEvent(sig, evs[dev][ev_index], 0));
+        }
+        return sgr_peer_signal(plan->peer_flag_tab, plan->peer_nranks, slot, plan->peer_rank, plan->peer_seq, sig);
+    };
     if (peer) {
-        int rc = sgr_peer_signal(plan->peer_flag_tab, plan->peer_nranks, plan->peer_slot_blend, plan->peer_rank,
-                                 plan->peer_seq, st);
+        // BLEND goes out on `st` itself: the wait right behind it spins, and a spinning kernel must never be dispatched
+        // ahead of a signal of its own rank that the peers need in order to answer
+        int rc = signal(plan->peer_slot_blend, 0, true);
         if (rc) return rc;
         if (plan->peer_view_blocks && dL_dsh && g->shs) {
             // the per-Gaussian pass sums every view's SH gradient into dL_dsh: the peers' factor blocks must be final
@@ -1405,6 +1452,8 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
     a.drots = dL_drotations;
     a.rec11 = rec11;
     a.view_tab = nullptr;
+    a.stage_tab = nullptr;
+    a.pf_off = 0;
     a.nviews = 1;
     a.my_view = 0;
     a.campos_off = (size_t)3 * P;
@@ -1415,6 +1464,11 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
         a.nviews = plan->peer_nranks;
         a.my_view = plan->peer_rank;
         a.dsh_scale = plan->peer_dsh_scale;
+        a.stage_tab = (float *const *)plan->peer_record_stages;
+        if (a.stage_tab && (!rec11 || PB_T != 64)) {
+            set_error("peer_record_stages needs reduce_records (the local staging array) and 64-thread CTAs");
+            return SGR_EINVAL;
+        }
     }
     a.sh_rest = g->sh_rest;
     a.rec = geom.rec;
@@ -1446,12 +1500,44 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
             a.sh_stride = (row_f & 1) ? row_f : row_f + 1;
         }
     }
-    const size_t dyn = (size_t)(PB_SH + PB_T * (raw ? (g->M > 0 ? (g->M - 1) * 3 : 0) : a.sh_stride)) * sizeof(float) + 16;
+    a.pf_off = PB_SH + PB_T * (raw ? (g->M > 0 ? (g->M - 1) * 3 : 0) : a.sh_stride);
+    const int pulled = a.view_tab ? (a.nviews - 1 < PB_VB ? a.nviews - 1 : PB_VB) : 0;
+    const size_t dyn = (size_t)(a.pf_off + pulled * PB_T * 3) * sizeof(float) + 16;
     // the per-Gaussian pass, in `num_chunks` Gaussian ranges (multiples of the CTA size) so that a caller
     // can start reducing a finished range while the next one is computed
     int nchunks = plan && plan->num_chunks > 1 ? plan->num_chunks : 1;
     const int blocks = (P + PB_T - 1) / PB_T;
     if (nchunks > blocks) nchunks = blocks;
+    int split_c = -1, split_p0 = 0, split_p1 = 0;
+    auto side_event = [&](int index, cudaEvent_t *out) -> int {
+        static std::mutex mu;
+        static cudaEvent_t evs[64][20] = {};
+        int dev = 0;
+        SGR_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || index < 0 || index >= 20) {
+            set_error("peer_side_stream: device / chunk index out of range");
+            return SGR_EINVAL;
+        }
+        std::lock_guard<std::mutex> lock(mu);
+        if (!evs[dev][index]) SGR_CUDA(cudaEventCreateWithFlags(&evs[dev][index], cudaEventDisableTiming));
+        *out = evs[dev][index];
+        return SGR_OK;
+    };
+    auto split_chunk = [&](cudaStream_t B, int c, int p0, int p1) -> int {
+        int rc = sgr_peer_wait(plan->peer_flags, plan->peer_nranks, plan->peer_slot_reduced0 + c, 1, plan->peer_seq,
+                               plan->peer_timeout_s, B);
+        if (rc) return rc;
+        return finalize_impl(P, p0, p1, g->M, view->sh_degree, plan->peer_nranks, g->means3D, nullptr, nullptr, 0, 0, nullptr,
+                             nullptr, plan->peer_sums, plan->peer_dsh_scale, dL_dmeans3D, dL_dopacity, dL_dscales,
+                             dL_drotations, B, "peer exchange: bad arguments to the record split");
+    };
+    if (peer && plan->peer_side_stream &&
+        (!plan->peer_rec_tab || !plan->peer_sum_tab || !plan->peer_sums || !plan->peer_flags || !rec11 || !dL_dmeans3D ||
+         !dL_dopacity || !dL_dscales || !dL_drotations || nchunks > 16)) {
+        set_error("peer_side_stream needs peer_rec_tab / peer_sum_tab / peer_sums / peer_flags, reduce_records, the four "
+                  "record-bound gradient arrays and at most 16 chunks");
+        return SGR_EINVAL;
+    }
     for (int c = 0; c < nchunks; c++) {
         int b0, b1;
         chunk_blocks(blocks, nchunks, c, plan ? plan->chunk_taper : 0, &b0, &b1);
@@ -1464,10 +1550,46 @@ int launch_backward(const SgrView *view, const SgrGaussians *g, const int32_t *r
                        else preprocess_backward_kernel<false><<<b1 - b0, PB_T, dyn, st>>>(a));
         if (hook) hook(hook_ctx, SGR_STAGE_CHUNK_DONE + c);
         if (peer) {
-            const int rc = sgr_peer_signal(plan->peer_flag_tab, plan->peer_nranks, plan->peer_slot_chunk0 + c,
-                                           plan->peer_rank, plan->peer_seq, st);
+            int rc = signal(plan->peer_slot_chunk0 + c, 1 + c);
             if (rc) return rc;
+            if (plan->peer_side_stream) {
+                // The records' exchange of this chunk, on the side stream.  Its kernels spin on flags: they may start
+                // only once THIS rank's own signal for the chunk is out (an event behind the signal kernel) -- a
+                // spinning kernel must never sit in front of a signal some rank is waiting for.
+                cudaStream_t B = (cudaStream_t)plan->peer_side_stream;
+                cudaStream_t sig = plan->peer_signal_stream ? (cudaStream_t)plan->peer_signal_stream : st;
+                cudaEvent_t e2 = nullptr;
+                rc = side_event(c, &e2);
+                if (rc) return rc;
+                SGR_CUDA(cudaEventRecord(e2, sig));
+                SGR_CUDA(cudaStreamWaitEvent(B, e2, 0));
+                unsigned int *counters = (unsigned int *)plan->peer_flags + (size_t)(SGR_PEER_MAX_SLOTS - 1) * SGR_PEER_MAX_RANKS;
+                for (int r = 0; r < plan->peer_nranks; r++) {
+                    const bool me = r == plan->peer_rank;
+                    if (!me && !((plan->peer_emulate_ranks >> r) & 1)) continue;
+                    // one kernel: wait(CHUNK c, every rank) -> sum the owned slice -> its last CTA signals REDUCED c
+                    rc = sgr_peer_reduce_records_synced(plan->peer_rec_tab, plan->peer_sum_tab, plan->peer_nranks, r, a.p0, a.p1,
+                                                        plan->peer_flags, plan->peer_slot_chunk0 + c,
+                                                        me ? plan->peer_flag_tab : nullptr, plan->peer_slot_reduced0 + c,
+                                                        plan->peer_seq, me ? (void *)(counters + c) : nullptr,
+                                                        plan->peer_timeout_s, B);
+                    if (rc) return rc;
+                }
+                // the split of the chunk before runs behind this chunk's reduce: the other owners' slices of it have
+                // landed by then, and only the last (smallest) chunk's reduce + split is exposed
+                if (split_c >= 0) {
+                    rc = split_chunk(B, split_c, split_p0, split_p1);
+                    if (rc) return rc;
+                }
+                split_c = c;
+                split_p0 = a.p0;
+                split_p1 = a.p1;
+            }
         }
+    }
+    if (peer && plan->peer_side_stream && split_c >= 0) {
+        const int rc = split_chunk((cudaStream_t)plan->peer_side_stream, split_c, split_p0, split_p1);
+        if (rc) return rc;
     }
     SGR_CUDA(cudaGetLastError());
     if (view->debug) SGR_CUDA(cudaStreamSynchronize(st));

@@ -4,20 +4,23 @@
 // the reference has no counterpart (1 view / 1 GPU, sugar_trainers/coarse_sdf.py:98,507).
 //
 // Every rank owns ONE peer-visible allocation (sgr_peer_alloc), laid out by the caller:
-//     flags  u32[PEER_SLOTS][PEER_RANKS]   word [slot][j] is written by rank j only, monotonically (a step counter)
-//     F0,F1  f32[3P+4]                     this rank's SH factor block (dL/dRGB per Gaussian + its camera position),
-//                                          double-buffered by step parity (peers may still read step k-1's while
-//                                          step k's blend pass accumulates)
-//     R      f32[11P]                      this rank's 44-byte gradient records (per-Gaussian pass output)
-//     S      f32[11P]                      the records summed over the ranks (written by the owners of each slice)
-// Stream picture of one backward on rank r (main = the caller's stream; A, B = two high-priority side streams):
-//     main  memset  blend ─sig(BLEND)─ pb chunk 0 ─sig(CHUNK 0)─ pb chunk 1 ─sig(CHUNK 1)─ ...          wait(A,B)
-//     A            wait(BLEND, all ranks) ─ finalize SH half: loads every peer's factors over NVLink (the all-gather
-//                                           is fused into the consumer; no gathered copy exists)
-//     B            wait(CHUNK 0, all) ─ reduce slice r of chunk 0: peer loads, sum in rank order, peer stores into every
-//                  rank's S ─sig(REDUCED 0)─ wait(CHUNK 1, all) ─ ... ─ wait(REDUCED *, all) ─ finalize records half
-// A rank's main stream never waits for a peer, so the signals always arrive and the side streams always drain; a
-// wait that outlives its timeout traps (the context dies with an error instead of hanging the box).
+//     flags     u32[PEER_SLOTS][PEER_RANKS]  word [slot][j] is written by rank j only, monotonically (a step counter)
+//     F0, F1    f32[3P+4]     this rank's SH factor block (dL/dRGB per Gaussian + its camera position), double-buffered by
+//                             step parity (peers may still read step k-1's while step k's blend pass accumulates)
+//     S         f32[11P+]     the 44-byte gradient records summed over the ranks (written by the owners of each slice)
+//     STAGE[j]  f32[11P+]     records computed by rank j for the blocks THIS rank owns (j = 0 .. N-1, own included)
+// Stream picture of one backward on rank r (main = the caller's stream, B = a high-priority side stream):
+//     main  memset  blend ─sig(BLEND)─ wait(BLEND, all ranks) ─ pb chunk 0 ─sig(CHUNK 0)─ pb chunk 1 ─sig(CHUNK 1)─ ...  wait(B)
+//              pb = the per-Gaussian pass (sgr_backward.cu, MULTI): bulk-loads (TMA) the other ranks' factor blocks of
+//              its 64 Gaussians straight from their memory and writes dL_dsh summed over ALL views -- the all-gather is
+//              fused into the consumer; bulk-stores (TMA) its 64 records into the staging array of the rank that owns
+//              them -- the reduce-scatter is fused into the producer
+//     B     wait(CHUNK 0, all) ─ reduce: sum the owned slice of chunk 0 over STAGE[0..N-1] (local loads), store the sums
+//           into every rank's S (posted NVLink writes) ─sig(REDUCED 0)─ wait(CHUNK 1, all) ─ reduce ─ ... ; behind the
+//           reduce of chunk c: wait(REDUCED c-1, all) ─ split S of chunk c-1 into the gradient arrays
+// Chunks halve in size (SgrBackwardPlan.chunk_taper), so what is left after the last one is small.  A rank's main stream
+// waits for its peers once per backward (BLEND); a wait that outlives its timeout traps (the context dies with an error
+// instead of hanging the box).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -79,14 +82,65 @@ __global__ void peer_wait_kernel(const uint32_t *__restrict__ flags, int nranks,
     }
 }
 
+// Flag handshake folded into a kernel (saves the microsecond-sized launches around it):
+//  begin  threads 0 .. nranks-1 of every CTA poll the LOCAL flag words of `wait_slot` until all ranks reached `seq`;
+//  end    every thread fences its stores system-wide, the CTAs count themselves on a local counter, and the last one
+//         to finish writes `seq` into word [signal_slot][my_rank] of every rank's flags (and re-arms the counter).
+struct PeerSync {
+    const uint32_t *flags;      // local flag words; NULL: no wait
+    uint32_t *const *flag_tab;  // every rank's flag words; NULL: no signal
+    unsigned int *counter;      // local, zero between launches
+    int wait_slot, signal_slot, nranks, my_rank;
+    uint32_t seq;
+    long long timeout_cycles;
+};
+
+__device__ __forceinline__ void peer_sync_begin(const PeerSync &s)
+{
+    if (!s.flags) return;
+    if ((int)threadIdx.x < s.nranks) {
+        const uint32_t *w = s.flags + (size_t)s.wait_slot * PEER_RANKS + threadIdx.x;
+        if ((int32_t)(ld_relaxed_sys(w) - s.seq) < 0) {
+            const long long t0 = clock64();
+            while ((int32_t)(ld_relaxed_sys(w) - s.seq) < 0) {
+                __nanosleep(32);
+                if (clock64() - t0 > s.timeout_cycles) {
+                    printf("sugar_b200: peer wait timed out in a fused kernel (slot %d, rank %d, seq %u)\n", s.wait_slot,
+                           (int)threadIdx.x, s.seq);
+                    __trap();
+                }
+            }
+        }
+        (void)ld_acquire_sys(w);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void peer_sync_end(const PeerSync &s)
+{
+    if (!s.flag_tab) return;
+    __shared__ int s_last;
+    __threadfence_system();  // this thread's stores, local and into peer memory, are performed before what follows
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(s.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x == 0) atomicExch(s.counter, 0u);
+        __threadfence_system();  // the other CTAs' increments (each behind its own fence) have been observed
+        if ((int)threadIdx.x < s.nranks)
+            st_release_sys(s.flag_tab[threadIdx.x] + (size_t)s.signal_slot * PEER_RANKS + s.my_rank, s.seq);
+    }
+}
+
 // Two-shot all-reduce of the record units [q0, q1) (16-byte units) this rank owns: loads from every rank's R in rank
 // order (so the sum is the same bits whoever owns the slice), stores into every rank's S.  All of a thread's loads are
 // issued before the first add: what hides the NVLink round trip is bytes in flight.
 template <int NR>
 __global__ void __launch_bounds__(256) peer_reduce_kernel(const float4 *const *__restrict__ rec_tab,
                                                           float4 *const *__restrict__ sum_tab, int nranks, size_t q0,
-                                                          size_t q1)
+                                                          size_t q1, const PeerSync sync)
 {
+    peer_sync_begin(sync);
     const float4 *src[NR];
     float4 *dst[NR];
 #pragma unroll
@@ -125,13 +179,15 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const float4 *const *_
                 if (j < nranks) __stcg(dst[j] + q, a);
         }
     }
+    peer_sync_end(sync);
 }
 
 // any number of ranks (tables read per element)
 __global__ void __launch_bounds__(256) peer_reduce_generic_kernel(const float4 *const *__restrict__ rec_tab,
                                                                   float4 *const *__restrict__ sum_tab, int nranks,
-                                                                  size_t q0, size_t q1)
+                                                                  size_t q0, size_t q1, const PeerSync sync)
 {
+    peer_sync_begin(sync);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t q = q0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += stride) {
         float4 a = __ldcg(rec_tab[0] + q);
@@ -144,6 +200,7 @@ __global__ void __launch_bounds__(256) peer_reduce_generic_kernel(const float4 *
         }
         for (int j = 0; j < nranks; j++) __stcg(sum_tab[j] + q, a);
     }
+    peer_sync_end(sync);
 }
 
 }  // namespace sgr
@@ -241,19 +298,27 @@ int sgr_peer_wait(const void *flags, int32_t nranks, int32_t slot0, int32_t nslo
     return SGR_OK;
 }
 
-int sgr_peer_reduce_records(const void *const *rec_tab, void *const *sum_tab, int32_t nranks, int32_t my_rank, int32_t p0,
-                            int32_t p1, void *stream)
+int sgr_peer_reduce_records_synced(const void *const *rec_tab, void *const *sum_tab, int32_t nranks, int32_t my_rank,
+                                   int32_t p0, int32_t p1, const void *flags, int32_t wait_slot, void *const *flag_tab,
+                                   int32_t signal_slot, uint32_t seq, void *counter, double timeout_s, void *stream)
 {
     if (!rec_tab || !sum_tab || nranks < 1 || nranks > PEER_RANKS || my_rank < 0 || my_rank >= nranks || p0 < 0 ||
-        p1 < p0 || (((int64_t)p0 * 11) & 3)) {
-        set_error("bad arguments to sgr_peer_reduce_records (p0 * 11 floats must be a multiple of 16 bytes)");
+        p1 < p0 || (p0 & 63) || (flags && (wait_slot < 0 || wait_slot >= PEER_SLOTS)) ||
+        (flag_tab && (signal_slot < 0 || signal_slot >= PEER_SLOTS || !counter))) {
+        set_error("bad arguments to sgr_peer_reduce_records (p0 must be a multiple of 64)");
         return SGR_EINVAL;
     }
-    // the chunk's records in 16-byte units (the last unit may run up to 12 bytes past record p1-1: R and S are padded),
-    // dealt to the ranks in equal contiguous slices
-    const size_t Q0 = (size_t)p0 * 11 / 4, Q1 = ((size_t)p1 * 11 + 3) / 4, n = Q1 - Q0;
-    const size_t q0 = Q0 + n * (size_t)my_rank / nranks, q1 = Q0 + n * (size_t)(my_rank + 1) / nranks;
-    if (q1 == q0) return SGR_OK;
+    // ownership follows the per-Gaussian pass (PreBwdArgs::stage_tab): block b of the chunk's nb 64-record blocks belongs
+    // to rank b * nranks / nb, i.e. this rank owns the blocks [ceil(r nb / n), ceil((r + 1) nb / n)).  One block = 176
+    // 16-byte units; the chunk's last block may be partial (its last unit may run up to 12 bytes past record p1 - 1: the
+    // arrays are padded).
+    const int64_t nb = ((int64_t)(p1 - p0) + 63) / 64;
+    const int64_t bs = (nb * my_rank + nranks - 1) / nranks, be = (nb * (my_rank + 1) + nranks - 1) / nranks;
+    const size_t Q0 = (size_t)p0 * 11 / 4, Qend = ((size_t)p1 * 11 + 3) / 4;
+    size_t q0 = Q0 + (size_t)bs * 176, q1 = Q0 + (size_t)be * 176;
+    if (q1 > Qend) q1 = Qend;
+    if (q0 > q1) q0 = q1;
+    if (q1 == q0 && !flag_tab) return SGR_OK;  // nothing owned and nobody to tell
     cudaStream_t st = (cudaStream_t)stream;
     const int T = 256;
     // 2 CTAs of 256 threads per SM by default, grid-stride over the slice
@@ -264,15 +329,33 @@ int sgr_peer_reduce_records(const void *const *rec_tab, void *const *sum_tab, in
         return (size_t)(v > 0 ? v : 148 * 2);
     }();
     if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;  // the handshake still runs
+    PeerSync sy;
+    sy.flags = (const uint32_t *)flags;
+    sy.flag_tab = (uint32_t *const *)flag_tab;
+    sy.counter = (unsigned int *)counter;
+    sy.wait_slot = wait_slot;
+    sy.signal_slot = signal_slot;
+    sy.nranks = nranks;
+    sy.my_rank = my_rank;
+    sy.seq = seq;
+    sy.timeout_cycles = (long long)((timeout_s > 0 ? timeout_s : 20.0) * 1.9e9);
     const float4 *const *rt = (const float4 *const *)rec_tab;
     float4 *const *stb = (float4 *const *)sum_tab;
     SGR_LAUNCH(K_PEER_REDUCE, st,
-               if (nranks <= 2) peer_reduce_kernel<2><<<(unsigned)blocks, T, 0, st>>>(rt, stb, nranks, q0, q1);
-               else if (nranks <= 4) peer_reduce_kernel<4><<<(unsigned)blocks, T, 0, st>>>(rt, stb, nranks, q0, q1);
-               else if (nranks <= 8) peer_reduce_kernel<8><<<(unsigned)blocks, T, 0, st>>>(rt, stb, nranks, q0, q1);
-               else peer_reduce_generic_kernel<<<(unsigned)blocks, T, 0, st>>>(rt, stb, nranks, q0, q1));
+               if (nranks <= 2) peer_reduce_kernel<2><<<(unsigned)blocks, T, 0, st>>>(rt, stb, nranks, q0, q1, sy);
+               else if (nranks <= 4) peer_reduce_kernel<4><<<(unsigned)blocks, T, 0, st>>>(rt, stb, nranks, q0, q1, sy);
+               else if (nranks <= 8) peer_reduce_kernel<8><<<(unsigned)blocks, T, 0, st>>>(rt, stb, nranks, q0, q1, sy);
+               else peer_reduce_generic_kernel<<<(unsigned)blocks, T, 0, st>>>(rt, stb, nranks, q0, q1, sy));
     SGR_CUDA(cudaGetLastError());
     return SGR_OK;
+}
+
+int sgr_peer_reduce_records(const void *const *rec_tab, void *const *sum_tab, int32_t nranks, int32_t my_rank, int32_t p0,
+                            int32_t p1, void *stream)
+{
+    return sgr_peer_reduce_records_synced(rec_tab, sum_tab, nranks, my_rank, p0, p1, nullptr, 0, nullptr, 0, 0, nullptr, 0.0,
+                                          stream);
 }
 
 }  // extern "C"

@@ -79,6 +79,14 @@ def reduce_grad(t: torch.Tensor, scale: float = 1.0, group=None) -> torch.Tensor
 
 
 _SLOT_BLEND, _SLOT_CHUNK0, _SLOT_REDUCED0, _PEER_MAX_CHUNKS = 0, 1, 17, 16   # flag slots (csrc/sgr_peer.cu)
+PEER_AUTO_WORLDS = (2,)   # measured: 2 GPUs 2.96 ms / step (e2e 661 views/s) vs 3.00 (630) over NCCL; see profiles/r02_scaling.md
+
+
+def _peer_auto_worlds():
+    e = os.environ.get("SGR_PEER_WORLDS")
+    return tuple(int(x) for x in e.split(",") if x.strip()) if e else PEER_AUTO_WORLDS
+
+
 _PEER_SERIAL = os.environ.get("SGR_PEER_SERIAL", "0") == "1"                 # diagnostics (scripts/timeline_peer.py)
 _PEER_LOCAL_FACTORS = os.environ.get("SGR_PEER_LOCAL_FACTORS", "0") == "1"
 
@@ -94,12 +102,14 @@ class _PeerState:
     """One rank's peer-visible exchange buffer for P Gaussians and the mappings of the other ranks' buffers
     (layout: csrc/sgr_peer.cu).  Building it is collective (the IPC handles travel in one all-gather)."""
 
-    def __init__(self, lib, check, P, rank, world, group, dev):
+    def __init__(self, lib, check, P, rank, world, group, dev, nstage=None):
         self.P, self.rank, self.world, self.dev, self.seq = P, rank, world, dev, 0
+        nstage = nstage or world
         up = lambda n: (n + 255) // 256 * 256
         fl, fb, rb = int(lib.sgr_peer_flag_bytes()), up(4 * (3 * P + 4)), up(4 * 11 * P + 64)
-        off = {"flags": 0, "F0": fl, "F1": fl + fb, "R": fl + 2 * fb, "S": fl + 2 * fb + rb}
-        total = fl + 2 * fb + 2 * rb
+        off = {"flags": 0, "F0": fl, "F1": fl + fb, "S": fl + 2 * fb, "STAGE": fl + 2 * fb + rb}
+        self.off, self.stage_stride = off, rb
+        total = off["STAGE"] + nstage * rb
         self.imported = []
         with torch.cuda.device(dev):
             base = C.c_void_p()
@@ -123,19 +133,28 @@ class _PeerState:
                     check(lib.sgr_peer_import(h, C.byref(q)))
                     self.imported.append(q.value)
                     bases.append(q.value)
-            tab = lambda name: torch.tensor([b + off[name] for b in bases], dtype=torch.int64, device=dev)
-            self.flag_tab, self.R_tab, self.S_tab = tab("flags"), tab("R"), tab("S")
+            i64 = lambda ptrs: torch.tensor(ptrs, dtype=torch.int64, device=dev)
+            tab = lambda name: i64([b + off[name] for b in bases])
+            self.flag_tab, self.S_tab = tab("flags"), tab("S")
             self.F_tab = [tab("F0"), tab("F1")]
             if _PEER_LOCAL_FACTORS:   # diagnostic (WRONG gradients): every "peer" factor block is this rank's own
-                self.F_tab = [torch.tensor([self.base + off[k]] * world, dtype=torch.int64, device=dev) for k in ("F0", "F1")]
-            self.flags_ptr, self.R_ptr, self.S_ptr = self.base, self.base + off["R"], self.base + off["S"]
+                self.F_tab = [i64([self.base + off[k]] * world) for k in ("F0", "F1")]
+            # records: rank j's staging array number `rank` receives what this rank's per-Gaussian pass computes for the
+            # blocks j owns; this rank's own arrays 0 .. world-1 receive every rank's records of the blocks IT owns
+            self.stage_tab = i64([b + off["STAGE"] + rank * rb for b in bases])
+            self.rec_tab = i64([self.base + off["STAGE"] + j * rb for j in range(nstage)])
+            self.flags_ptr, self.S_ptr = self.base, self.base + off["S"]
+            self.counters_ptr = self.base + 63 * 64 * 4   # flag row 63: the fused kernels' CTA counters (local use only)
+            self.R_ptr = self.base + off["STAGE"] + rank * rb
             self.F_local = [torch.as_tensor(_DevMem(self.base + off[k], 3 * P + 4), device=dev) for k in ("F0", "F1")]
             torch.cuda.synchronize(dev)
         self._streams = None
 
     def streams(self, dev):
+        """(side stream of the record exchange, stream of the backward's own signal kernels, start event)"""
         if self._streams is None:
-            self._streams = (torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Event())
+            self._streams = (torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev, priority=-1),
+                             torch.cuda.Event())
         return self._streams
 
     def close(self, lib):
@@ -160,7 +179,7 @@ class ViewParallel:
     """
 
     def __init__(self, sh_factors: bool = True, chunks: int = 4, scale: float = 1.0, group=None, force: bool = False,
-                 side_stream: bool = False, peer=False, peer_timeout_s: float = 20.0, taper: bool = True):
+                 side_stream: bool = False, peer="auto", peer_timeout_s: float = 8.0, taper: bool = True):
         from . import _C
         self.sh_factors, self.chunks, self.scale, self.group, self.force = bool(sh_factors), int(chunks), float(scale), group, force
         self.side_stream = bool(side_stream)
@@ -184,8 +203,15 @@ class ViewParallel:
         return self.force or _world(self.group) > 1
 
     def uses_peer_memory(self, M: int, has_cov_precomp: bool) -> bool:
-        """Peer mode serves the common case: SH colours exchanged as factors, covariances computed in the op."""
-        return bool(self.peer) and bool(M) and self.sh_factors and not has_cov_precomp and self.chunks <= _PEER_MAX_CHUNKS
+        """Peer mode serves the common case: SH colours exchanged as factors, covariances computed in the op.
+        peer=True: always (raises if the buffers cannot be mapped); False: never; "auto" (default): on the world sizes
+        it has been measured faster than the NCCL exchange on (PEER_AUTO_WORLDS; override: SGR_PEER_WORLDS="2,4,8"),
+        falling back to NCCL if the ranks cannot map each other's memory."""
+        if not self.peer or not M or not self.sh_factors or has_cov_precomp or self.chunks > _PEER_MAX_CHUNKS:
+            return False
+        if self.peer == "auto" and not self.force:
+            return _world(self.group) in _peer_auto_worlds()
+        return True
 
     # -- the exchange, driven from _C.rasterize_gaussians_backward ------------------------------------------
     def run_backward(self, lib, check, stage_hook_type, plan_type, args, bufs, P, M, degree, means3D, campos,
@@ -205,8 +231,10 @@ class ViewParallel:
         dev = means3D.device
         factor = bool(M) and self.sh_factors
         nchunks = max(1, self.chunks)
-        if getattr(self, "_ranges_key", None) != (P, nchunks, 0):
-            self._ranges_key, self._ranges = (P, nchunks, 0), [self._range(lib, check, P, nchunks, c) for c in range(nchunks)]
+        taper = 0   # equal chunks here: halving ones measured slower with NCCL (2 GPUs: 3.09 vs 3.00 ms per step)
+        if getattr(self, "_ranges_key", None) != (P, nchunks, taper):
+            self._ranges_key = (P, nchunks, taper)
+            self._ranges = [self._range(lib, check, P, nchunks, c, taper) for c in range(nchunks)]
         ranges = self._ranges
         pending = {c: [] for c in range(nchunks)}
         early = []
@@ -249,6 +277,7 @@ class ViewParallel:
 
         cb = stage_hook_type(on_stage)
         plan = plan_type(cb, None, nchunks, bufs["records"].data_ptr(), None)
+        plan.chunk_taper = taper
         check(lib.sgr_rasterize_backward_staged(*args, C.byref(plan)))
         if failure:
             raise failure[0]
@@ -292,7 +321,7 @@ class ViewParallel:
             rank = dist.get_rank(self.group) if world > 1 else 0
             st, err = None, None
             try:
-                st = _PeerState(lib, check, P, rank, world, self.group, dev)
+                st = _PeerState(lib, check, P, rank, world, self.group, dev, nstage=getattr(self, "_nstage", None))
             except Exception as e:  # no IPC / no peer access on this box: every rank must take the same branch
                 err = e
             if world > 1:
@@ -314,52 +343,36 @@ class ViewParallel:
         world, rank = st.world, st.rank
         nchunks = max(1, self.chunks)
         taper = int(self.taper)
-        if getattr(self, "_ranges_key", None) != (P, nchunks, taper):
-            self._ranges_key = (P, nchunks, taper)
-            self._ranges = [self._range(lib, check, P, nchunks, c, taper) for c in range(nchunks)]
-        ranges = [(c, r) for c, r in enumerate(self._ranges) if r[1] > r[0]]   # the chunks the op really launches
         st.seq += 1
         seq, par = st.seq, st.seq & 1
         main = torch.cuda.current_stream(dev)
-        B, ev = st.streams(dev)
+        B, Csig, ev = st.streams(dev)
         if _PEER_SERIAL:     # diagnostic: everything on the caller's stream (isolated kernel durations)
-            B = main
+            B, Csig = main, None
         F = st.F_local[par]
         F[3 * P:3 * P + 3].copy_(campos.reshape(3))     # the camera position rides behind the factors
-        ev.record(main)                                  # the side stream starts no earlier than this backward
         args = list(args)
         args[9] = F.data_ptr()       # dL_dcolors: the blend pass accumulates straight into the peer-visible factor block
         args[13] = bufs["sh"].data_ptr()                 # dL_dsh: written by the per-Gaussian pass, summed over ALL views
         # main stream, all inside the C call: blend -> signal(BLEND) -> wait(BLEND, every rank) -> per-Gaussian pass in
-        # chunks, which loads the other ranks' factors over NVLink and writes the summed dL_dsh and this rank's 44-byte
-        # records (into the peer-visible R) -> signal(CHUNK c) after each chunk
+        # chunks: TMA-loads the other ranks' factor blocks over NVLink, writes the summed dL_dsh, TMA-stores each CTA's
+        # 44-byte records into the staging array of the rank that owns them -> signal(CHUNK c) after each chunk
+        emulate = 0
+        for r in self._emulated:
+            emulate |= 1 << r
         plan = plan_type(stage_hook_type(0), None, nchunks, st.R_ptr, None, st.flag_tab.data_ptr(), world, rank,
                          _SLOT_BLEND, _SLOT_CHUNK0, seq, st.F_tab[par].data_ptr(), st.flags_ptr, self.scale,
-                         self.peer_timeout_s, taper)
+                         self.peer_timeout_s, taper, st.stage_tab.data_ptr(),
+                         Csig.cuda_stream if Csig is not None else None, B.cuda_stream, st.rec_tab.data_ptr(),
+                         st.S_tab.data_ptr(), st.S_ptr, _SLOT_REDUCED0, emulate)
+        # ... and on the side stream, also enqueued by the C call, chunk by chunk underneath the per-Gaussian pass of the
+        # later chunks: [wait(CHUNK c, every rank) -> sum the slice this rank owns over the staging arrays (local loads)
+        # -> store the sums into every rank's S (posted NVLink writes) -> signal(REDUCED c)] as ONE kernel, then behind
+        # the next chunk's reduce: wait(REDUCED c) -> split S into the four gradient arrays (x scale)
         check(lib.sgr_rasterize_backward_staged(*args, C.byref(plan)))
-        tmo, flags, mp = self.peer_timeout_s, st.flags_ptr, means3D.data_ptr()
-        # side stream: two-shot all-reduce of the records chunk by chunk, underneath the per-Gaussian pass of the later
-        # chunks; the split of chunk c-1 runs behind the reduce of chunk c, so the peers' slices of c-1 have landed by
-        # then and only the last chunk's reduce + split is exposed
-        B.wait_event(ev)
-
-        def split(c, p0, p1):
-            check(lib.sgr_peer_wait(flags, world, _SLOT_REDUCED0 + c, 1, seq, tmo, B.cuda_stream))
-            check(lib.sgr_view_grad_finalize_peers(P, p0, p1, M, degree, world, mp, None, None, st.S_ptr, self.scale,
-                                                   bufs["means3D"].data_ptr(), bufs["opacity"].data_ptr(),
-                                                   bufs["scales"].data_ptr(), bufs["rotations"].data_ptr(), B.cuda_stream))
-        prev = None
-        for c, (p0, p1) in ranges:
-            check(lib.sgr_peer_wait(flags, world, _SLOT_CHUNK0 + c, 1, seq, tmo, B.cuda_stream))
-            for r in (rank,) + tuple(self._emulated):
-                check(lib.sgr_peer_reduce_records(st.R_tab.data_ptr(), st.S_tab.data_ptr(), world, r, p0, p1, B.cuda_stream))
-            check(lib.sgr_peer_signal(st.flag_tab.data_ptr(), world, _SLOT_REDUCED0 + c, rank, seq, B.cuda_stream))
-            if prev is not None:
-                split(*prev)
-            prev = (c, p0, p1)
-        if prev is not None:
-            split(*prev)
         main.wait_stream(B)
+        if Csig is not None:
+            main.wait_stream(Csig)
         self.stats["backwards"] += 1
 
     def close(self):

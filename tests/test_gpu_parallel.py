@@ -186,19 +186,24 @@ def test_peer_exchange_with_three_emulated_ranks():
     want = {k: scale * sum(p[k] for p in plain) for k in names}
 
     vp = parallel.ViewParallel(chunks=3, scale=scale, force=True, peer=True)
+    vp._nstage = 3      # staging arrays for three source ranks in this (single) rank's buffer
     st = vp._peer_state(_lib.lib, _lib.check, P, torch.device("cuda", torch.cuda.current_device()))
-    # stand-ins for ranks 1 and 2: padded record / sum arrays and their (static) factor blocks
-    pad = lambda r: torch.cat([r.reshape(-1), torch.zeros(16, device="cuda")]).contiguous()
-    R_fake = [pad(records[1]), pad(records[2])]
+    # stand-ins for ranks 1 and 2: their records sit in this rank's staging arrays 1 and 2 (as if their per-Gaussian
+    # passes had stored them), their sum arrays are plain local tensors, their factor blocks are static
+    stage = lambda j: torch.as_tensor(parallel._DevMem(st.base + st.off["STAGE"] + j * st.stage_stride, 11 * P),
+                                      device="cuda")
+    stage(1).copy_(records[1].reshape(-1))
+    stage(2).copy_(records[2].reshape(-1))
     S_fake = [torch.zeros(11 * P + 16, device="cuda"), torch.zeros(11 * P + 16, device="cuda")]
     tab = lambda own, others: torch.tensor([int(own)] + [o.data_ptr() for o in others], dtype=torch.int64, device="cuda")
     st.world = 3
     st.F_tab = [tab(st.F_tab[0][0], factors[1:]), tab(st.F_tab[1][0], factors[1:])]
-    st.R_tab, st.S_tab = tab(st.R_tab[0], R_fake), tab(st.S_tab[0], S_fake)
+    st.S_tab = tab(st.S_tab[0], S_fake)
+    st.stage_tab = torch.tensor([st.R_ptr] * 3, dtype=torch.int64, device="cuda")   # every owner's array for OUR records = ours
     st.flag_tab = torch.tensor([st.base] * 3, dtype=torch.int64, device="cuda")   # "every rank's flags" = ours
     flags = torch.as_tensor(type("M", (), {"__cuda_array_interface__": {
         "shape": (64, 64), "typestr": "<i4", "data": (st.base, False), "version": 2}})(), device="cuda")
-    flags[:, 1:3] = 1 << 30     # ranks 1 and 2 have "already signalled" every slot of every step
+    flags[:63, 1:3] = 1 << 30   # ranks 1 and 2 have "already signalled" every slot of every step (row 63: CTA counters)
     vp._emulated = (1, 2)
     t0, sc0 = h.to_torch(views[0]), views[0]
     dL0 = torch.from_numpy(scenes.upstream_grad(W, H, seed=5)).cuda()
