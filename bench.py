@@ -6,7 +6,8 @@
 Metric (BASELINE.json): forward+backward views/sec @ 3M Gaussians, 1920x1080, SH degree 3,
 plus achieved HBM GB/s of the dominant kernel vs the measured peak.  One "step" = one view
 rendered forward and backward on each GPU (weak scaling: every rank renders its own view of the
-replicated cloud; for N>1 the per-Gaussian gradients are then summed with one NCCL all-reduce).
+replicated cloud; for N>1 the per-Gaussian gradients are summed over the ranks inside the op's backward,
+over peer memory or NCCL -- sugar_b200/parallel.py, --exchange).
 
 Prints ONE JSON line (rank 0).  Keys are documented in DESIGN.md section "Measurement".
   value        views/s, inputs resident in HBM, CUDA-event timed, max over ranks
