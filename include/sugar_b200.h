@@ -391,6 +391,9 @@ SGR_API int sgr_profile_enable(int on);
 SGR_API int sgr_profile_read(float *total_ms, int *counts);
 SGR_API int sgr_profile_timeline(int max_records, int *kinds, float *t_begin_ms, float *t_end_ms);
 
+/* sizeof of an ABI struct as the library was compiled (0 SgrView, 1 SgrGaussians, 2 SgrBackwardPlan, 3 SgrFieldParams;
+ * else 0): lets a foreign-language binding check its own struct layout. */
+SGR_API size_t sgr_struct_bytes(int32_t which);
 SGR_API const char *sgr_last_error(void);
 SGR_API const char *sgr_version(void);
 

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "sgr_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_knn": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                           C.c_void_p]),
+    "sgr_struct_bytes": (C.c_size_t, [C.c_int32]),
     "sgr_launch_count": (C.c_ulonglong, []),
     "sgr_num_kernel_kinds": (C.c_int, []),
     "sgr_kernel_name": (C.c_char_p, [C.c_int]),
@@ -124,6 +125,10 @@ def _load():
 
 
 lib = _load()
+for _i, _t in enumerate((SgrView, SgrGaussians, SgrBackwardPlan, SgrFieldParams)):
+    if lib.sgr_struct_bytes(_i) != C.sizeof(_t):   # a stale library or a binding edited without the header
+        raise SgrError(f"{LIB_PATH}: struct {_t.__name__} is {lib.sgr_struct_bytes(_i)} bytes in the library, "
+                       f"{C.sizeof(_t)} in this binding -- rebuild with `python sugar_b200/build.py`")
 
 
 def check(status: int) -> None:

@@ -204,6 +204,18 @@ const char *sgr_last_error(void) { return g_err; }
 
 unsigned long long sgr_launch_count(void) { return g_launches; }
 int sgr_num_kernel_kinds(void) { return K_NUM_KINDS; }
+
+// sizes of the ABI structs as this library was compiled: a binding checks its own layout against them
+size_t sgr_struct_bytes(int32_t which)
+{
+    switch (which) {
+        case 0: return sizeof(SgrView);
+        case 1: return sizeof(SgrGaussians);
+        case 2: return sizeof(SgrBackwardPlan);
+        case 3: return sizeof(SgrFieldParams);
+        default: return 0;
+    }
+}
 const char *sgr_kernel_name(int kind) { return (kind >= 0 && kind < K_NUM_KINDS) ? g_kind_names[kind] : "?"; }
 
 int sgr_profile_enable(int on)

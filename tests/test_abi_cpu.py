@@ -92,3 +92,57 @@ def test_new_entry_points_validate_arguments_without_gpu():
         assert seen == P and prev == P
     assert L.sgr_backward_chunk_range(10, 2, 2, ctypes.byref(p0), ctypes.byref(p1)) == -1
     assert L.sgr_view_grad_finalize(10, 0, 10, 16, 3, 1, None, None, None, 30, 3, None, None, 1.0, *([None] * 5)) == -1
+
+
+def test_struct_layouts_match_the_library():
+    """The ctypes structs of the binding have the sizes the library was compiled with (sgr_struct_bytes)."""
+    from sugar_b200 import _lib
+    for i, t in enumerate((_lib.SgrView, _lib.SgrGaussians, _lib.SgrBackwardPlan, _lib.SgrFieldParams)):
+        assert _lib.lib.sgr_struct_bytes(i) == ctypes.sizeof(t), t.__name__
+    assert _lib.lib.sgr_struct_bytes(99) == 0
+
+
+def test_tapered_chunk_ranges_cover_and_halve():
+    """SgrBackwardPlan.chunk_taper: contiguous cover of [0, P), boundaries on 64-Gaussian blocks, every chunk about half
+    of the one before it; taper 0 is the plain equal split."""
+    from sugar_b200 import _lib
+    L = _lib.lib
+    p0, p1 = ctypes.c_int32(), ctypes.c_int32()
+    for P, n in ((3_000_000, 4), (6_000_000, 3), (6001, 3), (129, 3), (64, 4), (1000, 1), (257, 16)):
+        prev, sizes = 0, []
+        for c in range(n):
+            assert L.sgr_backward_chunk_range_tapered(P, n, c, 1, ctypes.byref(p0), ctypes.byref(p1)) == 0
+            assert p0.value == min(prev, P) and p0.value <= p1.value <= P
+            assert p0.value % 64 == 0 or p0.value == P
+            prev = p1.value
+            sizes.append(p1.value - p0.value)
+        assert prev == P and sum(sizes) == P
+        if P >= 64 * 64 * n:
+            for a, b in zip(sizes, sizes[1:]):
+                assert 0.4 * a <= b <= 0.6 * a, sizes
+        for c in range(n):   # taper 0 == the untapered entry point
+            L.sgr_backward_chunk_range_tapered(P, n, c, 0, ctypes.byref(p0), ctypes.byref(p1))
+            q0, q1 = ctypes.c_int32(), ctypes.c_int32()
+            L.sgr_backward_chunk_range(P, n, c, ctypes.byref(q0), ctypes.byref(q1))
+            assert (p0.value, p1.value) == (q0.value, q1.value)
+
+
+def test_peer_entry_points_validate_before_touching_cuda():
+    from sugar_b200 import _lib
+    L = _lib.lib
+    assert L.sgr_peer_flag_bytes() == 64 * 64 * 4
+    assert L.sgr_peer_alloc(0, None) == -1 and b"sgr_peer_alloc" in L.sgr_last_error()
+    assert L.sgr_peer_export(None, None) == -1 and L.sgr_peer_import(None, None) == -1
+    assert L.sgr_peer_free(None) == 0 and L.sgr_peer_close(None) == 0          # nothing to do
+    assert L.sgr_peer_signal(None, 2, 0, 0, 1, None) == -1                     # no flag table
+    assert L.sgr_peer_wait(None, 2, 0, 1, 1, 1.0, None) == -1
+    dummy = ctypes.c_void_p(16)
+    assert L.sgr_peer_signal(dummy, 65, 0, 0, 1, None) == -1                   # more ranks than flag columns
+    assert L.sgr_peer_signal(dummy, 2, 64, 0, 1, None) == -1                   # slot out of range
+    assert L.sgr_peer_signal(dummy, 2, 0, 2, 1, None) == -1                    # rank out of range
+    assert L.sgr_peer_wait(dummy, 2, 60, 5, 1, 1.0, None) == -1                # slots run past the table
+    assert L.sgr_peer_reduce_records(None, None, 2, 0, 0, 64, None) == -1
+    assert L.sgr_peer_reduce_records(dummy, dummy, 2, 0, 32, 64, None) == -1   # p0 not on a 64-record block
+    assert L.sgr_peer_reduce_records_synced(dummy, dummy, 2, 0, 0, 64, None, 0, dummy, 3, 1, None, 1.0, None) == -1  # signal without counter
+    assert L.sgr_view_grad_finalize_peers(10, 0, 10, 16, 3, 1, None, None, dummy, None, 1.0, *([None] * 5)) == -1
+    assert b"sgr_view_grad_finalize_peers" in L.sgr_last_error()

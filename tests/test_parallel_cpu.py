@@ -105,3 +105,22 @@ def test_reduce_grad_single_process_is_identity_times_scale():
     parallel.reduce_grad(x, scale=0.25).sum().backward()
     assert torch.allclose(x.grad, torch.full((4,), 0.25))
     assert parallel.shard_views(5, 1, 2) == [1, 3]
+
+
+def test_exchange_policy_without_a_process_group(monkeypatch):
+    """ViewParallel.uses_peer_memory: "auto" follows PEER_AUTO_WORLDS / SGR_PEER_WORLDS, True / False force, and the cases
+    the peer exchange does not serve (no SH factors, precomputed covariances, > 16 chunks) go to NCCL."""
+    from sugar_b200 import parallel
+    assert parallel.PEER_AUTO_WORLDS == (2,)
+    vp = parallel.ViewParallel()                       # "auto", world size 1 here
+    assert vp.peer == "auto" and not vp.enabled()
+    assert not vp.uses_peer_memory(16, False)
+    monkeypatch.setenv("SGR_PEER_WORLDS", "1, 4")
+    assert vp.uses_peer_memory(16, False)
+    assert not vp.uses_peer_memory(16, True) and not vp.uses_peer_memory(0, False)
+    monkeypatch.delenv("SGR_PEER_WORLDS")
+    assert parallel.ViewParallel(peer=True).uses_peer_memory(16, False)
+    assert not parallel.ViewParallel(peer=False, force=True).uses_peer_memory(16, False)
+    assert parallel.ViewParallel(force=True).uses_peer_memory(16, False)          # forced single-rank runs (tests)
+    assert not parallel.ViewParallel(peer=True, sh_factors=False).uses_peer_memory(16, False)
+    assert not parallel.ViewParallel(peer=True, chunks=17).uses_peer_memory(16, False)
