@@ -126,18 +126,23 @@ class _Arena:
         self.block = _big_empty(_round_up(reserve_bytes, _ROUND), torch.uint8, device) if reserve_bytes else None
         self.used = 0
         self.parts = {}
+        self.error = None   # an exception raised inside a callback (e.g. torch OOM): re-raised after the C call returns
         self.cbs = {name: _lib.ALLOC_FN(lambda _ctx, n, name=name: self._alloc(name, n)) for name in ("geom", "binning", "img")}
 
     def _alloc(self, name, nbytes):
-        nbytes = int(nbytes)
-        if self.block is not None and self.used + nbytes + 256 <= self.block.numel():
-            off = _round_up(self.block.data_ptr() + self.used, 256) - self.block.data_ptr()
-            t = self.block[off:off + nbytes]
-            self.used = off + nbytes
-        else:  # no (or too small a) reservation: plain allocation, still rounded
-            t = _big_empty(_round_up(nbytes, _ROUND), torch.uint8, self.device)[:nbytes]
-        self.parts[name] = t
-        return t.data_ptr()
+        try:
+            nbytes = int(nbytes)
+            if self.block is not None and self.used + nbytes + 256 <= self.block.numel():
+                off = _round_up(self.block.data_ptr() + self.used, 256) - self.block.data_ptr()
+                t = self.block[off:off + nbytes]
+                self.used = off + nbytes
+            else:  # no (or too small a) reservation: plain allocation, still rounded
+                t = _big_empty(_round_up(nbytes, _ROUND), torch.uint8, self.device)[:nbytes]
+            self.parts[name] = t
+            return t.data_ptr()
+        except BaseException as e:  # never unwind through the C frame: NULL makes the library stop with an error status
+            self.error = e
+            return None
 
     def get(self, name):
         return self.parts.get(name, torch.empty(0, dtype=torch.uint8, device=self.device))
@@ -222,9 +227,14 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         g = _gauss_struct(P, M, means3D, opacity, sh, colors, scales, rotations, cov3D_precomp, sh_rest)
         rendered = C.c_int64(0)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        check(lib.sgr_rasterize_forward(C.byref(view), C.byref(g), arena.cbs["geom"], None, arena.cbs["binning"], None,
-                                        arena.cbs["img"], None, out_color.data_ptr(), radii.data_ptr() if P else None,
-                                        hint, C.byref(rendered), stream))
+        status = lib.sgr_rasterize_forward(C.byref(view), C.byref(g), arena.cbs["geom"], None, arena.cbs["binning"], None,
+                                           arena.cbs["img"], None, out_color.data_ptr(), radii.data_ptr() if P else None,
+                                           hint, C.byref(rendered), stream)
+        if arena.error is not None:   # the allocator callback failed (e.g. out of memory): its own exception, not
+            err = arena.error         # the library's generic "allocator returned NULL"
+            arena.release()
+            raise err
+        check(status)
         R = int(rendered.value)
         if P:
             # next view's optimistic capacity: 25% headroom, rounded to 1M instances (stable sizes)

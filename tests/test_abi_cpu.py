@@ -146,3 +146,12 @@ def test_peer_entry_points_validate_before_touching_cuda():
     assert L.sgr_peer_reduce_records_synced(dummy, dummy, 2, 0, 0, 64, None, 0, dummy, 3, 1, None, 1.0, None) == -1  # signal without counter
     assert L.sgr_view_grad_finalize_peers(10, 0, 10, 16, 3, 1, None, None, dummy, None, 1.0, *([None] * 5)) == -1
     assert b"sgr_view_grad_finalize_peers" in L.sgr_last_error()
+
+
+def test_allocator_callback_exception_is_kept_for_the_caller():
+    """_Arena._alloc never unwinds through the C frame: it records the exception and hands the library NULL."""
+    import torch
+    from sugar_b200 import _C
+    arena = _C._Arena(torch.device("cpu"), 0)
+    assert arena._alloc("geom", "not a size") is None and isinstance(arena.error, ValueError)
+    arena.release()
