@@ -584,7 +584,10 @@ def main():
             R = _C.rasterize_gaussians(bg, params["means3D"], torch.Tensor([]), params["opacities"], params["scales"],
                                        params["rotations"], 1.0, torch.Tensor([]), viewmatrix, projmatrix, sc.tanfovx,
                                        sc.tanfovy, H, W, params["shs"], D, campos, False, False)[0]
-        alg = algorithmic_bytes(P, V_vis, R, W, H, 16, D, sh_written=(world == 1 or args.no_sh_factors))
+        # the per-Gaussian pass writes dL_dsh itself on one GPU, with --no-sh-factors, and in the peer-memory exchange
+        # (there summed over all views); only the NCCL factor exchange leaves it to the epilogue
+        used_peer = bool((exchange_check or {}).get("peer_memory")) or (args.force_exchange and args.exchange != "nccl")
+        alg = algorithmic_bytes(P, V_vis, R, W, H, 16, D, sh_written=(world == 1 or args.no_sh_factors or used_peer))
         peak, peak_src = load_peaks()
         ncu = load_ncu_facts()
         sm_clock = (clk.get("sm_mhz") or 1965.0) * 1e6

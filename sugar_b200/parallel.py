@@ -9,21 +9,16 @@ batch's views.
         image, radii = rasterizer(means3D=..., shs=..., ...)      # the drop-in module, unchanged
         loss(image).backward()                    # gradients arrive already summed over the ranks
 
-What the backward does when an exchange is attached (sugar_b200/_C.py, include/sugar_b200.h):
-
-    blend pass ─► hook BLEND_DONE ─► per-Gaussian pass, chunk 0 ─► hook ─► chunk 1 ─► hook ─► ... ─► finalize
-                     │ all-gather of the SH factors                │ all-reduce of chunk 0's records
-                     └─ runs underneath the per-Gaussian pass       └─ runs underneath chunk 1 ...
+What the backward does when an exchange is attached (sugar_b200/_C.py, include/sugar_b200.h).  Common to both
+implementations:
 
   * SH factor mode (default): 192 of the 236 B/Gaussian of gradients are dL_dsh, and each view's dL_dsh is an
-    outer product  basis(dir_view)[M] x dL/dRGB[3]  (backward.cu:20-139).  The ranks all-gather the 12-byte
-    factors dL/dRGB (they are the blend pass's colour accumulators, final when it ends) plus their camera
-    positions, and every rank rebuilds the summed dL_dsh itself (sgr_view_grad_finalize); the per-Gaussian pass
-    does not even write its own dL_dsh.
+    outer product  basis(dir_view)[M] x dL/dRGB[3]  (backward.cu:20-139).  Only the 12-byte factors dL/dRGB (the
+    blend pass's colour accumulators, final when it ends) and the camera positions cross the wire; the summed
+    dL_dsh is rebuilt from them.
   * The other 11 floats (means3D 3, opacity 1, scales 3, rotations 4) are written by the per-Gaussian pass as
-    one 44-byte record per Gaussian, in `chunks` Gaussian ranges; each range is all-reduced as soon as it is
-    enqueued, so only the last range's collective is exposed.  The finalize kernel splits the reduced records
-    into the arrays autograd expects (and applies `scale`).
+    one 44-byte record per Gaussian, in `chunks` Gaussian ranges; each range is exchanged while the next one is
+    computed, so only the last range's exchange is exposed.
   * Because the sum happens on the rasterizer's OUTPUT gradients, anything in front of the op (exp / sigmoid /
     normalize / cat of SuGaR's raw parameters) just backpropagates the summed gradient: inputs need not be
     leaves, and several backwards per step (several views per rank) each do their own exchange.
@@ -32,6 +27,23 @@ What the backward does when an exchange is attached (sugar_b200/_C.py, include/s
   * Losses that reach the parameters without going through the rasterizer (density / SDF regularisation,
     evaluated per view on its rank) are summed with `reduce_grad(tensor)`: identity in the forward, all-reduce of
     the incoming gradient in the backward.
+
+Over peer memory (`peer=True`, or "auto" on PEER_AUTO_WORLDS; csrc/sgr_peer.cu): the ranks map
+each other's exchange buffers with CUDA IPC once; a backward is then ONE C call, no NCCL call, no host callback:
+
+    main   blend ─ signal ─ wait(all ranks) ─ per-Gaussian pass <MULTI> chunk 0 ─ chunk 1 ─ ...       (+ signals on a 3rd stream)
+                                               TMA-loads the other ranks' factor blocks (NVLink), writes the SUMMED dL_dsh,
+                                               TMA-stores its records into the staging array of the rank that owns them
+    side                                       [chunk 0 signalled] reduce owned slice, post sums to every rank ─ split ─ ...
+
+Over NCCL (`peer=False`, and wherever "auto" has not measured the peer exchange faster):
+
+    blend pass ─► hook BLEND_DONE ─► per-Gaussian pass, chunk 0 ─► hook ─► chunk 1 ─► hook ─► ... ─► finalize
+                     │ all-gather of the SH factors                │ all-reduce of chunk 0's records
+                     └─ runs underneath the per-Gaussian pass       └─ runs underneath chunk 1 ...
+
+    the per-Gaussian pass does not write dL_dsh; `sgr_view_grad_finalize` rebuilds the sum over the views from the
+    gathered factors and splits the reduced records into the arrays autograd expects (and applies `scale`).
 
 `GradArena` is the plain utility underneath the CPU tests and for callers that prefer one explicit all-reduce
 of leaf gradients after the backward (236 B/Gaussian, not overlapped).
@@ -174,8 +186,12 @@ class ViewParallel:
     chunks      Gaussian ranges of the per-Gaussian pass; each range's all-reduce overlaps the next range
     scale       multiplies every summed gradient (1/num_views for a mean over the batch)
     force       run the record / finalize path even with a single rank (tests; no collectives are issued)
-    side_stream finalize range c on a second (high-priority) stream as soon as its collective is done, concurrently
-                with the per-Gaussian pass of the ranges behind it, instead of after the whole pass on the caller's stream
+    side_stream (NCCL exchange) finalize range c on a second (high-priority) stream as soon as its collective is done,
+                concurrently with the per-Gaussian pass of the ranges behind it, instead of after the whole pass
+    peer        "auto" (default): the peer-memory exchange on the world sizes it measured faster on (PEER_AUTO_WORLDS,
+                override SGR_PEER_WORLDS), NCCL elsewhere or if the ranks cannot map each other's memory; True / False
+    peer_timeout_s  a flag wait of the peer exchange traps after this long (a lost rank must not hang the others)
+    taper       peer exchange: chunk c+1 is half the size of chunk c (the exposed tail is the last chunk's reduce + split)
     """
 
     def __init__(self, sh_factors: bool = True, chunks: int = 4, scale: float = 1.0, group=None, force: bool = False,
