@@ -36,10 +36,13 @@ def main():
     scaling = torch.exp(torch.randn(P, 3, generator=g) * 0.5 - 4.0).to(dev)
     quats = torch.nn.functional.normalize(torch.randn(P, 4, generator=g), dim=-1).to(dev)
     strengths = torch.sigmoid(torch.randn(P, generator=g) * 2).to(dev)
-    # neighbours: K random nearby indices (a K-NN build is not part of this path); samples inside Gaussians
+    # neighbours as the trainer has them (sugar_model.py:1013-1030, coarse_sdf.py:631): the exact K-NN table of the
+    # cloud against itself (self is neighbour 0), looked up at the Gaussian each sample was drawn in -- the gather
+    # locality of the field kernels is the trainer's, not that of random "nearby" indices
+    from sugar_b200 import knn
+    _, knn_idx = knn.reset_neighbors(points, K)
     gi = torch.randint(0, P, (N,), generator=g).to(dev)
-    nbr = (gi[:, None] + torch.randint(-4096, 4096, (N, K), generator=g).to(dev)).clamp_(0, P - 1)
-    nbr[:, 0] = gi
+    nbr = knn_idx[gi].contiguous()
     x = points[gi] + fo.quaternion_apply(quats[gi], 1.5 * scaling[gi] * torch.randn(N, 3, generator=g).to(dev))
     leaves = [t.clone().requires_grad_(True) for t in (x, points, scaling, quats, strengths)]
     w = torch.randn(N, device=dev)
