@@ -124,3 +124,20 @@ def test_exchange_policy_without_a_process_group(monkeypatch):
     assert parallel.ViewParallel(force=True).uses_peer_memory(16, False)          # forced single-rank runs (tests)
     assert not parallel.ViewParallel(peer=True, sh_factors=False).uses_peer_memory(16, False)
     assert not parallel.ViewParallel(peer=True, chunks=17).uses_peer_memory(16, False)
+
+
+def test_record_ownership_of_producer_and_reducer_agree():
+    """Peer exchange: the per-Gaussian pass sends CTA b of a chunk's nb CTAs to rank  b * N // nb  (sgr_backward.cu,
+    PreBwdArgs::stage_tab); sgr_peer_reduce_records lets rank r sum the blocks [ceil(r nb / N), ceil((r + 1) nb / N))
+    (sgr_peer.cu).  Both are restated here: every block has exactly one owner and the two formulas name the same one."""
+    for N in (1, 2, 3, 4, 7, 8, 16, 64):
+        for nb in (1, 2, 3, 5, 8, 63, 64, 65, 1000, 11719, 46875):
+            owner = [b * N // nb for b in range(nb)]
+            seen = [0] * nb
+            for r in range(N):
+                bs, be = (nb * r + N - 1) // N, (nb * (r + 1) + N - 1) // N
+                assert 0 <= bs <= be <= nb
+                for b in range(bs, be):
+                    assert owner[b] == r, (N, nb, b)
+                    seen[b] += 1
+            assert all(s == 1 for s in seen), (N, nb)
