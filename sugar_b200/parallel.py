@@ -122,21 +122,38 @@ class _PeerState:
         off = {"flags": 0, "F0": fl, "F1": fl + fb, "S": fl + 2 * fb, "STAGE": fl + 2 * fb + rb}
         self.off, self.stage_stride = off, rb
         total = off["STAGE"] + nstage * rb
-        self.imported = []
+        self.imported, self.base, self.F_local = [], 0, []
+        try:
+            self._build(lib, check, P, rank, world, group, dev, nstage, off, rb, total)
+        except BaseException:
+            self.close(lib)   # nothing half-mapped or allocated is left behind
+            raise
+        self._streams = None
+
+    def _build(self, lib, check, P, rank, world, group, dev, nstage, off, rb, total):
         with torch.cuda.device(dev):
-            base = C.c_void_p()
-            check(lib.sgr_peer_alloc(total, C.byref(base)))
-            self.base = base.value
-            handle = (C.c_ubyte * 64)()
-            check(lib.sgr_peer_export(self.base, handle))
+            # A rank that cannot allocate / export still takes part in the handle all-gather (with an all-zero handle):
+            # every rank then fails the same way and the caller's agreement step falls back to NCCL on all of them.
+            handle, local_err = (C.c_ubyte * 64)(), None
+            try:
+                base = C.c_void_p()
+                check(lib.sgr_peer_alloc(total, C.byref(base)))
+                self.base = base.value
+                check(lib.sgr_peer_export(self.base, handle))
+            except Exception as e:
+                local_err, handle = e, (C.c_ubyte * 64)()
             bases = [self.base]
             if world > 1:
                 mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
                 every = torch.empty((world, 64), dtype=torch.uint8, device=dev)
                 dist.all_gather_into_tensor(every, mine, group=group)
                 every = every.cpu()
+                if local_err is None and not bool(every.any(dim=1).all()):
+                    local_err = RuntimeError("a peer rank could not allocate / export its exchange buffer")
                 bases = []
                 for j in range(world):
+                    if local_err is not None:
+                        break
                     if j == rank:
                         bases.append(self.base)
                         continue
@@ -145,6 +162,8 @@ class _PeerState:
                     check(lib.sgr_peer_import(h, C.byref(q)))
                     self.imported.append(q.value)
                     bases.append(q.value)
+            if local_err is not None:
+                raise local_err
             i64 = lambda ptrs: torch.tensor(ptrs, dtype=torch.int64, device=dev)
             tab = lambda name: i64([b + off[name] for b in bases])
             self.flag_tab, self.S_tab = tab("flags"), tab("S")
@@ -160,7 +179,6 @@ class _PeerState:
             self.R_ptr = self.base + off["STAGE"] + rank * rb
             self.F_local = [torch.as_tensor(_DevMem(self.base + off[k], 3 * P + 4), device=dev) for k in ("F0", "F1")]
             torch.cuda.synchronize(dev)
-        self._streams = None
 
     def streams(self, dev):
         """(side stream of the record exchange, stream of the backward's own signal kernels, start event)"""
