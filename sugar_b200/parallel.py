@@ -145,9 +145,9 @@ class _PeerState:
             bases = [self.base]
             if world > 1:
                 mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
-                every = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+                every = torch.empty(world * 64, dtype=torch.uint8, device=dev)   # flat: the form every backend takes
                 dist.all_gather_into_tensor(every, mine, group=group)
-                every = every.cpu()
+                every = every.view(world, 64).cpu()
                 if local_err is None and not bool(every.any(dim=1).all()):
                     local_err = RuntimeError("a peer rank could not allocate / export its exchange buffer")
                 bases = []

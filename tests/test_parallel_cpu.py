@@ -141,3 +141,119 @@ def test_record_ownership_of_producer_and_reducer_agree():
                     assert owner[b] == r, (N, nb, b)
                     seen[b] += 1
             assert all(s == 1 for s in seen), (N, nb)
+
+
+def _peer_setup_worker(rank, world, port, q, fail_rank):
+    """Set-up of the peer-memory exchange (parallel._PeerState / ViewParallel._peer_state) over gloo with a stand-in for
+    the five sgr_peer_* entry points: addresses are just numbers, nothing touches CUDA."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import contextlib
+    from sugar_b200 import parallel
+
+    class FakeLib:
+        def __init__(self):
+            self.log = []
+
+        def sgr_peer_flag_bytes(self):
+            return 16384
+
+        def sgr_peer_alloc(self, nbytes, out):
+            if rank == fail_rank:
+                return -1
+            self.log.append(("alloc", int(nbytes)))
+            out._obj.value = 0x100000000 * (rank + 1)
+            return 0
+
+        def sgr_peer_export(self, ptr, handle):
+            handle[0], handle[1] = rank + 1, 0xAB          # "IPC handle": who owns the allocation
+            return 0
+
+        def sgr_peer_import(self, handle, out):
+            self.log.append(("import", int(handle[0])))
+            out._obj.value = 0x100000000 * int(handle[0]) + 0x1000   # the owner's buffer as mapped HERE
+            return 0
+
+        def sgr_peer_close(self, ptr):
+            self.log.append(("close", int(ptr)))
+            return 0
+
+        def sgr_peer_free(self, ptr):
+            self.log.append(("free", int(ptr)))
+            return 0
+
+    def check(status):
+        if status:
+            raise RuntimeError("stand-in library error")
+
+    fake, dev, P = FakeLib(), torch.device("cpu"), 1000
+    real = (parallel.torch.cuda.device, parallel.torch.cuda.synchronize, parallel.torch.as_tensor)
+    parallel.torch.cuda.device = lambda d: contextlib.nullcontext()
+    parallel.torch.cuda.synchronize = lambda d=None: None
+    parallel.torch.as_tensor = lambda obj, device=None: torch.zeros(obj.__cuda_array_interface__["shape"])
+    try:
+        vp = parallel.ViewParallel(peer="auto")
+        st = vp._peer_state(fake, check, P, dev)
+    finally:
+        parallel.torch.cuda.device, parallel.torch.cuda.synchronize, parallel.torch.as_tensor = real
+    out = {"rank": rank, "ok": st is not None, "peer": vp.peer, "error": vp.peer_error, "log": fake.log}
+    if st is not None:
+        out.update(flag_tab=st.flag_tab.tolist(), stage_tab=st.stage_tab.tolist(), rec_tab=st.rec_tab.tolist(),
+                   S_tab=st.S_tab.tolist(), F_tab=[t.tolist() for t in st.F_tab], R_ptr=st.R_ptr, base=st.base,
+                   off=dict(st.off), stride=st.stage_stride, imported=list(st.imported))
+    q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.close()
+    q.join_thread()
+
+
+def _run_peer_setup(fail_rank):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [ctx.Process(target=_peer_setup_worker, args=(r, world, port, q, fail_rank)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda r: r["rank"])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+def test_peer_state_setup_gloo_world2():
+    """Both ranks map each other's buffer: the pointer tables name rank j's regions as seen from each rank."""
+    res = _run_peer_setup(fail_rank=-1)
+    for me, r in enumerate(res):
+        other = 1 - me
+        assert r["ok"] and r["peer"] == "auto" and r["error"] is None
+        own, mapped = 0x100000000 * (me + 1), 0x100000000 * (other + 1) + 0x1000
+        bases = [own, mapped] if me == 0 else [mapped, own]
+        assert r["base"] == own and r["imported"] == [mapped] and ("import", other + 1) in r["log"]
+        assert r["flag_tab"] == bases
+        off, rb = r["off"], r["stride"]
+        assert r["S_tab"] == [b + off["S"] for b in bases]
+        assert r["F_tab"] == [[b + off["F0"] for b in bases], [b + off["F1"] for b in bases]]
+        # rank j's staging array number `me` receives my records; my own arrays 0..1 are what my reduce reads
+        assert r["stage_tab"] == [b + off["STAGE"] + me * rb for b in bases]
+        assert r["rec_tab"] == [own + off["STAGE"] + j * rb for j in range(2)]
+        assert r["R_ptr"] == r["rec_tab"][me] == r["stage_tab"][me]
+        assert off["F0"] % 256 == 0 and off["S"] % 256 == 0 and off["STAGE"] % 256 == 0 and rb % 256 == 0
+        assert r["log"][0][0] == "alloc" and r["log"][0][1] == off["STAGE"] + 2 * rb
+
+
+def test_peer_state_setup_falls_back_on_every_rank_when_one_cannot_allocate():
+    """Rank 1 cannot allocate: it still joins the handle all-gather, rank 0 sees the zero handle, frees its own buffer
+    without mapping anything, and BOTH fall back to the NCCL exchange (no rank is left waiting in a collective)."""
+    res = _run_peer_setup(fail_rank=1)
+    for r in res:
+        assert not r["ok"] and r["peer"] is False and r["error"]
+    assert ("free", 0x100000000) in res[0]["log"] and not any(c[0] == "import" for c in res[0]["log"])
+    assert res[1]["log"] == []
