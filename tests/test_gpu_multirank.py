@@ -1,0 +1,33 @@
+"""Two real ranks on one box (only where at least two GPUs are visible; the single-GPU box skips it): every rank renders
+its own view and the gradients summed inside the backward -- over peer memory and over NCCL, SH factors on and off,
+1 / 4 / 7 chunks -- must equal the locally computed gradients summed with dist.all_reduce.  Runs
+scripts/check_view_parallel.py under torchrun, exactly as the multi-GPU sessions behind profiles/r02_scaling.md did."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exchange_inside_the_backward_matches_a_plain_allreduce_on_two_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "scripts", "check_view_parallel.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["world"] == 2 and len(res["max_rel_err"]) == 9
+    assert any("peer=True" in k for k in res["max_rel_err"])          # the peer-memory exchange really ran
+    for k, v in res["max_rel_err"].items():
+        assert v <= 1e-4, (k, v)
