@@ -24,11 +24,14 @@ dist.init_process_group("nccl", device_id=dev)
 from sugar_b200 import diff_gaussian_rasterization as mod, parallel
 scenes = bench.load_scenes()
 res = {}
-for factors, peer in ((True, True), (True, False), (False, False)):
+os.environ.setdefault("SGR_PEER_WORLDS", str(world))   # "auto" = peer memory at this world size, NCCL if it cannot be mapped
+fallback = None
+for factors, peer in ((True, "auto"), (True, False), (False, False)):
     for chunks in (1, 4, 7):
         r = bench.verify_exchange(torch, dist, mod, parallel, scenes, dev, rank, world, 3, sh_factors=factors, chunks=chunks,
                                   peer=peer)
         res[f"factors={factors},peer={r['peer_memory']},chunks={chunks}"] = r["max_rel_err"]
+        fallback = fallback or r.get("peer_fallback_reason")
 if rank == 0:
-    print(json.dumps({"world": world, "max_rel_err": res}))
+    print(json.dumps({"world": world, "max_rel_err": res, "peer_fallback_reason": fallback}))
 dist.destroy_process_group()
