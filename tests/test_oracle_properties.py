@@ -80,3 +80,54 @@ def test_linear_properties_checker_on_the_oracle():
                                                             "dL_dscales", "dL_drotations")}
         return fw["color"], fw["radii"], grads
     h.check_linear_properties(run, sc.width, sc.height, tol_img=1e-6, tol_grad=2e-5)
+
+
+def _sh_basis(d, deg):
+    """Real SH basis values in the reference's order and sign convention (forward.cu:20-71 / backward.cu:20-139)."""
+    C0, C1 = 0.28209479177387814, 0.4886025119029199
+    C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+    C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435)
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    b = np.zeros((d.shape[0], 16))
+    b[:, 0] = C0
+    if deg > 0:
+        b[:, 1], b[:, 2], b[:, 3] = -C1 * y, C1 * z, -C1 * x
+    if deg > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        b[:, 4], b[:, 5], b[:, 6] = C2[0] * xy, C2[1] * yz, C2[2] * (2 * zz - xx - yy)
+        b[:, 7], b[:, 8] = C2[3] * xz, C2[4] * (xx - yy)
+    if deg > 2:
+        b[:, 9], b[:, 10] = C3[0] * y * (3 * xx - yy), C3[1] * xy * z
+        b[:, 11], b[:, 12] = C3[2] * y * (4 * zz - xx - yy), C3[3] * z * (2 * zz - 3 * xx - 3 * yy)
+        b[:, 13], b[:, 14] = C3[4] * x * (4 * zz - xx - yy), C3[5] * z * (xx - yy)
+        b[:, 15] = C3[6] * x * (xx - 3 * yy)
+    return b
+
+
+def test_a_views_sh_gradient_is_a_rank_one_product_of_its_colour_gradient():
+    """What the multi-GPU exchange rests on (sugar_b200/parallel.py): per view, dL_dsh[i] = basis(normalize(mean_i -
+    campos)) (x) (dL_dcolor_i masked where the forward clamped the colour) -- so 12 bytes per Gaussian and view describe
+    its 192 bytes of SH gradient, and the sum over views can be rebuilt from the views' factors.  Checked on the restated
+    reference backward (backward.cu:20-139) for two views and every SH degree."""
+    from sugar_b200 import scenes
+    P, W, H = 1200, 96, 64
+    base = scenes.make_scene(P, W, H, seed=11, camera="posed")
+    views = [base, scenes.with_camera_offset(base, 0.2, (0.3, -0.1, 0.2))]
+    for deg in (0, 1, 2, 3):
+        total, rebuilt = 0.0, 0.0
+        for v, sc in enumerate(views):
+            dL = scenes.upstream_grad(W, H, seed=3 + v)
+            fw, bw = h.run_oracle(sc, np.zeros(3, np.float32), dL, use_sh=True, sh_degree=deg)
+            vis = fw["radii"] > 0
+            factor = bw["dL_dcolors"].astype(np.float64) * (1.0 - fw["clamped"].astype(np.float64))
+            factor[~vis] = 0.0
+            d = sc.means3D.astype(np.float64) - np.asarray(sc.campos, np.float64).reshape(1, 3)
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            want = _sh_basis(d, deg)[:, :, None] * factor[:, None, :]
+            got = bw["dL_dsh"].astype(np.float64)
+            assert vis.sum() > 100
+            assert np.abs(got - want).max() <= 2e-6 * max(np.abs(want).max(), 1e-30), deg
+            assert np.all(got[:, (deg + 1) ** 2:] == 0.0)
+            total, rebuilt = total + got, rebuilt + want
+        assert np.abs(total - rebuilt).max() <= 2e-6 * np.abs(total).max()
